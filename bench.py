@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- fused encode -> fuse -> OOD-score windows/sec (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision fp32|bf16]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the path's CPU implementation on the host cores
+
+One step = one pass of the hot path over one batch (per GPU) of the configs[1] workload:
+B IMU windows (B,6,250) fp32 + the video trunk's feature maps (B*16,512,4,4) bf16 ->
+IMU encoder + classifier head + arg-max/MSP/energy/Mahalanobis (one launch), video tail
+(pool + projection), both projection heads, L2 normalisation, B x B similarity with the fused
+sigmoid contrastive loss.  Weak scaling: every rank owns its own batch, no data-path collective.
+
+Timing: W warm-up steps, K timed steps bracketed by barrier + synchronize, CUDA events on the
+launching stream, max over ranks.  Inputs rotate over enough distinct batches that the set exceeds
+the 126 MB L2 ("inputs_larger_than_L2").  One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fused encode->fuse->OOD-score windows/sec"
+UNIT = "windows/s"
+FRAMES, FEAT_C, FEAT_HW, WINDOW = 16, 512, 4, 250
+# algorithmic work per window (dead channels 1-5 never counted)
+FLOP_IMU = 25_890_816           # patch embed + 4 encoder layers (16 tokens) + classifier head
+BYTES_VIDEO = FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2 + 768 * 4     # bf16 fmap in + pooled-projected feature out
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=256, help="windows per GPU per step (configs[1]: 256)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- model construction
+def build_modules(device, seed=0):
+    """Random-init weights of the reference architecture (no checkpoints exist offline); BatchNorm
+    running statistics / affine terms are randomised so BN folding is exercised."""
+    import torch
+    import crossmodal_imu_video_ood_har_b200 as cm
+    torch.manual_seed(seed)
+    cfg = cm.default_config()
+    clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg)
+    xm = cm.CrossModalModel(cfg)
+    xm.imu_encoder.load_state_dict(clf.imu_encoder.state_dict())
+    g = torch.Generator().manual_seed(seed + 1)
+    for mod in list(clf.modules()) + list(xm.modules()):
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g))
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) * 1.5 + 0.5)
+            mod.weight.data.copy_(torch.randn(mod.num_features, generator=g))
+            mod.bias.data.copy_(torch.randn(mod.num_features, generator=g))
+    return cfg, clf.to(device).eval(), xm.to(device).eval()
+
+
+def synth_inputs(device, batch, n_sets, rank):
+    import torch
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    sets = []
+    for _ in range(n_sets):
+        imu = torch.randn(batch, 6, WINDOW, device=device, generator=g)
+        fmap = torch.relu(torch.randn(batch * FRAMES, FEAT_C, FEAT_HW, FEAT_HW, device=device, generator=g)).to(torch.bfloat16)
+        sets.append((imu, fmap))
+    return sets
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------- CPU baseline / reference arm
+def cpu_workload(clf, xm, batch, budget_s=15.0, min_iters=3):
+    """The oracle port (oracle/oracle.py = CPU restatement of the reference modules, torch CPU ops,
+    all host threads) on the same workload: one sample = one full batch of `batch` windows.
+    Returns (windows_per_s, cores, n_iters)."""
+    import numpy as np
+    import torch
+    from oracle import ood_spec, oracle, weights as W
+    sd_c = {k: v.detach().cpu().numpy() for k, v in clf.state_dict().items()}
+    sd_x = {k: v.detach().cpu().numpy() for k, v in xm.state_dict().items()}
+    dims = W.Dims()
+    rs = np.random.RandomState(99)
+    imu = rs.standard_normal((batch, 6, WINDOW)).astype(np.float32)
+    fmap = np.maximum(rs.standard_normal((batch * FRAMES, FEAT_C, FEAT_HW, FEAT_HW)), 0).astype(np.float32)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    feats, labels = W.class_features(1, 4096)
+    fit = ood_spec.mahalanobis_fit(feats, labels, 32)
+    whiten, mw = torch.from_numpy(fit["whiten"]).float(), torch.from_numpy(fit["mean_whitened"]).float()
+
+    def one():
+        with torch.no_grad():
+            logits, cls = oracle.imu_classifier(imu, sd_c, dims)
+            oracle.predict(logits)
+            z = logits - logits.max(1, keepdim=True)[0]
+            (-1.0 / z.exp().sum(1)); (-torch.logsumexp(logits, 1))
+            y = cls @ whiten
+            ((y[:, None, :] - mw[None]) ** 2).sum(-1).min(1)
+            vf = oracle.video_tail(fmap, sd_x, FRAMES)
+            ip = oracle.l2_normalize(oracle.projection_head(cls, sd_x, "imu_proj."))
+            vp = oracle.l2_normalize(oracle.projection_head(vf, sd_x, "video_proj."))
+            oracle.sigmoid_contrastive_loss(ip, vp)
+    for _ in range(2):
+        one()
+    t0, iters = time.perf_counter(), 0
+    while iters < min_iters or (time.perf_counter() - t0 < budget_s and iters < 2000):
+        one()
+        iters += 1
+    dt = time.perf_counter() - t0
+    return batch * iters / dt, cores, iters
+
+
+def run_reference(args):
+    """--impl reference: the path's CPU implementation on the box's host cores.  The reference is
+    pure Python/PyTorch and cannot travel to the GPU box, so this is the oracle port (kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cfg, clf, xm = build_modules("cpu")
+    # K timed steps, each one bounded sample (one batch) of the workload
+    import numpy as np
+    from oracle import weights as W  # noqa
+    per = []
+    wps, cores, _ = cpu_workload(clf, xm, args.batch, budget_s=0.0, min_iters=max(1, args.warmup))
+    t0 = time.perf_counter()
+    wps, cores, iters = cpu_workload(clf, xm, args.batch, budget_s=0.0, min_iters=max(1, min(args.steps, 50)))
+    ms = args.batch / wps * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": wps, "unit": UNIT, "n_gpus": args.gpus, "steps": iters,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"configs[1] cross-modal batch {args.batch}: IMU (B,6,250) fp32 + trunk feature maps (B*16,512,4,4) -> encoder+head+MSP/energy/Mahalanobis, video tail, projection heads, similarity + sigmoid loss",
+                       "batch_per_gpu": args.batch},
+            "cpu_baseline": {"value": wps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{iters} batches of {args.batch} windows (oracle/oracle.py on torch CPU ops, {torch.get_num_threads()} threads)"},
+            "e2e": {"value": wps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    import crossmodal_imu_video_ood_har_b200 as cm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    cfg, clf, xm = build_modules(dev)
+    precision = args.precision
+    if precision == "auto":
+        try:
+            clf.forward_scores(torch.zeros(8, 6, WINDOW, device=dev), precision="bf16")
+            precision = "bf16"
+        except RuntimeError:
+            precision = "fp32"
+    B = args.batch
+    # Mahalanobis state: fitted (untimed) on this rank's shard of synthetic ID features, all-reduced
+    fit_x = torch.randn(4096, 6, WINDOW, device=dev, generator=torch.Generator(device=dev).manual_seed(77 + rank))
+    fit_y = torch.randint(0, 32, (4096,), device=dev, generator=torch.Generator(device=dev).manual_seed(78 + rank))
+    maha = cm.MahalanobisOOD(32, dev, ridge=1e-3)
+    maha.accumulate(clf.forward_scores(fit_x, precision=precision, want_cls=True)["cls"], fit_y)
+    maha.finalize()
+    pipe = cm.CrossModalOODPipeline(clf, xm, maha, frames=FRAMES, precision=precision)
+
+    bytes_per_set = B * (6 * WINDOW * 4 + FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2)
+    n_sets = max(2, -(-300_000_000 // bytes_per_set))           # rotate over > 2x L2 worth of inputs
+    n_sets = min(n_sets, 64)
+    sets = synth_inputs(dev, B, n_sets, rank)
+    l0 = cm._native.launch_count()
+    graphs = [pipe.capture(imu, fmap) for imu, fmap in sets]
+    launches_per_step = (cm._native.launch_count() - l0) // (2 * n_sets)     # warm-up + capture per set
+    stream = torch.cuda.current_stream(dev)
+
+    def run_steps(k, offset=0):
+        for i in range(k):
+            graphs[(offset + i) % n_sets][0].replay()
+
+    # ---- device-resident throughput
+    run_steps(max(args.warmup, 3))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    run_steps(args.steps, offset=args.warmup)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t)
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- dominant kernel alone (roofline): the fused IMU launch, timed with CUDA events
+    k_iters = max(20, min(args.steps, 200))
+    outs = [dict() for _ in range(n_sets)]
+    for i in range(n_sets):
+        clf.forward_scores(sets[i][0], precision=precision, want_cls=True, out=outs[i])
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for i in range(k_iters):
+        clf.forward_scores(sets[i % n_sets][0], precision=precision, want_cls=True, out=outs[i % n_sets])
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    imu_ms = e0.elapsed_time(e1) / k_iters
+    # ... and the video pooling kernel (the HBM-bound stage)
+    pooled = torch.empty(B, FEAT_C, device=dev)
+    N = cm._native
+    e0.record(stream)
+    for i in range(k_iters):
+        N.check(N.lib().cmhar_video_pool(sets[i % n_sets][1].data_ptr(), 1, B, FRAMES, FEAT_C, FEAT_HW * FEAT_HW, pooled.data_ptr(), N.stream_ptr(dev)))
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    pool_ms = e0.elapsed_time(e1) / k_iters
+    peaks = measured_peaks()
+    tf = FLOP_IMU * B / (imu_ms * 1e-3) / 1e12
+    gbs = (B * FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2 + B * FEAT_C * 4) / (pool_ms * 1e-3) / 1e9
+    roofline = {"kernel": f"imu_forward_{precision}_kernel", "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " burst (kernel timed alone)",
+                "launch_ms": imu_ms, "flop_per_window": FLOP_IMU}
+    roofline_video = {"kernel": "video_pool_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                      "frac": gbs / peaks["hbm_gbs"], "traffic": None, "launch_ms": pool_ms}
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the region
+    imu_host = sets[0][0].cpu().pin_memory()
+    fmap_host = sets[0][1].cpu().pin_memory()
+    e2e_steps = max(5, min(args.steps, 50))
+    for _ in range(3):
+        pipe.run_host(imu_host, fmap_host)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        pipe.run_host(imu_host, fmap_host)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(t) * 1e-3)
+    h2d, d2h = pipe.host_bytes_per_step(B, WINDOW, fmap_host)
+    # IMU-only end to end (the reference Evaluator.predict path: windows in, labels + scores out)
+    for _ in range(3):
+        pipe.run_host(imu_host, None)
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        pipe.run_host(imu_host, None)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    e2e_imu = B * e2e_steps / (e0.elapsed_time(e1) * 1e-3)
+
+    # ---- batch sweep of the fused IMU launch (information only; rank 0)
+    sweep = {}
+    if rank == 0 and not args.no_sweep:
+        for nb in (256, 4096, 65536):
+            xs = [torch.randn(nb, 6, WINDOW, device=dev) for _ in range(max(2, min(8, 200_000_000 // (nb * 6000))))]
+            so = [dict() for _ in xs]
+            for i, x in enumerate(xs):
+                clf.forward_scores(x, precision=precision, out=so[i])
+            reps = max(3, min(50, 2_000_000 // nb))
+            torch.cuda.synchronize(dev)
+            e0.record(stream)
+            for i in range(reps):
+                clf.forward_scores(xs[i % len(xs)], precision=precision, out=so[i % len(xs)])
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / reps
+            sweep[str(nb)] = {"windows_per_s": nb / (ms * 1e-3), "tflops": FLOP_IMU * nb / (ms * 1e-3) / 1e12}
+            del xs, so
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        wps, cores, iters = cpu_workload(clf, xm, B, budget_s=12.0)
+        cpu_baseline = {"value": wps, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{iters} batches of {B} windows of the same workload (oracle/oracle.py, torch CPU ops)"}
+    if world > 1:
+        dist.barrier(device_ids=[local])
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": precision, "data": "synthetic",
+                "config": {"workload": f"configs[1] cross-modal batch {B}/GPU: IMU (B,6,250) fp32 + trunk feature maps (B*16,512,4,4) bf16 -> IMU encoder+head+MSP/energy/Mahalanobis, video tail, projection heads, L2-norm, BxB similarity + sigmoid loss",
+                           "batch_per_gpu": B, "global_batch": B * world, "frames": FRAMES, "parallelism": f"dp{world} (windows sharded by rank, no collective)",
+                           "l2_policy": f"inputs_larger_than_L2: {n_sets} rotating input sets, {n_sets * bytes_per_set / 1e6:.0f} MB",
+                           "cuda_graph": True},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "imu_only_value": e2e_imu, "note": "pinned host buffers; fmap H2D (262 KB/clip) dominates"},
+                "gpu_launches": launches_per_step * args.steps,
+                "launches_per_step": launches_per_step,
+                "roofline": roofline, "roofline_video_tail": roofline_video,
+                "cpu_baseline": cpu_baseline, "imu_batch_sweep": sweep}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

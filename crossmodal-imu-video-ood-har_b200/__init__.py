@@ -1,0 +1,17 @@
+"""crossmodal-imu-video-ood-har_b200 -- B200-native (sm_100a) cross-modal IMU/video inference and
+OOD-scoring hot path, behind the reference's ``nn.Module`` / evaluator surface.
+
+Import name: ``crossmodal_imu_video_ood_har_b200`` (the hyphenated directory is not a valid
+Python identifier; ``crossmodal_imu_video_ood_har_b200/__init__.py`` at the repo root aliases it).
+"""
+from . import _native
+from .config import default_config
+from .models import (PatchEmbedding, IMUEncoder, VideoEncoder, ProjectionHead, CrossModalModel,
+                     IMUClassifier, set_default_precision, get_default_precision)
+from .losses import SigmoidContrastiveLoss, InfoNCELoss, similarity_native
+from .ood import (logit_scores, MahalanobisOOD, ScoreHistogram, auroc_fpr95, roc_from_histograms,
+                  finalize_mahalanobis)
+from .evaluator import Evaluator, classification_metrics, shard_bounds
+from .pipeline import CrossModalOODPipeline
+
+__version__ = "0.1.0"

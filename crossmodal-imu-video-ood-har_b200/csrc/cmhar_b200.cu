@@ -1,0 +1,12 @@
+// cmhar_b200.cu -- single translation unit of libcmhar_b200.so (unity build: kernels defined in
+// one file are launched from another without relocatable device code).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC cmhar_b200.cu
+#include "common.cuh"
+namespace cmhar { struct FwdArgs; }
+#include "pack.cu"
+#include "imu_encoder_fp32.cu"
+#include "imu_encoder_bf16.cu"
+#include "dense.cu"
+#include "similarity.cu"
+#include "ood.cu"
+#include "api.cu"

@@ -1,0 +1,137 @@
+// common.cuh -- shared host/device helpers for the cmhar_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/cmhar_b200.h"
+
+namespace cmhar {
+
+// ---- error reporting -----------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define CMHAR_CHECK_CUDA(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ::cmhar::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                               __FILE__, __LINE__);                                         \
+            return CMHAR_ERR_CUDA;                                                          \
+        }                                                                                   \
+    } while (0)
+
+#define CMHAR_REQUIRE(cond, ...)                                                            \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            ::cmhar::set_error(__VA_ARGS__);                                                \
+            return CMHAR_ERR_INVALID;                                                       \
+        }                                                                                   \
+    } while (0)
+
+#define CMHAR_LAUNCH_CHECK()                                                                \
+    do {                                                                                    \
+        ::cmhar::count_launch();                                                            \
+        CMHAR_CHECK_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+// ---- sizes fixed by the reference configuration -------------------------------------------
+constexpr int D = CMHAR_D_MODEL;      // 128
+constexpr int H = CMHAR_NHEAD;        // 8
+constexpr int HD = D / H;             // 16
+constexpr int FF = CMHAR_FFN;         // 512
+constexpr int P = CMHAR_PATCH;        // 16
+constexpr float LN_EPS = 1e-5f;
+constexpr float BN_EPS = 1e-5f;
+
+// ---- fp32 encoder blob layout (float offsets) ----------------------------------------------
+// [patch_wt (16,128)] [tok_bias (16,128)] [final ln w,b (2,128)] then per layer:
+// [w_in_t (128,384)] [b_in 384] [w_o_t (128,128)] [b_o 128] [w1_t (128,512)] [b1 512]
+// [w2_t (512,128)] [b2 128] [ln1 w,b 256] [ln2 w,b 256]
+struct EncLayout {
+    static constexpr size_t patch_wt = 0;
+    static constexpr size_t tok_bias = patch_wt + P * D;
+    static constexpr size_t final_ln = tok_bias + CMHAR_MAX_SEQ * D;
+    static constexpr size_t layers0 = final_ln + 2 * D;
+    static constexpr size_t l_w_in = 0;
+    static constexpr size_t l_b_in = l_w_in + D * 3 * D;
+    static constexpr size_t l_w_o = l_b_in + 3 * D;
+    static constexpr size_t l_b_o = l_w_o + D * D;
+    static constexpr size_t l_w1 = l_b_o + D;
+    static constexpr size_t l_b1 = l_w1 + D * FF;
+    static constexpr size_t l_w2 = l_b1 + FF;
+    static constexpr size_t l_b2 = l_w2 + FF * D;
+    static constexpr size_t l_ln1 = l_b2 + D;
+    static constexpr size_t l_ln2 = l_ln1 + 2 * D;
+    static constexpr size_t layer_floats = l_ln2 + 2 * D;
+    static constexpr size_t header_ints = 8;      // [magic, seq, layers, ...] stored as int32 in front
+    static constexpr size_t fp32_floats(int layers) { return layers0 + (size_t)layers * layer_floats; }
+};
+constexpr uint32_t ENC_MAGIC = 0x434d4831u;   // "CMH1"
+constexpr uint32_t HEAD_MAGIC = 0x434d4832u;
+constexpr uint32_t MAHA_MAGIC = 0x434d4833u;
+constexpr uint32_t LIN_MAGIC = 0x434d4834u;
+
+struct BlobHeader {          // 64 bytes in front of every blob
+    uint32_t magic;
+    int32_t a, b, c, d;      // meaning depends on the blob kind
+    int32_t has_bf16;
+    int32_t pad[10];
+};
+static_assert(sizeof(BlobHeader) == 64, "header must stay 64 bytes");
+
+// head blob (floats after header): w0_t (128,h1) b0 h1 | w1_t (h1,h2) b1 h2 | w2_t (h2,C) b2 C
+struct HeadLayout {
+    int h1, h2, C;
+    __host__ __device__ size_t w0() const { return 0; }
+    __host__ __device__ size_t b0() const { return w0() + (size_t)D * h1; }
+    __host__ __device__ size_t w1() const { return b0() + h1; }
+    __host__ __device__ size_t b1() const { return w1() + (size_t)h1 * h2; }
+    __host__ __device__ size_t w2() const { return b1() + h2; }
+    __host__ __device__ size_t b2() const { return w2() + (size_t)h2 * C; }
+    __host__ __device__ size_t total() const { return b2() + C; }
+};
+
+// maha blob (floats after header): whiten (128,128) row-major [k][j], mean_w (C,128), mnorm (C)
+// mnorm_c = ||mean_w_c||^2 or +inf for empty classes.
+struct MahaLayout {
+    int C;
+    __host__ __device__ size_t whiten() const { return 0; }
+    __host__ __device__ size_t mean_w() const { return (size_t)D * D; }
+    __host__ __device__ size_t valid() const { return mean_w() + (size_t)C * D; }
+    __host__ __device__ size_t total() const { return valid() + C; }
+};
+
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace cmhar

@@ -1,0 +1,203 @@
+// dense.cu -- fp32 dense layers (Linear with folded BatchNorm + optional ReLU), row L2
+// normalisation and the video-tail pooling reduction.
+//
+// Replaces reference src/models/models.py:213 (VideoEncoder.projection), :226-234
+// (ProjectionHead: Linear-BN-ReLU-Linear), :288-289 (F.normalize) and :210-215 (spatial average
+// pool + temporal mean; both are linear so pool-then-project == project-then-pool).
+#include "common.cuh"
+
+namespace cmhar {
+
+constexpr int LT_ROWS = 64, LT_COLS = 128, LT_K = 64, LT_LDA = LT_K + 4;
+
+// y (n,N) = act(x (n,K) @ Wt (K,N) + b);  K % 4 == 0, N % 4 == 0
+__global__ void __launch_bounds__(256) linear_fp32_kernel(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                          const float* __restrict__ X, long long n, int K, int N,
+                                                          int relu, float* __restrict__ Y) {
+    __shared__ __align__(16) float As[LT_ROWS * LT_LDA];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * LT_ROWS;
+    const int col = blockIdx.y * LT_COLS + lane * 4;
+    const bool col_ok = col < N;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += LT_K) {
+        const int kc = min(LT_K, K - k0);
+        __syncthreads();
+        for (int e = tid; e < LT_ROWS * (LT_K / 4); e += 256) {
+            const int r = e / (LT_K / 4), k4 = (e % (LT_K / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < n && k4 < kc) v = __ldg(reinterpret_cast<const float4*>(X + (row0 + r) * K + k0 + k4));
+            *reinterpret_cast<float4*>(As + r * LT_LDA + k4) = v;
+        }
+        __syncthreads();
+        if (col_ok) {
+            const float* a0 = As + warp * 8 * LT_LDA;
+            const float* w0 = Wt + (size_t)k0 * N + col;
+#pragma unroll 2
+            for (int k = 0; k < kc; k += 4) {
+                float4 w[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(reinterpret_cast<const float4*>(w0 + (size_t)(k + kk) * N));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 a = *reinterpret_cast<const float4*>(a0 + i * LT_LDA + k);
+                    acc[i][0] = fmaf(a.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(a.x, w[0].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.x, w[0].z, acc[i][2]); acc[i][3] = fmaf(a.x, w[0].w, acc[i][3]);
+                    acc[i][0] = fmaf(a.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(a.y, w[1].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.y, w[1].z, acc[i][2]); acc[i][3] = fmaf(a.y, w[1].w, acc[i][3]);
+                    acc[i][0] = fmaf(a.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(a.z, w[2].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.z, w[2].z, acc[i][2]); acc[i][3] = fmaf(a.z, w[2].w, acc[i][3]);
+                    acc[i][0] = fmaf(a.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(a.w, w[3].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.w, w[3].z, acc[i][2]); acc[i][3] = fmaf(a.w, w[3].w, acc[i][3]);
+                }
+            }
+        }
+    }
+    if (!col_ok) return;
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long r = row0 + warp * 8 + i;
+        if (r >= n) continue;
+        float4 o = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(Y + r * N + col) = o;
+    }
+}
+
+// one warp per row: y = x / max(||x||, 1e-12)
+__global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ x, long long n, int dim,
+                                                           float* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* xr = x + row * dim;
+    float ss = 0.f;
+    for (int c = lane; c < dim; c += 32) { const float v = xr[c]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < dim; c += 32) y[row * dim + c] = xr[c] * inv;
+}
+
+// ---- video tail: pooled[b][c] = mean_{t,p} fmap[b][t][c][p] ---------------------------------------
+// One thread per (b, c); adjacent threads read adjacent hw-blocks, so a warp's request is one
+// contiguous 32*hw*sizeof(T) span per frame (1 KiB for bf16 4x4).  All `frames` loads of a
+// thread are independent and unrolled to keep >= 256 B in flight per thread (HBM-bound stage).
+template <typename T, int VEC /* elements per 16-byte vector, 0 = scalar path */>
+__global__ void __launch_bounds__(256) video_pool_kernel(const T* __restrict__ fmap, long long n, int frames,
+                                                         int channels, int hw, float* __restrict__ pooled) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    const size_t fstride = (size_t)channels * hw;
+    for (long long b = blockIdx.y; b < n; b += gridDim.y) {
+    const T* base = fmap + ((size_t)b * frames * channels + c) * hw;
+    float acc = 0.f;
+    if constexpr (VEC > 0) {
+        const int nv = hw / VEC;
+#pragma unroll 4
+        for (int t = 0; t < frames; ++t) {
+            const uint4* p = reinterpret_cast<const uint4*>(base + t * fstride);
+            for (int v = 0; v < nv; ++v) {
+                uint4 u;
+                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p + v));
+                if (sizeof(T) == 2) {
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h2[q]); acc += f.x + f.y; }
+                } else {
+                    const float* f = reinterpret_cast<const float*>(&u);
+                    acc += (f[0] + f[1]) + (f[2] + f[3]);
+                }
+            }
+        }
+    } else {
+        for (int t = 0; t < frames; ++t)
+            for (int p = 0; p < hw; ++p) {
+                if (sizeof(T) == 2) acc += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base + t * fstride)[p]);
+                else acc += reinterpret_cast<const float*>(base + t * fstride)[p];
+            }
+    }
+    pooled[b * channels + c] = acc / (float)(frames * hw);
+    }
+}
+
+}  // namespace cmhar
+
+using namespace cmhar;
+
+extern "C" {
+
+size_t cmhar_linear_blob_bytes(int32_t in_dim, int32_t out_dim) {
+    if (in_dim < 4 || out_dim < 4 || (in_dim & 3) || (out_dim & 3)) return 0;
+    return sizeof(BlobHeader) + ((size_t)in_dim * out_dim + out_dim) * sizeof(float);
+}
+
+int cmhar_linear_pack(const float* weight, const float* bias, const float* bn_weight, const float* bn_bias,
+                      const float* bn_mean, const float* bn_var, int32_t in_dim, int32_t out_dim, void* blob,
+                      cmhar_stream_t s) {
+    CMHAR_REQUIRE(weight && blob, "cmhar_linear_pack: null argument");
+    CMHAR_REQUIRE(cmhar_linear_blob_bytes(in_dim, out_dim) != 0, "linear dims (%d,%d) must be multiples of 4", in_dim, out_dim);
+    CMHAR_REQUIRE(!bn_weight || (bn_bias && bn_mean && bn_var), "BatchNorm needs weight, bias, mean and var");
+    cudaStream_t st = (cudaStream_t)s;
+    float* f = reinterpret_cast<float*>(reinterpret_cast<char*>(blob) + sizeof(BlobHeader));
+    const long long tot = (long long)in_dim * out_dim;
+    transpose_fold_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(weight, out_dim, in_dim, f, out_dim, 0, 1.f, bn_weight, bn_var);
+    CMHAR_LAUNCH_CHECK();
+    bias_fold_kernel<<<(out_dim + 255) / 256, 256, 0, st>>>(bias, out_dim, f + tot, 0, 1.f, bn_weight, bn_bias, bn_mean, bn_var);
+    CMHAR_LAUNCH_CHECK();
+    BlobHeader h{};
+    h.magic = LIN_MAGIC; h.a = in_dim; h.b = out_dim;
+    write_header_kernel<<<1, 1, 0, st>>>(reinterpret_cast<BlobHeader*>(blob), h);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+int cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in_dim, int32_t out_dim, int32_t relu,
+                         float* y, int32_t precision, cmhar_stream_t s) {
+    CMHAR_REQUIRE(blob && x && y, "cmhar_linear_forward: null argument");
+    CMHAR_REQUIRE(cmhar_linear_blob_bytes(in_dim, out_dim) != 0, "linear dims (%d,%d) must be multiples of 4", in_dim, out_dim);
+    CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
+    if (n <= 0) return CMHAR_OK;
+    const float* f = reinterpret_cast<const float*>(reinterpret_cast<const char*>(blob) + sizeof(BlobHeader));
+    dim3 grid((unsigned)((n + LT_ROWS - 1) / LT_ROWS), (unsigned)((out_dim + LT_COLS - 1) / LT_COLS));
+    linear_fp32_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(f, f + (size_t)in_dim * out_dim, x, n, in_dim, out_dim, relu, y);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+int cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmhar_stream_t s) {
+    CMHAR_REQUIRE(x && y && dim > 0, "cmhar_l2_normalize: bad argument");
+    if (n <= 0) return CMHAR_OK;
+    l2_normalize_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)s>>>(x, n, dim, y);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
+                     float* pooled, cmhar_stream_t s) {
+    CMHAR_REQUIRE(fmap && pooled && frames > 0 && channels > 0 && hw > 0, "cmhar_video_pool: bad argument");
+    if (n <= 0) return CMHAR_OK;
+    cudaStream_t st = (cudaStream_t)s;
+    dim3 grid((channels + 255) / 256, (unsigned)(n < 32768 ? n : 32768));
+    const bool aligned = ((uintptr_t)fmap & 15) == 0;
+    if (is_bf16) {
+        if (aligned && hw % 8 == 0)
+            video_pool_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled);
+        else
+            video_pool_kernel<__nv_bfloat16, 0><<<grid, 256, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled);
+    } else {
+        if (aligned && hw % 4 == 0)
+            video_pool_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled);
+        else
+            video_pool_kernel<float, 0><<<grid, 256, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled);
+    }
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// ood.cu -- OOD scoring stage.  SPEC-DERIVED: the reference has no OOD code (SURVEY.md F2, rows
+// A1-A5); definitions are the literature ones restated in oracle/ood_spec.py.
+//   A1 MSP      score = -max softmax(logits)
+//   A2 energy   score = -T logsumexp(logits / T)
+//   A3 fit      per-class counts / sums and sum f f^T (double) -> all-reduced, finalised on host
+//   A4 score    min_c || f W - mu_c W ||^2    (W = whitening factor of the tied covariance)
+//   A5 AUROC/FPR95 from order-preserving score histograms
+#include "common.cuh"
+
+namespace cmhar {
+
+// ---- A1/A2 from stored logits: one warp per row -------------------------------------------------
+__global__ void __launch_bounds__(256) logit_scores_kernel(const float* __restrict__ logits, long long n, int C,
+                                                           float invT, float T, long long* __restrict__ pred,
+                                                           float* __restrict__ msp, float* __restrict__ energy) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* z = logits + row * C;
+    float m = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+        const float v = z[c];
+        if (v > m) { m = v; idx = c; }
+    }
+    const float gm = warp_max(m);
+    idx = (m == gm) ? idx : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, o));
+    float s1 = 0.f, sT = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float v = z[c];
+        s1 += expf(v - gm);
+        sT += expf((v - gm) * invT);
+    }
+    s1 = warp_sum(s1);
+    sT = warp_sum(sT);
+    if (lane == 0) {
+        if (pred) pred[row] = idx;
+        if (msp) msp[row] = -1.f / s1;
+        if (energy) energy[row] = -(gm + T * logf(sT));
+    }
+}
+
+// ---- A4 from stored features -----------------------------------------------------------------
+// 64 rows per tile: Y = F W (64x128x128 register-tiled fp32 GEMM), then squared distances to the
+// whitened class means.
+__global__ void __launch_bounds__(256) maha_score_kernel(const char* __restrict__ blob, const float* __restrict__ feat,
+                                                         long long n, float* __restrict__ score) {
+    constexpr int LDY = D + 4;
+    extern __shared__ __align__(16) float ms_smem[];
+    float* F = ms_smem;                 // [64][128]
+    float* Y = ms_smem + 64 * D;        // [64][132]
+    const BlobHeader* mh = reinterpret_cast<const BlobHeader*>(blob);
+    const MahaLayout ml{mh->a};
+    const float* maha = reinterpret_cast<const float*>(blob + sizeof(BlobHeader));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long tiles = (n + 63) / 64;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long r0 = tile * 64;
+        __syncthreads();
+        for (int e = tid; e < 64 * (D / 4); e += 256) {
+            const int r = e / (D / 4), c4 = e % (D / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < n) v = __ldg(reinterpret_cast<const float4*>(feat + (r0 + r) * D) + c4);
+            reinterpret_cast<float4*>(F + r * D)[c4] = v;
+        }
+        __syncthreads();
+        {
+            float acc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            const float* a0 = F + warp * 8 * D;
+            const float* w0 = maha + ml.whiten() + lane * 4;
+#pragma unroll 2
+            for (int k = 0; k < D; k += 4) {
+                float4 w[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(reinterpret_cast<const float4*>(w0 + (size_t)(k + kk) * D));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 a = *reinterpret_cast<const float4*>(a0 + i * D + k);
+                    acc[i][0] = fmaf(a.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(a.x, w[0].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.x, w[0].z, acc[i][2]); acc[i][3] = fmaf(a.x, w[0].w, acc[i][3]);
+                    acc[i][0] = fmaf(a.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(a.y, w[1].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.y, w[1].z, acc[i][2]); acc[i][3] = fmaf(a.y, w[1].w, acc[i][3]);
+                    acc[i][0] = fmaf(a.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(a.z, w[2].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.z, w[2].z, acc[i][2]); acc[i][3] = fmaf(a.z, w[2].w, acc[i][3]);
+                    acc[i][0] = fmaf(a.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(a.w, w[3].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.w, w[3].z, acc[i][2]); acc[i][3] = fmaf(a.w, w[3].w, acc[i][3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(Y + (warp * 8 + i) * LDY + lane * 4) =
+                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        __syncthreads();
+        {   // thread (r = tid/4, q = tid%4) scans classes q, q+4, ...
+            const int r = tid >> 2, q = tid & 3;
+            float best = INFINITY;
+            for (int c = q; c < ml.C; c += 4) {
+                const float* mu = maha + ml.mean_w() + (size_t)c * D;
+                float d = 0.f;
+#pragma unroll 8
+                for (int j = 0; j < D; j += 4) {
+                    const float4 y = *reinterpret_cast<const float4*>(Y + r * LDY + j);
+                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + j));
+                    const float dx = y.x - m4.x, dy = y.y - m4.y, dz = y.z - m4.z, dw = y.w - m4.w;
+                    d = fmaf(dx, dx, d); d = fmaf(dy, dy, d); d = fmaf(dz, dz, d); d = fmaf(dw, dw, d);
+                }
+                if (__ldg(maha + ml.valid() + c) > 0.f) best = fminf(best, d);
+            }
+            best = fminf(best, __shfl_xor_sync(0xffffffffu, best, 1));
+            best = fminf(best, __shfl_xor_sync(0xffffffffu, best, 2));
+            if (q == 0 && r0 + r < n) score[r0 + r] = best;
+        }
+    }
+}
+
+// ---- A3 sufficient statistics --------------------------------------------------------------
+// Persistent CTAs; each keeps a private double-precision 128x128 second-moment accumulator and
+// per-class sums in shared memory, feeds them from 32-row fp32 register-tiled partial products,
+// and adds them to the global double buffers once at the end (one atomic per element per CTA).
+constexpr int MA_ROWS = 32;
+__global__ void __launch_bounds__(256, 1) maha_accumulate_kernel(const float* __restrict__ feat,
+                                                                 const long long* __restrict__ labels, long long n,
+                                                                 int C, double* __restrict__ count,
+                                                                 double* __restrict__ sum, double* __restrict__ second) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    double* s2 = reinterpret_cast<double*>(sm_raw);                 // [128][128]
+    double* ssum = s2 + D * D;                                      // [C][128]
+    double* scnt = ssum + (size_t)C * D;                            // [C]
+    float* F = reinterpret_cast<float*>(scnt + ((C + 1) & ~1));     // [MA_ROWS][128], 16-byte aligned
+    int* lab = reinterpret_cast<int*>(F + MA_ROWS * D);             // [MA_ROWS]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // thread owns rows ty*8.., cols tx*8..
+    for (int e = tid; e < D * D + C * D + C; e += 256) s2[e] = 0.0;
+    const long long chunks = (n + MA_ROWS - 1) / MA_ROWS;
+    float acc[8][8];
+    int pending = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const long long r0 = ch * MA_ROWS;
+        __syncthreads();
+        for (int e = tid; e < MA_ROWS * (D / 4); e += 256) {
+            const int r = e / (D / 4), c4 = e % (D / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < n) {
+                const long long y = labels[r0 + r];
+                if (y >= 0 && y < C) v = __ldg(reinterpret_cast<const float4*>(feat + (r0 + r) * D) + c4);
+            }
+            reinterpret_cast<float4*>(F + r * D)[c4] = v;
+        }
+        if (tid < MA_ROWS) {
+            long long y = (r0 + tid < n) ? labels[r0 + tid] : -1;
+            lab[tid] = (y >= 0 && y < C) ? (int)y : -1;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < MA_ROWS; ++r) {
+            const float4 a0 = *reinterpret_cast<const float4*>(F + r * D + ty * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(F + r * D + ty * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(F + r * D + tx * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(F + r * D + tx * 8 + 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        // class sums / counts: thread (half = tid/128, c = tid%128) walks every other row
+        {
+            const int c = tid & 127;
+            for (int r = tid >> 7; r < MA_ROWS; r += 2) {
+                const int y = lab[r];
+                if (y >= 0) {
+                    atomicAdd(&ssum[(size_t)y * D + c], (double)F[r * D + c]);
+                    if (c == 0) atomicAdd(&scnt[y], 1.0);
+                }
+            }
+        }
+        if (++pending == 16) {        // flush fp32 partials (512 rows) into the double accumulator
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s2[(ty * 8 + i) * D + tx * 8 + j] += (double)acc[i][j]; acc[i][j] = 0.f; }
+            pending = 0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s2[(ty * 8 + i) * D + tx * 8 + j] += (double)acc[i][j];
+    __syncthreads();
+    for (int e = tid; e < D * D; e += 256) if (s2[e] != 0.0) atomicAdd(&second[e], s2[e]);
+    for (int e = tid; e < C * D; e += 256) if (ssum[e] != 0.0) atomicAdd(&sum[e], ssum[e]);
+    for (int e = tid; e < C; e += 256) if (scnt[e] != 0.0) atomicAdd(&count[e], scnt[e]);
+}
+
+// ---- A5 histograms ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t score_key(float v) {      // order-preserving float -> uint32
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) score_key_range_kernel(const float* __restrict__ s, long long n,
+                                                              uint32_t* __restrict__ mm) {
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = s[i];
+        if (v != v) continue;                                  // NaN scores are ignored
+        const uint32_t k = score_key(v);
+        lo = min(lo, k); hi = max(hi, k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
+}
+
+__global__ void __launch_bounds__(256) score_histogram_kernel(const float* __restrict__ s, long long n, uint32_t key_lo,
+                                                              int shift, int bins, unsigned long long* __restrict__ hist) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = s[i];
+        if (v != v) continue;
+        const uint32_t k = score_key(v);
+        long long b = (k < key_lo) ? 0 : (long long)((k - key_lo) >> shift);
+        if (b >= bins) b = bins - 1;
+        atomicAdd(&hist[b], 1ull);
+    }
+}
+
+}  // namespace cmhar
+
+using namespace cmhar;
+
+extern "C" {
+
+int cmhar_logit_scores(const float* logits, int64_t n, int32_t classes, float temperature, int64_t* pred_out,
+                       float* msp_out, float* energy_out, cmhar_stream_t s) {
+    CMHAR_REQUIRE(logits && classes >= 1 && temperature > 0.f, "cmhar_logit_scores: bad argument");
+    if (n <= 0) return CMHAR_OK;
+    logit_scores_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)s>>>(
+        logits, n, classes, 1.f / temperature, temperature, reinterpret_cast<long long*>(pred_out), msp_out, energy_out);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float* score, cmhar_stream_t s) {
+    CMHAR_REQUIRE(maha_blob && feat && score, "cmhar_maha_score: null argument");
+    if (n <= 0) return CMHAR_OK;
+    const long long tiles = (n + 63) / 64;
+    const int grid = (int)((tiles < 3LL * sm_count()) ? tiles : 3LL * sm_count());
+    const size_t smem = sizeof(float) * (64 * D + 64 * (D + 4));
+    static bool configured[64] = {};
+    int dev = 0;
+    CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(maha_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev & 63] = true;
+    }
+    maha_score_kernel<<<grid, 256, smem, (cudaStream_t)s>>>(reinterpret_cast<const char*>(maha_blob), feat, n, score);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+int cmhar_maha_accumulate(const float* feat, const int64_t* labels, int64_t n, int32_t classes, double* count,
+                          double* sum, double* second, cmhar_stream_t s) {
+    CMHAR_REQUIRE(feat && labels && count && sum && second, "cmhar_maha_accumulate: null argument");
+    CMHAR_REQUIRE(classes >= 1 && classes <= 64, "classes=%d outside [1,64]", classes);
+    if (n <= 0) return CMHAR_OK;
+    const size_t smem = sizeof(double) * ((size_t)D * D + (size_t)classes * D + ((classes + 1) & ~1)) + sizeof(float) * MA_ROWS * D + sizeof(int) * MA_ROWS;
+    static bool configured[64] = {};
+    int dev = 0;
+    CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(maha_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured[dev & 63] = true;
+    }
+    const long long chunks = (n + MA_ROWS - 1) / MA_ROWS;
+    const int grid = (int)((chunks < (long long)sm_count()) ? chunks : (long long)sm_count());
+    maha_accumulate_kernel<<<grid, 256, smem, (cudaStream_t)s>>>(feat, reinterpret_cast<const long long*>(labels), n, classes, count, sum, second);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+int cmhar_score_key_range(const float* scores, int64_t n, uint32_t* key_min_max, cmhar_stream_t s) {
+    CMHAR_REQUIRE(scores && key_min_max, "cmhar_score_key_range: null argument");
+    if (n <= 0) return CMHAR_OK;
+    const long long blocks = (n + 255) / 256;
+    const int grid = (int)((blocks < 8LL * sm_count()) ? blocks : 8LL * sm_count());
+    score_key_range_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(scores, n, key_min_max);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+int cmhar_score_histogram(const float* scores, int64_t n, uint32_t key_lo, int32_t shift, int32_t bins,
+                          unsigned long long* hist, cmhar_stream_t s) {
+    CMHAR_REQUIRE(scores && hist && bins >= 1 && shift >= 0 && shift < 32, "cmhar_score_histogram: bad argument");
+    if (n <= 0) return CMHAR_OK;
+    const long long blocks = (n + 255) / 256;
+    const int grid = (int)((blocks < 8LL * sm_count()) ? blocks : 8LL * sm_count());
+    score_histogram_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(scores, n, key_lo, shift, bins, hist);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+"""Drop-in surface of the reference's ``src/eval/evaluator.py`` ``Evaluator`` (rows a8/a9) plus
+the OOD evaluation the north_star adds (rows A1-A5, spec-derived).
+
+``predict`` keeps the reference's contract -- ``(preds int64 (N,), labels (N,), logits fp32
+(N, C))`` as numpy arrays, arg-max = first maximal index (``logits.max(1)``,
+src/eval/evaluator.py:45) -- but restructures the data movement:
+
+* only the live samples of each window (channel 0, first 16*(S-1) samples -- SURVEY.md F4) are
+  staged into pinned host memory and copied to the device, 6.25x fewer PCIe bytes than the
+  reference's ``batch['imu'].to(device)``;
+* encoder + head + arg-max + MSP/energy(/Mahalanobis) run as ONE kernel launch per batch;
+* results stay on the device in preallocated buffers; there is one device->host copy at the end
+  instead of a synchronising ``.cpu()`` per batch.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .models import IMUClassifier
+from .ood import MahalanobisOOD, auroc_fpr95
+
+__all__ = ["Evaluator", "classification_metrics", "shard_bounds"]
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous window range [lo, hi) owned by ``rank`` (rows by rank,
+    no data-path collective)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def classification_metrics(y_true, y_pred) -> Dict[str, float]:
+    """The six numbers of reference src/eval/evaluator.py:55-65 (sklearn accuracy, balanced
+    accuracy, macro/weighted F1, macro precision/recall with zero_division=0; all x100), computed
+    from one confusion matrix.  Label set = union(y_true, y_pred) like sklearn's."""
+    yt = np.asarray(y_true).astype(np.int64).ravel()
+    yp = np.asarray(y_pred).astype(np.int64).ravel()
+    labels, inv = np.unique(np.concatenate([yt, yp]), return_inverse=True)
+    k = labels.size
+    ti, pi = inv[:yt.size], inv[yt.size:]
+    cm = np.bincount(ti * k + pi, minlength=k * k).reshape(k, k).astype(np.float64)
+    hit, support, called = np.diag(cm), cm.sum(1), cm.sum(0)
+    recall = np.divide(hit, support, out=np.zeros(k), where=support > 0)
+    precision = np.divide(hit, called, out=np.zeros(k), where=called > 0)
+    denom = precision + recall
+    f1 = np.divide(2 * precision * recall, denom, out=np.zeros(k), where=denom > 0)
+    seen = support > 0
+    return {
+        "accuracy": float(hit.sum() / max(yt.size, 1) * 100),
+        "balanced_accuracy": float(recall[seen].mean() * 100) if seen.any() else 0.0,
+        "f1_macro": float(f1.mean() * 100),
+        "f1_weighted": float((f1 * support).sum() / max(support.sum(), 1) * 100),
+        "precision_macro": float(precision.mean() * 100),
+        "recall_macro": float(recall.mean() * 100),
+    }
+
+
+class Evaluator:
+    """``Evaluator(model, config, device='cuda')`` -- same constructor and methods as the
+    reference class (src/eval/evaluator.py:18-77)."""
+
+    def __init__(self, model, config, device="cuda", precision: Optional[str] = None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("cmhar_b200.Evaluator runs the CUDA hot path only; device must be a CUDA device "
+                               "(there is no CPU fallback)")
+        self.model = model.to(self.device)
+        self.config = config
+        self.precision = precision
+        self.model.eval()
+        self._stage = None            # pinned host staging buffer
+        self._dev_in = None           # device input double buffer
+
+    # ------------------------------------------------------------------ data movement
+    def _live(self, L: int) -> int:
+        enc = self.model.imu_encoder
+        S = enc._check_native_dims(L)
+        return 16 * (S - 1)
+
+    def _upload(self, imu: torch.Tensor, slot: int) -> torch.Tensor:
+        """batch['imu'] (B, C, L) on the host -> compact (B, live) fp32 on the device."""
+        if imu.is_cuda:
+            return imu
+        B, L = imu.shape[0], imu.shape[-1]
+        live = self._live(L)
+        if self._stage is None or self._stage.shape[1] < B or self._stage.shape[2] != live:
+            cap = max(B, 64)
+            self._stage = torch.empty((2, cap, live), dtype=torch.float32).pin_memory()
+            self._dev_in = torch.empty((2, cap, live), dtype=torch.float32, device=self.device)
+            self._events = [torch.cuda.Event(), torch.cuda.Event()]
+            self._used = [False, False]
+        if self._used[slot]:
+            self._events[slot].synchronize()          # the H2D that last read this pinned slot is done
+        st = self._stage[slot, :B]
+        st.copy_(imu[:, 0, :live] if imu.dim() == 3 else imu[:, :live])
+        dv = self._dev_in[slot, :B]
+        dv.copy_(st, non_blocking=True)
+        self._events[slot].record(torch.cuda.current_stream(self.device))
+        self._used[slot] = True
+        return dv
+
+    @torch.no_grad()
+    def predict_scores(self, dataloader: Iterable, want_cls: bool = False) -> Dict[str, np.ndarray]:
+        """One pass over the loader: preds, labels, logits, msp, energy (+ maha, + cls)."""
+        if not isinstance(self.model, IMUClassifier):
+            raise TypeError("Evaluator needs an IMUClassifier")
+        outs = []
+        labels = []
+        with torch.cuda.device(self.device):
+            for i, batch in enumerate(dataloader):
+                x = self._upload(batch["imu"], i & 1)
+                res = self.model.forward_scores(x, precision=self.precision, want_cls=want_cls,
+                                                window_stride=x.stride(0) if x.dim() == 2 else None)
+                outs.append(res)
+                if "label" in batch:
+                    labels.append(torch.as_tensor(batch["label"]).reshape(-1))
+            merged = {}
+            if outs:
+                for k in outs[0]:
+                    merged[k] = torch.cat([o[k] for o in outs]).cpu().numpy()     # single D2H per field
+        out = {"predictions": merged.get("pred", np.zeros(0, np.int64)),
+               "logits": merged.get("logits", np.zeros((0, self.model.num_classes), np.float32)),
+               "labels": torch.cat(labels).numpy() if labels else np.zeros(0, np.int64)}
+        for k in ("msp", "energy", "maha", "cls"):
+            if k in merged:
+                out[k] = merged[k]
+        return out
+
+    @torch.no_grad()
+    def predict(self, dataloader):
+        """reference src/eval/evaluator.py:27-53 -> (predictions, labels, logits)."""
+        r = self.predict_scores(dataloader)
+        return r["predictions"], r["labels"], r["logits"]
+
+    def compute_metrics(self, y_true, y_pred):
+        """reference src/eval/evaluator.py:55-65."""
+        return classification_metrics(y_true, y_pred)
+
+    def evaluate(self, dataloader):
+        """reference src/eval/evaluator.py:67-77."""
+        preds, labels, logits = self.predict(dataloader)
+        return {"metrics": self.compute_metrics(labels, preds), "predictions": preds, "labels": labels,
+                "logits": logits}
+
+    # ------------------------------------------------------------------ OOD (spec rows A1-A5)
+    @torch.no_grad()
+    def fit_mahalanobis(self, dataloader, ridge: float = 0.0) -> MahalanobisOOD:
+        """Fit class means + tied covariance on the CLS features of an ID-train loader and attach
+        the scorer to the model (so later passes emit 'maha' from the same fused launch)."""
+        maha = MahalanobisOOD(self.model.num_classes, self.device, ridge)
+        self.model.set_mahalanobis(None)
+        with torch.cuda.device(self.device):
+            for i, batch in enumerate(dataloader):
+                x = self._upload(batch["imu"], i & 1)
+                res = self.model.forward_scores(x, precision=self.precision, want_cls=True, want_logits=False,
+                                                window_stride=x.stride(0) if x.dim() == 2 else None)
+                maha.accumulate(res["cls"], torch.as_tensor(batch["label"]))
+        maha.finalize()
+        self.model.set_mahalanobis(maha)
+        return maha
+
+    @torch.no_grad()
+    def evaluate_ood(self, id_loader, ood_loader, scorers=("msp", "energy", "maha")) -> Dict[str, Dict[str, float]]:
+        """AUROC / FPR95 per scorer, ID loader vs held-out-activity (OOD) loader."""
+        rid, rood = self.predict_scores(id_loader), self.predict_scores(ood_loader)
+        table = {}
+        for name in scorers:
+            if name not in rid:
+                continue
+            a = torch.from_numpy(rid[name]).to(self.device)
+            b = torch.from_numpy(rood[name]).to(self.device)
+            r = auroc_fpr95(a, b)
+            table[name] = {"auroc": r["auroc"], "fpr95": r["fpr"], "auroc_bound": r["auroc_bound"]}
+        return table

@@ -1,0 +1,118 @@
+"""Fused encode -> fuse -> OOD-score pass over one batch (BASELINE.json's metric).
+
+``CrossModalOODPipeline.run`` is the call a user makes for a batch of IMU windows plus the video
+trunk's feature maps:
+
+    IMU windows --(1 launch)--> CLS feature, logits, arg-max, MSP, energy, Mahalanobis
+    feature maps --(pool + GEMM)--> video feature
+    both --> projection heads --> L2 normalise --> B x B similarity with fused sigmoid loss
+
+Every stage is a kernel of ``libcmhar_b200.so``; nothing is computed by torch ops.  ``capture``
+records the whole pass into a CUDA graph (10 launches -> one graph launch), which is what the
+throughput benchmark replays.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _native as N
+from .losses import similarity_native
+from .models import CrossModalModel, IMUClassifier, l2_normalize_native
+from .ood import MahalanobisOOD
+
+__all__ = ["CrossModalOODPipeline"]
+
+
+class CrossModalOODPipeline:
+    def __init__(self, classifier: IMUClassifier, cross_modal: CrossModalModel,
+                 mahalanobis: Optional[MahalanobisOOD] = None, frames: int = 16,
+                 precision: Optional[str] = None, sigmoid_scale: float = 10.0, sigmoid_bias: float = -10.0):
+        self.clf, self.xm, self.frames, self.precision = classifier.eval(), cross_modal.eval(), frames, precision
+        if mahalanobis is not None:
+            self.clf.set_mahalanobis(mahalanobis)
+        self.sig = (float(sigmoid_scale), float(sigmoid_bias))
+        self._host = None
+
+    @torch.no_grad()
+    def run(self, imu: torch.Tensor, fmap: Optional[torch.Tensor], window_stride: Optional[int] = None
+            ) -> Dict[str, torch.Tensor]:
+        """imu (B,6,L) fp32 [or compact (B,live) with window_stride]; fmap (B*frames,F,h,w) bf16/fp32
+        or None for the IMU-only path.  Returns device tensors: pred, msp, energy, (maha,) logits,
+        cls and, with fmap, imu_proj, video_proj, loss (mean sigmoid contrastive loss, fp64 0-dim)."""
+        out = self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
+        if fmap is None:
+            return out
+        vfeat = self.xm.video_encoder.forward_features(fmap, self.frames, precision=self.precision)
+        ip = l2_normalize_native(self.xm.imu_proj(out["cls"]))
+        vp = l2_normalize_native(self.xm.video_proj(vfeat))
+        res = similarity_native(ip, vp, sigmoid=self.sig, precision=self.precision)
+        out.update(imu_proj=ip, video_proj=vp, loss=res["sigmoid_sum"] / float(ip.shape[0] * vp.shape[0]))
+        return out
+
+    def capture(self, imu: torch.Tensor, fmap: Optional[torch.Tensor]):
+        """Record ``run`` on static inputs into a CUDA graph; returns (graph, outputs)."""
+        side = torch.cuda.Stream(device=imu.device)
+        side.wait_stream(torch.cuda.current_stream(imu.device))
+        with torch.cuda.stream(side):
+            self.run(imu, fmap)                      # warm-up: packs weights, sizes allocations
+        torch.cuda.current_stream(imu.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.run(imu, fmap)
+        return graph, out
+
+    # ------------------------------------------------------------------ host-buffer entry (e2e)
+    @torch.no_grad()
+    def run_host(self, imu_host: torch.Tensor, fmap_host: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Same pass from HOST tensors: stages the live IMU samples (channel 0, 16*(S-1) samples) and
+        the feature maps through pinned buffers, runs the fused pass, and copies the per-window
+        results (pred, msp, energy, maha) and the loss back to pinned host memory.  Synchronises."""
+        dev = next(self.clf.parameters()).device
+        B, L = imu_host.shape[0], imu_host.shape[-1]
+        live = 16 * (self.clf.imu_encoder._check_native_dims(L) - 1)
+        h = self._host
+        if h is None or h["B"] != B or h["live"] != live or (fmap_host is not None and h.get("fmap_shape") != tuple(fmap_host.shape)):
+            h = {"B": B, "live": live,
+                 "imu_pin": torch.empty((B, live), dtype=torch.float32).pin_memory(),
+                 "imu_dev": torch.empty((B, live), dtype=torch.float32, device=dev),
+                 "res_pin": torch.empty((4, B), dtype=torch.float32).pin_memory(),
+                 "pred_pin": torch.empty((B,), dtype=torch.int64).pin_memory(),
+                 "loss_pin": torch.empty((), dtype=torch.float64).pin_memory()}
+            if fmap_host is not None:
+                h["fmap_shape"] = tuple(fmap_host.shape)
+                h["fmap_pin"] = fmap_host if fmap_host.is_pinned() else torch.empty_like(fmap_host).pin_memory()
+                h["fmap_dev"] = torch.empty(fmap_host.shape, dtype=fmap_host.dtype, device=dev)
+            self._host = h
+        h["imu_pin"].copy_(imu_host[:, 0, :live] if imu_host.dim() == 3 else imu_host[:, :live])
+        h["imu_dev"].copy_(h["imu_pin"], non_blocking=True)
+        fdev = None
+        if fmap_host is not None:
+            src = fmap_host
+            if not fmap_host.is_pinned():
+                h["fmap_pin"].copy_(fmap_host)
+                src = h["fmap_pin"]
+            h["fmap_dev"].copy_(src, non_blocking=True)
+            fdev = h["fmap_dev"]
+        out = self.run(h["imu_dev"], fdev, window_stride=live)
+        h["pred_pin"].copy_(out["pred"], non_blocking=True)
+        h["res_pin"][0].copy_(out["msp"], non_blocking=True)
+        h["res_pin"][1].copy_(out["energy"], non_blocking=True)
+        if "maha" in out:
+            h["res_pin"][2].copy_(out["maha"], non_blocking=True)
+        if "loss" in out:
+            h["loss_pin"].copy_(out["loss"], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        res = {"pred": h["pred_pin"], "msp": h["res_pin"][0], "energy": h["res_pin"][1]}
+        if "maha" in out:
+            res["maha"] = h["res_pin"][2]
+        if "loss" in out:
+            res["loss"] = h["loss_pin"]
+        return res
+
+    def host_bytes_per_step(self, B: int, L: int, fmap_host: Optional[torch.Tensor]):
+        live = 16 * (self.clf.imu_encoder._check_native_dims(L) - 1)
+        h2d = B * live * 4 + (fmap_host.numel() * fmap_host.element_size() if fmap_host is not None else 0)
+        d2h = B * (8 + 4 + 4 + (4 if self.clf._maha_state is not None else 0)) + (8 if fmap_host is not None else 0)
+        return h2d, d2h

@@ -1,0 +1,209 @@
+/*
+ * cmhar_b200.h -- C ABI of the B200-native (sm_100a) cross-modal inference / OOD-scoring hot path.
+ *
+ * Drop-in boundary for YOUNESELBOUKNIFY/CrossModal-IMU-Video-OOD-HAR.  The reference has no FFI
+ * (it is pure PyTorch); its "operator API" for this path is the eval-mode
+ * forward of the nn.Modules in src/models/models.py, src/models/losses.py and the loop in
+ * src/eval/evaluator.py.  Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense row-major unless a stride argument says otherwise;
+ *   - no function allocates, frees or retains caller memory, none synchronises the device, all
+ *     work is enqueued on the given stream (so calls can be captured into a CUDA graph);
+ *   - return value: 0 = ok, negative = error; cmhar_last_error() returns a thread-local message;
+ *   - weights are handed over once through a *_pack call that folds BatchNorm, transposes and
+ *     (for the bf16 path) converts into a caller-owned blob; the blob is immutable afterwards
+ *     and can be shared by concurrent streams (the reference's nn.DataParallel use,
+ *     main.py:89-95, calls forward from several threads);
+ *   - "precision": CMHAR_FP32 = fp32 CUDA-core arithmetic (1e-3 contract),
+ *                  CMHAR_BF16 = bf16 tcgen05 tensor-core GEMMs with fp32 accumulation in TMEM
+ *                               (2e-2 contract).
+ *   - OOD scores: larger = more out-of-distribution.
+ */
+#ifndef CMHAR_B200_H
+#define CMHAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMHAR_ABI_VERSION 1
+
+#define CMHAR_OK               0
+#define CMHAR_ERR_INVALID     -1   /* bad argument / unsupported shape                       */
+#define CMHAR_ERR_CUDA        -2   /* a CUDA runtime call failed (message has the detail)    */
+#define CMHAR_ERR_UNSUPPORTED -3   /* valid request this build cannot serve                  */
+
+#define CMHAR_FP32 0
+#define CMHAR_BF16 1
+
+#define CMHAR_MAX_LAYERS 8
+#define CMHAR_D_MODEL    128       /* configs/config.py:79  (kernels are specialised to it)  */
+#define CMHAR_NHEAD      8         /* configs/config.py:80                                    */
+#define CMHAR_FFN        512       /* src/models/models.py:88                                 */
+#define CMHAR_PATCH      16        /* configs/config.py:77-78 (patch == stride)               */
+#define CMHAR_MAX_SEQ    16        /* 1 + (250-16)/16 + 1 tokens survive, models.py:122-123   */
+#define CMHAR_MAX_CLASSES 64
+
+typedef void* cmhar_stream_t;      /* cudaStream_t */
+
+int         cmhar_abi_version(void);
+const char* cmhar_last_error(void);
+/* number of kernel launches this library has enqueued since load (all threads) */
+int64_t     cmhar_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * IMU encoder  (replaces PatchEmbedding.forward + IMUEncoder.forward,
+ *               reference src/models/models.py:30-50,100-132, and the
+ *               nn.TransformerEncoderLayer stack it calls, torch/nn/modules/transformer.py:946-990)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float *in_proj_weight;   /* (384,128) */
+    const float *in_proj_bias;     /* (384)     */
+    const float *out_proj_weight;  /* (128,128) */
+    const float *out_proj_bias;    /* (128)     */
+    const float *linear1_weight;   /* (512,128) */
+    const float *linear1_bias;     /* (512)     */
+    const float *linear2_weight;   /* (128,512) */
+    const float *linear2_bias;     /* (128)     */
+    const float *norm1_weight, *norm1_bias;   /* (128) */
+    const float *norm2_weight, *norm2_bias;   /* (128) */
+} cmhar_encoder_layer_params;
+
+typedef struct {
+    int32_t seq;                   /* tokens kept = min(1+C*N, N+1), 2..16                    */
+    int32_t layers;                /* 1..CMHAR_MAX_LAYERS                                     */
+    const float *cls_token;        /* (128)       models.py:75                                */
+    const float *pos_encoding;     /* (>=seq,128) models.py:82                                */
+    const float *patch_weight;     /* (128,16) of channel 0 -- the only live channel (F4)     */
+    const float *patch_bias;       /* (128)                                                   */
+    const float *norm_weight, *norm_bias;     /* final LayerNorm, models.py:98                */
+    cmhar_encoder_layer_params layer[CMHAR_MAX_LAYERS];
+} cmhar_imu_encoder_params;
+
+/* Classifier head (replaces IMUClassifier.classifier, models.py:312-326: [Linear,BN,ReLU,Dropout]x2,
+ * Linear).  BatchNorm is folded with its running statistics (eval mode). */
+typedef struct {
+    int32_t hidden1, hidden2, classes;        /* 256, 128, 32; each <= 256, classes <= 64     */
+    const float *w0, *b0, *bn0_weight, *bn0_bias, *bn0_mean, *bn0_var;   /* (h1,128)          */
+    const float *w1, *b1, *bn1_weight, *bn1_bias, *bn1_mean, *bn1_var;   /* (h2,h1)           */
+    const float *w2, *b2;                                                 /* (classes,h2)      */
+} cmhar_head_params;
+
+size_t cmhar_imu_encoder_blob_bytes(int32_t seq, int32_t layers);
+int    cmhar_imu_encoder_pack(const cmhar_imu_encoder_params* p, void* blob, cmhar_stream_t s);
+size_t cmhar_head_blob_bytes(int32_t hidden1, int32_t hidden2, int32_t classes);
+int    cmhar_head_pack(const cmhar_head_params* p, void* blob, cmhar_stream_t s);
+
+/* Mahalanobis scorer state: whitening matrix and whitened class means (see cmhar_maha_*) */
+size_t cmhar_maha_blob_bytes(int32_t classes);
+int    cmhar_maha_pack(const float* whiten /*(128,128): dist=||f@whiten - mu_w||^2*/,
+                       const float* mean_whitened /*(classes,128)*/,
+                       const float* class_count /*(classes) or NULL; count<=0 => class skipped*/,
+                       int32_t classes, void* blob, cmhar_stream_t s);
+
+/* One fused launch: windows -> encoder -> [head -> logits, arg-max, MSP, energy] [-> Mahalanobis].
+ * Replaces IMUEncoder.forward / IMUClassifier.forward (models.py:100-132,328-339) and the per-batch
+ * body of Evaluator.predict (src/eval/evaluator.py:44-45).
+ *   x            channel-0 samples of window 0; window w starts at x + w*x_window_stride (floats);
+ *                at least 16*(seq-1) contiguous samples are read per window.  Pass the (B,6,L)
+ *                tensor's data pointer with x_window_stride = 6*L: channels 1..5 and the trailing
+ *                samples are dead inputs of the reference and are never touched.
+ *   head_blob    NULL => encoder only (logits/pred/msp/energy must be NULL)
+ *   maha_blob    NULL => no Mahalanobis score (maha_out must be NULL)
+ *   any output pointer may be NULL.  pred = first arg-max index (torch ``logits.max(1)``).
+ */
+int cmhar_imu_forward(const void* encoder_blob, const void* head_blob, const void* maha_blob,
+                      const float* x, int64_t n_windows, int64_t x_window_stride,
+                      float* cls_out        /* (n,128)      */,
+                      float* tokens_out     /* (n,seq,128)  */,
+                      float* logits_out     /* (n,classes)  */,
+                      int64_t* pred_out     /* (n)          */,
+                      float* msp_out        /* (n)  = -max softmax            */,
+                      float* energy_out     /* (n)  = -logsumexp(logits)      */,
+                      float* maha_out       /* (n)  = min_c Mahalanobis^2     */,
+                      int32_t precision, cmhar_stream_t s);
+
+/* Same head + scores from stored features (row-major (n,128) fp32). */
+int cmhar_head_forward(const void* head_blob, const void* maha_blob, const float* feat, int64_t n,
+                       float* logits_out, int64_t* pred_out, float* msp_out, float* energy_out,
+                       float* maha_out, cmhar_stream_t s);
+
+/* MSP / energy from stored logits (spec rows A1, A2; no reference implementation). */
+int cmhar_logit_scores(const float* logits, int64_t n, int32_t classes, float temperature,
+                       int64_t* pred_out, float* msp_out, float* energy_out, cmhar_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense layers (replace nn.Linear / ProjectionHead.forward / F.normalize,
+ *               reference src/models/models.py:213,226-234,288-289)
+ * ------------------------------------------------------------------------------------------ */
+/* blob for y = act(bn(x W^T + b)): folds BN (pass NULL bn_* for none) and transposes. */
+size_t cmhar_linear_blob_bytes(int32_t in_dim, int32_t out_dim);
+int    cmhar_linear_pack(const float* weight /*(out,in)*/, const float* bias /*(out) or NULL*/,
+                         const float* bn_weight, const float* bn_bias, const float* bn_mean,
+                         const float* bn_var, int32_t in_dim, int32_t out_dim, void* blob,
+                         cmhar_stream_t s);
+/* y (n,out) = relu?(x (n,in) @ W'^T + b');  in_dim % 4 == 0, out_dim % 4 == 0 */
+int    cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in_dim,
+                            int32_t out_dim, int32_t relu, float* y, int32_t precision,
+                            cmhar_stream_t s);
+/* rows x / max(||x||_2, 1e-12)   (F.normalize(dim=1), models.py:288-289); in place allowed */
+int    cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmhar_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Video tail (replaces VideoEncoder.forward after the trunk, models.py:210-216:
+ *             adaptive_avg_pool2d -> per-frame Linear -> temporal mean == Linear(mean_{t,h,w}))
+ * ------------------------------------------------------------------------------------------ */
+/* fmap (n*frames, channels, hw) contiguous, dtype bf16 (fmap_is_bf16=1) or fp32 ->
+ * pooled (n, channels) fp32 = mean over frames and hw.  The projection is cmhar_linear_forward. */
+int cmhar_video_pool(const void* fmap, int32_t fmap_is_bf16, int64_t n, int32_t frames,
+                     int32_t channels, int32_t hw, float* pooled, cmhar_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Contrastive similarity (replaces SigmoidContrastiveLoss.forward / InfoNCELoss.forward,
+ *                         reference src/models/losses.py:25-54,67-87)
+ * ------------------------------------------------------------------------------------------ */
+/* a (na,dim), b (nb,dim) fp32.  sim_out (na,nb) = a b^T, optional (NULL = never materialised).
+ * sigmoid_sum_out[0] += sum_ij softplus(-(sim*scale + bias))   (double; caller zeroes it)
+ * row_lse_out (na) / col_lse_out (nb): logsumexp over the row / column of sim*lse_scale; the
+ * column reduction is accumulated as (max, sumexp) pairs in col_work (2*nb floats per row-tile
+ * group, see cmhar_similarity_work_bytes) and finished by the same call.
+ * diag_out (min(na,nb)) = sim_ii * lse_scale.   Any of the outputs may be NULL. */
+size_t cmhar_similarity_work_bytes(int64_t na, int64_t nb);
+int cmhar_similarity(const float* a, const float* b, int64_t na, int64_t nb, int32_t dim,
+                     int64_t diag_offset /* column index of row 0's positive (sharded rows) */,
+                     float* sim_out, float sig_scale, float sig_bias, double* sigmoid_sum_out,
+                     float lse_scale, float* row_lse_out, float* col_lse_out, float* diag_out,
+                     void* work, int32_t precision, cmhar_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Mahalanobis OOD (spec rows A3/A4 -- no reference implementation)
+ * ------------------------------------------------------------------------------------------ */
+/* Accumulates (+=) sufficient statistics of feat (n,128) fp32 with int64 labels:
+ * count (classes) double, sum (classes,128) double, second (128,128) double = sum f f^T.
+ * Rows whose label is outside [0,classes) are skipped.  These three buffers are what the
+ * multi-GPU fit all-reduces over NCCL. */
+int cmhar_maha_accumulate(const float* feat, const int64_t* labels, int64_t n, int32_t classes,
+                          double* count, double* sum, double* second, cmhar_stream_t s);
+/* score (n) = min_c || feat@whiten - mean_whitened_c ||^2 */
+int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float* score,
+                     cmhar_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * AUROC / FPR95 (spec row A5): order-preserving histograms of float scores
+ * ------------------------------------------------------------------------------------------ */
+/* key(score) = monotone uint32 image of the float; bin = (key - key_lo) >> shift, clamped to
+ * [0,bins).  hist (bins) uint64 is accumulated (+=).  min/max keys via cmhar_score_key_range. */
+int cmhar_score_key_range(const float* scores, int64_t n, uint32_t* key_min_max /*[2], caller
+                          initialises to {0xffffffff,0}*/, cmhar_stream_t s);
+int cmhar_score_histogram(const float* scores, int64_t n, uint32_t key_lo, int32_t shift,
+                          int32_t bins, unsigned long long* hist, cmhar_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMHAR_B200_H */

@@ -1,0 +1,178 @@
+"""CPU tests (-m "not gpu"): state_dict/key parity with the reference, the autograd route of the
+drop-in modules against the oracle and the reference goldens, the C-ABI export list, host-side
+metric / ROC / Mahalanobis algebra and the world_size-2 gloo reductions.  No CUDA compute."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import crossmodal_imu_video_ood_har_b200 as cm
+from oracle import ood_spec, oracle, weights as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torch_sd(sd):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+
+
+def _classifier(seed=11, L=250):
+    cfg = cm.default_config(imu_window_size=L)
+    clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg)
+    sd = W.classifier_state(seed, W.Dims(imu_window=L))
+    clf.load_state_dict(_torch_sd(sd), strict=True)          # key + shape parity (Appendix B)
+    return clf, sd
+
+
+def test_state_dict_keys_match_reference_layout():
+    clf, sd = _classifier()
+    assert set(clf.state_dict().keys()) == set(sd.keys())
+    cfg = cm.default_config()
+    model = cm.CrossModalModel(cfg)
+    ref = W.cross_modal_state(31)
+    got = {k for k in model.state_dict() if not k.startswith("video_encoder.backbone")}
+    assert got == set(ref.keys())
+    model.load_state_dict(_torch_sd(ref), strict=True)
+    n_enc = sum(p.numel() for p in clf.imu_encoder.parameters())
+    n_head = sum(p.numel() for p in clf.classifier.parameters())
+    assert (n_enc, n_head) == (808576, 70816)
+
+
+@pytest.mark.parametrize("name", ["imu_classifier_L250_B64.npz", "imu_classifier_L100_B64.npz"])
+def test_autograd_route_matches_reference_golden(golden_dir, name):
+    """eval() with gradients enabled takes the differentiable torch route; it must equal the
+    reference's CPU outputs (this is the route the reference's trainers use)."""
+    g = np.load(os.path.join(golden_dir, name))
+    L = int(g["L"])
+    clf, _ = _classifier(int(g["seed_w"]), L)
+    clf.eval()
+    x = torch.from_numpy(W.imu_windows(int(g["seed_x"]), int(g["B"]), W.Dims(imu_window=L)))
+    logits = clf(x)
+    assert logits.requires_grad
+    np.testing.assert_allclose(logits.detach().numpy(), g["logits"], atol=3e-4, rtol=0)
+    cls, tok = clf.imu_encoder(x[:4])
+    np.testing.assert_allclose(tok.detach().numpy(), g["tokens_first4"], atol=3e-5, rtol=0)
+    logits.sum().backward()
+    assert clf.imu_encoder.patch_embed.projections[0].weight.grad.abs().sum() > 0
+    # dead channels get exactly zero gradient
+    assert clf.imu_encoder.patch_embed.projections[3].weight.grad.abs().sum() == 0
+
+
+def test_train_mode_runs_and_dropout_is_active():
+    clf, _ = _classifier()
+    clf.train()
+    x = torch.from_numpy(W.imu_windows(5, 8))
+    a, b = clf(x), clf(x)
+    assert not torch.allclose(a, b)
+
+
+def test_inference_route_refuses_cpu_tensors():
+    clf, _ = _classifier()
+    clf.eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        clf(torch.zeros(2, 6, 250))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cm.Evaluator(clf, cm.default_config(), device="cpu")
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        cm.InfoNCELoss()(torch.zeros(4, 8), torch.zeros(4, 8))
+
+
+def test_cross_modal_autograd_route_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cross_modal_B48.npz"))
+    cfg = cm.default_config()
+    model = cm.CrossModalModel(cfg)
+    model.load_state_dict(_torch_sd(W.cross_modal_state(int(g["seed_w"]))), strict=True)
+    model.eval()
+    B, T = int(g["B"]), int(g["T"])
+    imu = torch.from_numpy(W.imu_windows(int(g["seed_x"]), B))
+    video = torch.from_numpy(W.video_feature_maps(int(g["seed_v"]), B, T)).view(B, T, 512, 4, 4)
+    ip, vp = model(imu, video)
+    np.testing.assert_allclose(ip.detach().numpy(), g["imu_proj"], atol=3e-5, rtol=0)
+    np.testing.assert_allclose(vp.detach().numpy(), g["video_proj"], atol=3e-5, rtol=0)
+    sig = cm.SigmoidContrastiveLoss()(ip, vp)
+    nce = cm.InfoNCELoss()(ip, vp)
+    assert abs(float(sig) - float(g["sigmoid_loss"])) < 1e-4
+    assert abs(float(nce) - float(g["info_nce_loss"])) < 1e-4
+    assert {"temperature", "bias"} <= set(dict(cm.SigmoidContrastiveLoss().named_parameters()))
+
+
+def test_module_lifecycle_deepcopy_and_unknown_backbone():
+    clf, _ = _classifier()
+    twin = copy.deepcopy(clf)                                   # main.py:166-167
+    assert twin._packed == {} and twin.imu_encoder._packed is not clf.imu_encoder._packed
+    assert not clf.freeze_encoder
+    frozen = cm.IMUClassifier(cm.IMUEncoder(cm.default_config()), cm.default_config(), freeze_encoder=True)
+    assert frozen.freeze_encoder
+    frozen.unfreeze_encoder()
+    assert not frozen.freeze_encoder
+    with pytest.raises(ValueError, match="Backbone inconnu"):   # src/models/models.py:176
+        cm.VideoEncoder(cm.default_config(video_backbone="vgg"))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cmhar_b200.h")).read()
+    declared = set(re.findall(r"\b(cmhar_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(cm._native.EXPORTED), declared ^ set(cm._native.EXPORTED)
+    lib = ctypes.CDLL(cm._native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert cm._native.lib().cmhar_abi_version() == 1
+    # argument validation happens before any CUDA call
+    assert cm._native.lib().cmhar_imu_encoder_blob_bytes(16, 4) > 3_000_000
+    assert cm._native.lib().cmhar_imu_encoder_blob_bytes(17, 4) == 0
+    assert cm._native.lib().cmhar_head_blob_bytes(256, 128, 32) > 0
+    rc = cm._native.lib().cmhar_imu_forward(None, None, None, None, 4, 1500, *([None] * 7), 0, None)
+    assert rc == -1 and b"null" in cm._native.lib().cmhar_last_error()
+
+
+def test_classification_metrics_match_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "evaluator_n200.npz"))
+    m = cm.classification_metrics(g["labels"], g["preds"])
+    for k, v in zip(g["metric_names"], g["metrics"]):
+        assert abs(m[str(k)] - float(v)) < 1e-9
+    rs = np.random.RandomState(int(g["m2_seed"]))
+    yt = rs.randint(0, 32, size=5000)
+    yp = np.where(rs.rand(5000) < 0.7, yt, rs.randint(0, 30, size=5000))
+    m2 = cm.classification_metrics(yt, yp)
+    for k, v in zip(sorted(m2), g["m2"]):
+        assert abs(m2[k] - float(v)) < 1e-9
+
+
+def test_roc_from_histograms_against_spec():
+    rs = np.random.RandomState(2)
+    a = np.round(rs.standard_normal(4000) * 8) / 8              # heavily tied scores
+    b = np.round((rs.standard_normal(3000) + 1.2) * 8) / 8
+    edges = np.unique(np.r_[a, b])
+    ha = np.array([(a == e).sum() for e in edges])
+    hb = np.array([(b == e).sum() for e in edges])
+    r = cm.roc_from_histograms(ha, hb)
+    assert abs(r["auroc"] - ood_spec.auroc(a, b)) < 1e-12       # one distinct value per bin: exact
+    assert abs(r["fpr"] - ood_spec.fpr_at_tpr(a, b)) < 1e-12
+    # coarse bins: the reported bound really bounds the error
+    ha2, hb2 = ha.reshape(-1, 1)[: len(ha) // 4 * 4].reshape(-1, 4).sum(1), hb[: len(hb) // 4 * 4].reshape(-1, 4).sum(1)
+    keep = len(ha) // 4 * 4
+    a2, b2 = a[np.isin(a, edges[:keep])], b[np.isin(b, edges[:keep])]
+    r2 = cm.roc_from_histograms(ha2, hb2)
+    assert abs(r2["auroc"] - ood_spec.auroc(a2, b2)) <= r2["auroc_bound"] + 1e-12
+    assert abs(r2["fpr"] - ood_spec.fpr_at_tpr(a2, b2)) <= r2["fpr_bound"] + 1e-12
+
+
+def test_finalize_mahalanobis_against_spec():
+    f, y = W.class_features(3, 3000)
+    n, s, ff = ood_spec.mahalanobis_sufficient_stats(f, y, 32)
+    got = cm.finalize_mahalanobis(n, s, ff)
+    want = ood_spec.mahalanobis_finalize(n, s, ff)
+    np.testing.assert_allclose(got["mean"], want["mean"], atol=1e-12)
+    np.testing.assert_allclose(got["whiten"] @ got["whiten"].T, want["precision"], rtol=1e-8, atol=1e-10)
+
+
+def test_shard_bounds_cover_everything_once():
+    for n, w in ((10, 3), (1_000_003, 8), (5, 8), (0, 2)):
+        spans = [cm.shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
