@@ -267,7 +267,7 @@ def imu_forward_native(encoder: "IMUEncoder", head_blob: Optional[torch.Tensor],
         stride = x.numel()
     # tokens kept = min(1 + C*N, len(pos_encoding)) = min(1 + N, len(pos_encoding))  (F4)
     S = encoder._check_native_dims(L)
-    if stride < 16 * (S - 1):
+    if B > 0 and stride < 16 * (S - 1):
         raise ValueError(f"window stride {stride} shorter than the {16 * (S - 1)} live samples")
     dev = x.device
     blob = encoder.packed_blob(dev, S)
