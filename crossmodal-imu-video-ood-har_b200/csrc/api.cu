@@ -5,6 +5,7 @@ namespace cmhar {
 int launch_imu_forward_fp32(const FwdArgs& a, cudaStream_t stream);
 int launch_imu_forward_bf16(const FwdArgs& a, cudaStream_t stream);
 int launch_head_forward(const FwdArgs& a, cudaStream_t stream);
+int launch_imu_forward_bf16_debug(const FwdArgs& a, int stage, float* dump, int* progress, cudaStream_t stream);
 }  // namespace cmhar
 
 using namespace cmhar;
@@ -15,6 +16,7 @@ int cmhar_imu_forward(const void* encoder_blob, const void* head_blob, const voi
                       int64_t n_windows, int64_t x_window_stride, float* cls_out, float* tokens_out,
                       float* logits_out, int64_t* pred_out, float* msp_out, float* energy_out, float* maha_out,
                       int32_t precision, cmhar_stream_t s) {
+    if (n_windows <= 0) return CMHAR_OK;
     CMHAR_REQUIRE(encoder_blob && x, "cmhar_imu_forward: null encoder blob or input");
     CMHAR_REQUIRE(((uintptr_t)encoder_blob & 1023) == 0, "encoder blob must be 1024-byte aligned");
     CMHAR_REQUIRE(head_blob || !(logits_out || pred_out || msp_out || energy_out),
@@ -33,6 +35,17 @@ int cmhar_imu_forward(const void* encoder_blob, const void* head_blob, const voi
     a.msp_out = msp_out; a.energy_out = energy_out; a.maha_out = maha_out;
     if (precision == CMHAR_BF16) return launch_imu_forward_bf16(a, (cudaStream_t)s);
     return launch_imu_forward_fp32(a, (cudaStream_t)s);
+}
+
+int cmhar_debug_imu_bf16(const void* encoder_blob, const float* x, int64_t n_windows, int64_t x_window_stride,
+                         int32_t stage, float* residual_dump, float* cls_out, int32_t* progress_host_mapped,
+                         cmhar_stream_t s) {
+    CMHAR_REQUIRE(encoder_blob && x && residual_dump, "cmhar_debug_imu_bf16: null argument");
+    if (n_windows <= 0) return CMHAR_OK;
+    FwdArgs a{};
+    a.enc_blob = reinterpret_cast<const char*>(encoder_blob);
+    a.x = x; a.n = n_windows; a.xstride = x_window_stride; a.cls_out = cls_out;
+    return launch_imu_forward_bf16_debug(a, stage, residual_dump, progress_host_mapped, (cudaStream_t)s);
 }
 
 int cmhar_head_forward(const void* head_blob, const void* maha_blob, const float* feat, int64_t n, float* logits_out,

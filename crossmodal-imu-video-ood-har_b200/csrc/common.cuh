@@ -69,7 +69,7 @@ struct EncLayout {
     static constexpr size_t l_ln2 = l_ln1 + 2 * D;
     static constexpr size_t layer_floats = l_ln2 + 2 * D;
     static constexpr size_t header_ints = 8;      // [magic, seq, layers, ...] stored as int32 in front
-    static constexpr size_t fp32_floats(int layers) { return layers0 + (size_t)layers * layer_floats; }
+    __host__ __device__ static constexpr size_t fp32_floats(int layers) { return layers0 + (size_t)layers * layer_floats; }
 };
 constexpr uint32_t ENC_MAGIC = 0x434d4831u;   // "CMH1"
 constexpr uint32_t HEAD_MAGIC = 0x434d4832u;

@@ -1,20 +1,759 @@
-// imu_encoder_bf16.cu -- bf16 tcgen05/TMEM path of the fused IMU encoder (placeholder until the
-// tensor-core megakernel lands; the call fails loudly instead of silently using another path).
+// imu_encoder_bf16.cu -- bf16 tcgen05 / TMEM path of the fused IMU encoder (the throughput path,
+// 2e-2 contract).  Same algebra as imu_encoder_fp32.cu (reference src/models/models.py:30-50,
+// 100-132,328-339; torch/nn/modules/transformer.py:946-990), re-mapped onto 5th-gen tensor cores:
+//
+//   * one CTA owns a tile of 8 windows = 128 token rows (window w -> rows 16w..16w+15; for
+//     seq < 16 the tail rows of each 16-row group are padding, masked out of the softmax);
+//   * every GEMM is a chain of tcgen05.mma (M=128, K=16, bf16 in, fp32 accumulate in TMEM) issued
+//     by ONE thread; operands are K-major SWIZZLE_128B tiles in shared memory;
+//   * weights are pre-swizzled at pack time into 16 KiB chunks ([128 rows x 64 k] bf16) stored
+//     in consumption order, streamed L2 -> smem with cp.async.bulk (TMA engine, UBLKCP) through a
+//     4-stage mbarrier ring;
+//   * attention runs on the tensor cores too: per head S = Q_h K_h^T over the whole tile
+//     (128x128x16, cross-window entries ignored), softmax on the 16x16 diagonal blocks in
+//     registers, P (block-diagonal, bf16) back to smem, O_h = P V_h as eight 128x16x16 MMAs against
+//     V^T (V^T comes out of the QKV phase directly: V^T = W_v h^T, weights as the A operand);
+//   * the fp32 residual stream never leaves TMEM: LayerNorm epilogues write (LN(x) + next bias)
+//     back into the accumulator columns and the next GEMM accumulates on top of it;
+//   * TMEM map (512 columns): A=[0,128) B=[128,256) C=[256,384) scratch accumulators,
+//     R=[384,512) residual/accumulator.
+//
+// Roles: warps 0-7 epilogue (thread = (row, column half)), warp 8 lane 0 = MMA issuer,
+// warp 9 lane 0 = weight producer.
 #include "common.cuh"
 
 namespace cmhar {
+namespace tc {
 
-size_t encoder_bf16_bytes(int layers) { (void)layers; return 0; }
+constexpr int CHUNK = 16384;                 // bytes of one [128 x 64] bf16 SW128 chunk
+constexpr int NSTAGE = 4;
+constexpr int CHUNKS_PER_LAYER = 24;
+constexpr int NT_EPI = 256, NT_TC = 320;
+constexpr int MMA_WARP = 8, LOAD_WARP = 9;
+
+// shared memory map (bytes)
+constexpr int OFF_HA = 0;                    // h as bf16 A/B operand          [128 x 128]  2 chunks
+constexpr int OFF_Q = 32768;                 // Q (later O, hidden chunk 0)    [128 x 128]
+constexpr int OFF_K = 65536;                 // K (hidden chunk 1)
+constexpr int OFF_VT = 98304;                // V^T (hidden chunk 2)
+constexpr int OFF_P = 131072;                // P block-diagonal (hidden chunk 3)
+constexpr int OFF_W = 163840;                // weight ring, NSTAGE chunks
+constexpr int OFF_STAT = OFF_W + NSTAGE * CHUNK;   // LN partial stats [2][128] float2 = 2 KiB
+constexpr int OFF_BAR = OFF_STAT + 2048;     // mbarriers (8 B each) + tmem pointer
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB");
+
+// barrier indices
+enum {
+    B_WFULL = 0,                 // [NSTAGE]
+    B_WEMPTY = B_WFULL + NSTAGE, // [NSTAGE]
+    B_ACC = B_WEMPTY + NSTAGE,   // [4] accumulator buffer A,B,C,R complete (tcgen05.commit)
+    B_HA = B_ACC + 4,            // hA (+R) written by the epilogue        (256)
+    B_QKV = B_HA + 1,            // Q,K,V^T in smem, P zeroed              (256)
+    B_SFREE = B_QKV + 1,         // [2] S buffer drained                   (128)
+    B_PREADY = B_SFREE + 2,      // P_h written                            (128)
+    B_PFREE = B_PREADY + 1,      // PV_h done reading P                    (commit)
+    B_O = B_PFREE + 1,           // O in smem                              (256)
+    B_HID = B_O + 1,             // [4] hidden chunk c in smem             (256)
+    B_COUNT = B_HID + 4          // one barrier per chunk: a waiter may never fall two phases behind
+};
+static_assert(B_COUNT * 8 + 8 <= 256, "barrier area too small");
+
+constexpr uint32_t TM_A = 0, TM_B = 128, TM_C = 256, TM_R = 384;
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 22)) {       // watchdog: a protocol bug must fail loudly, never hang the GPU
+            if (spins == (1u << 22) + 1 && (threadIdx.x & 31) == 0 && blockIdx.x == 0)
+                printf("cmhar bf16 kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u site %d)\n",
+                       (int)blockIdx.x, (int)threadIdx.x, (bar & 0xffu) >> 3, parity, site);
+            if (spins > (1u << 26)) __trap();
+        }
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major SWIZZLE_128B
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 [0,14) | LBO=1 [16,30) | SBO=1024>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor, kind::f16: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define TMEM_LD32(addr, v)                                                                                        \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                        \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25," \
+                 "%26,%27,%28,%29,%30,%31}, [%32];"                                                               \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),       \
+                   "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),     \
+                   "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),     \
+                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                          \
+                 : "r"(addr)                                                                                      \
+                 : "memory")
+
+#define TMEM_ST32(addr, v)                                                                                        \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                  \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26," \
+                 "%27,%28,%29,%30,%31,%32};"                                                                      \
+                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
+                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
+                   "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), \
+                   "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), \
+                   "r"(v[31])                                                                                     \
+                 : "memory")
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// byte offset of the 16-byte piece holding columns [8j, 8j+8) of row r inside a [128 x 64] SW128 chunk
+__device__ __forceinline__ uint32_t sw128_off(int r, int j) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+}
+
+// store 32 consecutive columns (fp32 in v, already finished) of row r as bf16 into chunk `chunk_base`
+// at 16-byte pieces j0..j0+3
+__device__ __forceinline__ void store_bf16_32(uint8_t* chunk_base, int r, int j0, const float* v) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+        u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+        u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+        u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+        *reinterpret_cast<uint4*>(chunk_base + sw128_off(r, j0 + q)) = u;
+    }
+}
+
+struct Phase {       // parity bookkeeping: one bit per barrier index
+    uint32_t bits = 0;
+    __device__ __forceinline__ uint32_t next(int i) { const uint32_t p = (bits >> i) & 1u; bits ^= (1u << i); return p; }
+};
+
+}  // namespace tc
+
+using namespace tc;
+
+struct Bf16Args {
+    FwdArgs f;
+    int dbg_stage;          // <0: off; else dump the residual (fp32 [128][128] per tile) after that stage
+    float* dbg_out;
+    volatile int* progress; // debug: host-mapped [grid][16] progress codes (survive a trap), or null
+};
+
+// ======================================================================================== kernel
+__global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Args args) {
+    extern __shared__ __align__(1024) uint8_t smem_tc[];
+    uint8_t* const smem = smem_tc;
+    const FwdArgs& a = args.f;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const BlobHeader* eh = reinterpret_cast<const BlobHeader*>(a.enc_blob);
+    const int S = eh->a, n_layers = eh->b;
+    const float* encf = reinterpret_cast<const float*>(a.enc_blob + 1024);
+    const size_t fp32_bytes = (EncLayout::fp32_floats(n_layers) * sizeof(float) + 1023) / 1024 * 1024;
+    const uint8_t* wchunks = reinterpret_cast<const uint8_t*>(a.enc_blob) + 1024 + fp32_bytes;
+    const int n_chunks = 1 + n_layers * CHUNKS_PER_LAYER;
+    const long long tiles = (a.n + 7) / 8;
+
+#define PROG(code) do { if (args.progress && lane == 0) { args.progress[blockIdx.x * 16 + warp] = (code); __threadfence_system(); } } while (0)
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + OFF_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * B_COUNT);
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(BAR(B_WFULL + s), 1); mbar_init(BAR(B_WEMPTY + s), 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(BAR(B_ACC + i), 1);
+        mbar_init(BAR(B_HA), NT_EPI);
+        mbar_init(BAR(B_QKV), NT_EPI);
+        mbar_init(BAR(B_SFREE), 128);
+        mbar_init(BAR(B_SFREE + 1), 128);
+        mbar_init(BAR(B_PREADY), 128);
+        mbar_init(BAR(B_PFREE), 1);
+        mbar_init(BAR(B_O), NT_EPI);
+        for (int i = 0; i < 4; ++i) mbar_init(BAR(B_HID + i), NT_EPI);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == LOAD_WARP) {
+        // ================================================================= weight producer
+        if (lane == 0) {
+            uint32_t stage = 0, parity = 1;           // fresh barriers: waiting on parity 1 passes
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                for (int c = 0; c < n_chunks; ++c) {
+                    PROG(1); mbar_wait(BAR(B_WEMPTY + stage), parity, 1);
+                    mbar_expect_tx(BAR(B_WFULL + stage), CHUNK);
+                    bulk_g2s(sbase + OFF_W + stage * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(B_WFULL + stage));
+                    if (++stage == NSTAGE) { stage = 0; parity ^= 1; }
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            Phase ph;
+            uint32_t wstage = 0, wparity = 0;
+            constexpr uint32_t ID128 = idesc_bf16(128, 128), ID16 = idesc_bf16(128, 16);
+            const uint64_t dHA = sw128_desc(sbase + OFF_HA), dQ = sw128_desc(sbase + OFF_Q), dK = sw128_desc(sbase + OFF_K),
+                           dVT = sw128_desc(sbase + OFF_VT), dP = sw128_desc(sbase + OFF_P);
+            // one weight chunk = 64 k-columns = 4 MMAs of K=16.  `w_is_a`: weights are the A operand.
+            auto gemm_chunk = [&](uint32_t d, uint64_t other_desc, bool w_is_a, bool first_acc, int ksteps) {
+                PROG(2); mbar_wait(BAR(B_WFULL + wstage), wparity, 2);
+                tc_fence_after();
+                const uint64_t dW = sw128_desc(sbase + OFF_W + wstage * CHUNK);
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t wa = dW + (uint64_t)(2 * k), oa = other_desc + (uint64_t)(2 * k);
+                    umma(d, w_is_a ? wa : oa, w_is_a ? oa : wa, ID128, (first_acc || k > 0) ? 1u : 0u);
+                }
+                tc_commit(BAR(B_WEMPTY + wstage));
+                if (++wstage == NSTAGE) { wstage = 0; wparity ^= 1; }
+            };
+            const uint64_t CH = CHUNK >> 4;      // descriptor units per chunk
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                // ---- patch embedding: R(tok_bias) += patches(16 k) * Wp^T
+                PROG(3); mbar_wait(BAR(B_HA), ph.next(B_HA), 3);
+                tc_fence_after();
+                gemm_chunk(tmem + TM_R, dHA, false, true, 3);
+                tc_commit(BAR(B_ACC + 3));
+                for (int l = 0; l < n_layers; ++l) {
+                    // ---- Q, K (A = hA, B = W) and V^T (A = W_v, B = hA)
+                    PROG(4); mbar_wait(BAR(B_HA), ph.next(B_HA), 4);
+                    tc_fence_after();
+                    gemm_chunk(tmem + TM_A, dHA, false, false, 4);
+                    gemm_chunk(tmem + TM_A, dHA + CH, false, true, 4);
+                    tc_commit(BAR(B_ACC + 0));
+                    gemm_chunk(tmem + TM_B, dHA, false, false, 4);
+                    gemm_chunk(tmem + TM_B, dHA + CH, false, true, 4);
+                    tc_commit(BAR(B_ACC + 1));
+                    gemm_chunk(tmem + TM_C, dHA, true, false, 4);
+                    gemm_chunk(tmem + TM_C, dHA + CH, true, true, 4);
+                    tc_commit(BAR(B_ACC + 2));
+                    // ---- attention
+                    PROG(5); mbar_wait(BAR(B_QKV), ph.next(B_QKV), 5);
+                    tc_fence_after();
+                    auto issue_S = [&](int h) {      // S_h = Q_h K_h^T into buffer (h&1)
+                        const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)((h & 3) * 2);
+                        umma(tmem + ((h & 1) ? TM_B : TM_A), dQ + off, dK + off, ID128, 0u);
+                        tc_commit(BAR(B_ACC + (h & 1)));
+                    };
+                    issue_S(0);
+                    issue_S(1);
+                    for (int h = 0; h < H; ++h) {
+                        PROG(6); mbar_wait(BAR(B_PREADY), ph.next(B_PREADY), 6);
+                        tc_fence_after();
+                        for (int j = 0; j < 8; ++j) {     // O[:,16h..] (+)= P[:,16j..16j+15] * V^T_h[:,16j..]^T
+                            const uint64_t koff = (uint64_t)(j >> 2) * CH + (uint64_t)((j & 3) * 2);
+                            umma(tmem + TM_C + 16 * h, dP + koff, dVT + koff + (uint64_t)(h * 2 * 64), ID16, j > 0 ? 1u : 0u);
+                        }
+                        tc_commit(BAR(B_PFREE));
+                        PROG(7); mbar_wait(BAR(B_SFREE + (h & 1)), ph.next(B_SFREE + (h & 1)), 7);   // S_h drained
+                        tc_fence_after();
+                        if (h + 2 < H) issue_S(h + 2);
+                    }
+                    tc_commit(BAR(B_ACC + 2));            // O complete
+                    // ---- out-proj: R(h + b_o) += O * W_o^T
+                    PROG(8); mbar_wait(BAR(B_O), ph.next(B_O), 8);
+                    tc_fence_after();
+                    gemm_chunk(tmem + TM_R, dQ, false, true, 4);
+                    gemm_chunk(tmem + TM_R, dQ + CH, false, true, 4);
+                    tc_commit(BAR(B_ACC + 3));
+                    // ---- FFN: hidden chunk c -> buffers A,B,C,A ; R(h1 + b_2) += hidden_c * W_2[:,c]^T
+                    PROG(9); mbar_wait(BAR(B_HA), ph.next(B_HA), 9);
+                    tc_fence_after();
+                    for (int c = 0; c < 3; ++c) {
+                        gemm_chunk(tmem + 128 * c, dHA, false, false, 4);
+                        gemm_chunk(tmem + 128 * c, dHA + CH, false, true, 4);
+                        tc_commit(BAR(B_ACC + c));
+                    }
+                    for (int c = 0; c < 4; ++c) {
+                        PROG(10); mbar_wait(BAR(B_HID + c), ph.next(B_HID + c), 10);     // hidden chunk c in smem (and its TMEM buffer drained)
+                        tc_fence_after();
+                        const uint64_t dHid = sw128_desc(sbase + OFF_Q + c * 32768);
+                        gemm_chunk(tmem + TM_R, dHid, false, true, 4);
+                        gemm_chunk(tmem + TM_R, dHid + CH, false, true, 4);
+                        if (c == 0) {                              // 4th FFN1 chunk reuses buffer A
+                            gemm_chunk(tmem + TM_A, dHA, false, false, 4);
+                            gemm_chunk(tmem + TM_A, dHA + CH, false, true, 4);
+                            tc_commit(BAR(B_ACC + 0));
+                        }
+                    }
+                    tc_commit(BAR(B_ACC + 3));
+                }
+            }
+        }
+    } else {
+        // ================================================================= epilogue (warps 0-7)
+        const int wg = warp >> 2;                          // column half / head parity
+        const int row = (warp & 3) * 32 + lane;            // token row == TMEM lane
+        const int win = row >> 4, tok = row & 15;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const int c0 = wg * 64;                            // this thread's 64 columns of a 128-wide buffer
+        float2* stats = reinterpret_cast<float2*>(smem + OFF_STAT);
+        Phase ph;
+        uint32_t v[32];
+        float f[32];
+
+        // finish a 128-wide fp32 row held in R: y -> hA (bf16), y + next_bias -> R
+        auto write_h = [&](const float* y32, int cc, const float* next_bias) {
+            store_bf16_32(smem + OFF_HA + wg * CHUNK, row, (cc & 63) >> 3, y32);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 nb = __ldg(reinterpret_cast<const float4*>(next_bias + c0 + cc + i));
+                v[i] = __float_as_uint(y32[i] + nb.x); v[i + 1] = __float_as_uint(y32[i + 1] + nb.y);
+                v[i + 2] = __float_as_uint(y32[i + 2] + nb.z); v[i + 3] = __float_as_uint(y32[i + 3] + nb.w);
+            }
+            TMEM_ST32(lane_base + TM_R + c0 + cc, v);
+        };
+        // LayerNorm of the residual row in R (two threads per row exchange partial sums through smem)
+        auto layer_norm_R = [&](const float* gb, const float* next_bias, bool write_back, float* keep /*64 floats or null*/) {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 64; cc += 32) {
+                TMEM_LD32(lane_base + TM_R + c0 + cc, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { const float x = __uint_as_float(v[i]); s1 += x; s2 = fmaf(x, x, s2); }
+            }
+            stats[wg * 128 + row] = make_float2(s1, s2);
+            epi_bar();
+            const float2 o = stats[(wg ^ 1) * 128 + row];
+            const float mean = (s1 + o.x) * (1.f / D);
+            const float var = fmaxf((s2 + o.y) * (1.f / D) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + LN_EPS);
+#pragma unroll
+            for (int cc = 0; cc < 64; cc += 32) {
+                TMEM_LD32(lane_base + TM_R + c0 + cc, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gb + c0 + cc + i));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(gb + D + c0 + cc + i));
+                    f[i] = (__uint_as_float(v[i]) - mean) * rstd * g.x + b.x;
+                    f[i + 1] = (__uint_as_float(v[i + 1]) - mean) * rstd * g.y + b.y;
+                    f[i + 2] = (__uint_as_float(v[i + 2]) - mean) * rstd * g.z + b.z;
+                    f[i + 3] = (__uint_as_float(v[i + 3]) - mean) * rstd * g.w + b.w;
+                }
+                if (keep) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) keep[cc + i] = f[i];
+                }
+                if (write_back) write_h(f, cc, next_bias);
+            }
+            epi_bar();          // stats buffer reusable
+        };
+        auto publish = [&](int bar_idx) {   // make generic-proxy smem writes + TMEM accesses visible, then arrive
+            tc_wait_st();
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(BAR(bar_idx));
+        };
+        auto dump_R = [&](long long tile_idx) {
+            float* dst = args.dbg_out + ((size_t)tile_idx * 128 + row) * D + c0;
+#pragma unroll
+            for (int cc = 0; cc < 64; cc += 32) {
+                TMEM_LD32(lane_base + TM_R + c0 + cc, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dst[cc + i] = __uint_as_float(v[i]);
+            }
+        };
+
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const long long w0 = tile * 8;
+            // ---- stage patches (bf16, k = 16 -> pieces 0,1 of chunk 0 of hA) and preload R = tok_bias
+            if (wg == 0) {
+                float p16[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) p16[i] = 0.f;
+                if (tok > 0 && tok < S && w0 + win < a.n) {
+                    const float* src = a.x + (w0 + win) * a.xstride + (tok - 1) * P;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) p16[i] = __ldg(src + i);
+                }
+                // K = 48 split-precision patch GEMM: [x_hi | x_lo | x_hi] . [Wp_hi | Wp_hi | Wp_lo]^T
+                float lo16[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float hi = __bfloat162float(__float2bfloat16_rn(p16[i]));
+                    lo16[i] = p16[i] - hi;
+                }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const float* srcv = (q == 2 || q == 3) ? lo16 : p16;
+                    const int o = (q & 1) * 8;
+                    uint4 u;
+                    u.x = pack_bf16(srcv[o + 0], srcv[o + 1]); u.y = pack_bf16(srcv[o + 2], srcv[o + 3]);
+                    u.z = pack_bf16(srcv[o + 4], srcv[o + 5]); u.w = pack_bf16(srcv[o + 6], srcv[o + 7]);
+                    *reinterpret_cast<uint4*>(smem + OFF_HA + sw128_off(row, q)) = u;
+                }
+            }
+            {
+                const float* tb = encf + EncLayout::tok_bias + (tok < S ? tok : 0) * D + c0;
+#pragma unroll
+                for (int cc = 0; cc < 64; cc += 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(tb + cc + i));
+                        v[i] = __float_as_uint(t.x); v[i + 1] = __float_as_uint(t.y);
+                        v[i + 2] = __float_as_uint(t.z); v[i + 3] = __float_as_uint(t.w);
+                    }
+                    TMEM_ST32(lane_base + TM_R + c0 + cc, v);
+                }
+            }
+            publish(B_HA);
+            // ---- h0 = R ; hA = bf16(h0) ; R = h0 + b_o(layer 0)
+            PROG(11); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 11);
+            tc_fence_after();
+            {
+                const float* L0 = encf + EncLayout::layers0;
+#pragma unroll
+                for (int cc = 0; cc < 64; cc += 32) {
+                    TMEM_LD32(lane_base + TM_R + c0 + cc, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    write_h(f, cc, L0 + EncLayout::l_b_o);
+                }
+            }
+            if (args.dbg_stage == 0) { tc_wait_st(); dump_R(tile); }
+            publish(B_HA);
+
+            for (int l = 0; l < n_layers; ++l) {
+                const float* L = encf + EncLayout::layers0 + (size_t)l * EncLayout::layer_floats;
+                const bool last = (l + 1 == n_layers);
+                // ---- drain Q, K (bias per column) and V^T (bias per lane) into smem as bf16
+#pragma unroll 1
+                for (int m = 0; m < 3; ++m) {
+                    PROG(12); mbar_wait(BAR(B_ACC + m), ph.next(B_ACC + m), 12);
+                    tc_fence_after();
+                    uint8_t* dst = smem + OFF_Q + m * 32768 + wg * CHUNK;
+                    const float bv = (m == 2) ? __ldg(L + EncLayout::l_b_in + 2 * D + row) : 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < 64; cc += 32) {
+                        TMEM_LD32(lane_base + 128 * m + c0 + cc, v);
+                        tc_wait_ld();
+                        if (m < 2) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(L + EncLayout::l_b_in + m * D + c0 + cc + i));
+                                f[i] = __uint_as_float(v[i]) + b.x; f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
+                                f[i + 2] = __uint_as_float(v[i + 2]) + b.z; f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + bv;
+                        }
+                        store_bf16_32(dst, row, cc >> 3, f);
+                    }
+                }
+                // zero P (block-diagonal operand; this thread clears its half-row except its own block)
+                {
+                    const uint4 z = make_uint4(0, 0, 0, 0);
+                    uint8_t* pc = smem + OFF_P + wg * CHUNK;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(pc + sw128_off(row, j)) = z;
+                }
+                PROG(100 + l);
+                publish(B_QKV);
+                // ---- softmax of head h on the 16x16 diagonal block; wg handles heads of its parity
+#pragma unroll 1
+                for (int h = wg; h < H; h += 2) {
+                    PROG(13); mbar_wait(BAR(B_ACC + wg), ph.next(B_ACC + wg), 13);
+                    tc_fence_after();
+                    TMEM_LD32(lane_base + 128 * wg + (warp & 3) * 32, v);     // keys 32q..32q+31 = this warp's two windows
+                    tc_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(BAR(B_SFREE + wg));
+                    float s[16];
+                    const bool hi = (lane >= 16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s[i] = __uint_as_float(hi ? v[16 + i] : v[i]);
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { if (i >= S) s[i] = -INFINITY; m = fmaxf(m, s[i]); }
+                    float den = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { s[i] = __expf(s[i] - m); den += s[i]; }
+                    const float inv = 1.f / den;
+                    uint4 u0, u1;
+                    u0.x = pack_bf16(s[0] * inv, s[1] * inv); u0.y = pack_bf16(s[2] * inv, s[3] * inv);
+                    u0.z = pack_bf16(s[4] * inv, s[5] * inv); u0.w = pack_bf16(s[6] * inv, s[7] * inv);
+                    u1.x = pack_bf16(s[8] * inv, s[9] * inv); u1.y = pack_bf16(s[10] * inv, s[11] * inv);
+                    u1.z = pack_bf16(s[12] * inv, s[13] * inv); u1.w = pack_bf16(s[14] * inv, s[15] * inv);
+                    if (h > 0) mbar_wait(BAR(B_PFREE), (uint32_t)((h - 1) & 1), 14);   // PV_{h-1} finished reading P
+                    uint8_t* pc = smem + OFF_P + (win >> 2) * CHUNK;
+                    *reinterpret_cast<uint4*>(pc + sw128_off(row, (win & 3) * 2)) = u0;
+                    *reinterpret_cast<uint4*>(pc + sw128_off(row, (win & 3) * 2 + 1)) = u1;
+                    fence_async_smem();
+                    mbar_arrive(BAR(B_PREADY));
+                }
+                // ---- O (buffer C) -> smem (Q region) as bf16
+                PROG(15); mbar_wait(BAR(B_ACC + 2), ph.next(B_ACC + 2), 15);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 64; cc += 32) {
+                    TMEM_LD32(lane_base + TM_C + c0 + cc, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    store_bf16_32(smem + OFF_Q + wg * CHUNK, row, cc >> 3, f);
+                }
+                publish(B_O);
+                // ---- LN1: h1 = LN(R) ; hA = bf16(h1) ; R = h1 + b_2
+                PROG(16); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 16);
+                tc_fence_after();
+                layer_norm_R(L + EncLayout::l_ln1, L + EncLayout::l_b2, true, nullptr);
+                if (args.dbg_stage == 1 && l == 0) { tc_wait_st(); dump_R(tile); }
+                publish(B_HA);
+                // ---- FFN1 chunks: relu(acc + b_1) -> hidden chunk c (bf16)
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int buf = (c == 3) ? 0 : c;
+                    PROG(17); mbar_wait(BAR(B_ACC + buf), ph.next(B_ACC + buf), 17);
+                    PROG(170 + c);
+                    tc_fence_after();
+#pragma unroll
+                    for (int cc = 0; cc < 64; cc += 32) {
+                        TMEM_LD32(lane_base + 128 * buf + c0 + cc, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(L + EncLayout::l_b1 + c * 128 + c0 + cc + i));
+                            f[i] = fmaxf(__uint_as_float(v[i]) + b.x, 0.f); f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
+                            f[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f); f[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
+                        }
+                        store_bf16_32(smem + OFF_Q + c * 32768 + wg * CHUNK, row, cc >> 3, f);
+                    }
+                    PROG(180 + c);
+                    publish(B_HID + c);
+                    PROG(190 + c);
+                }
+                // ---- LN2: h2 = LN(R) ; hA = bf16(h2) ; R = h2 + b_o(next layer)
+                PROG(18); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 18);
+                tc_fence_after();
+                if (!last) {
+                    layer_norm_R(L + EncLayout::l_ln2, L + EncLayout::layer_floats + EncLayout::l_b_o, true, nullptr);
+                    if (args.dbg_stage == 2 && l == 0) { tc_wait_st(); dump_R(tile); }
+                    publish(B_HA);
+                } else {
+                    // last layer: LN2 then the encoder's final LayerNorm (models.py:127), fp32 in registers
+                    float y[64];
+                    layer_norm_R(L + EncLayout::l_ln2, nullptr, false, y);
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) { s1 += y[i]; s2 = fmaf(y[i], y[i], s2); }
+                    stats[wg * 128 + row] = make_float2(s1, s2);
+                    epi_bar();
+                    const float2 o = stats[(wg ^ 1) * 128 + row];
+                    const float mean = (s1 + o.x) * (1.f / D);
+                    const float rstd = rsqrtf(fmaxf((s2 + o.y) * (1.f / D) - mean * mean, 0.f) + LN_EPS);
+                    const float* gb = encf + EncLayout::final_ln;
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) y[i] = (y[i] - mean) * rstd * __ldg(gb + c0 + i) + __ldg(gb + D + c0 + i);
+                    const bool valid = (w0 + win < a.n);
+                    if (a.tokens_out && valid && tok < S) {
+                        float4* dst = reinterpret_cast<float4*>(a.tokens_out + ((w0 + win) * S + tok) * D + c0);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                    }
+                    // CLS rows -> head scratch in the (now dead) Q region: feat [8][128] fp32
+                    float* feat = reinterpret_cast<float*>(smem + OFF_Q);
+                    if (tok == 0) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            reinterpret_cast<float4*>(feat + win * D + c0)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                        if (a.cls_out && valid) {
+                            float4* dst = reinterpret_cast<float4*>(a.cls_out + (w0 + win) * D + c0);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                        }
+                    }
+                    epi_bar();
+                }
+            }
+            // ---- classifier head + scores (fp32 CUDA cores, shared with the fp32 path) on the 8 CLS rows
+            {
+                const float* head = nullptr;
+                const float* maha = nullptr;
+                HeadLayout hl{0, 0, 0};
+                MahaLayout ml{0};
+                if (a.head_blob) {
+                    const BlobHeader* hh = reinterpret_cast<const BlobHeader*>(a.head_blob);
+                    hl = HeadLayout{hh->a, hh->b, hh->c};
+                    head = reinterpret_cast<const float*>(a.head_blob + sizeof(BlobHeader));
+                }
+                if (a.maha_blob) {
+                    const BlobHeader* mh = reinterpret_cast<const BlobHeader*>(a.maha_blob);
+                    ml = MahaLayout{mh->a};
+                    maha = reinterpret_cast<const float*>(a.maha_blob + sizeof(BlobHeader));
+                }
+                if (head || maha) head_and_scores_t<NT_EPI, true>(reinterpret_cast<float*>(smem + OFF_Q), 8, w0, a, head, hl, maha, ml);
+                epi_bar();      // scratch (Q region) is rewritten by the next tile's QKV drain
+            }
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+// ================================================================================ weight packing
+// dst chunk image [128 rows x 64 cols] bf16, SWIZZLE_128B K-major; src = fp32 row-major (ld floats),
+// rows row0.., cols col0..col0+ncols-1 (zero padded to 64), rows < scaled_rows multiplied by scale.
+__global__ void pack_chunk_kernel(const float* __restrict__ src, int ld, int row0, int col0, int ncols, float scale,
+                                  uint8_t* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (row, 16-byte piece)
+    if (i >= 128 * 8) return;
+    const int r = i >> 3, j = i & 7;
+    float vals[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = j * 8 + e;
+        vals[e] = (c < ncols) ? src[(size_t)(row0 + r) * ld + col0 + c] * scale : 0.f;
+    }
+    uint4 u;
+    u.x = pack_bf16(vals[0], vals[1]); u.y = pack_bf16(vals[2], vals[3]);
+    u.z = pack_bf16(vals[4], vals[5]); u.w = pack_bf16(vals[6], vals[7]);
+    *reinterpret_cast<uint4*>(dst + sw128_off(r, j)) = u;
+}
+
+// patch-embedding chunk: columns [0,16) = hi(Wp), [16,32) = hi(Wp), [32,48) = lo(Wp), rest zero
+__global__ void pack_patch_chunk_kernel(const float* __restrict__ wp /*(128,16)*/, uint8_t* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 128 * 8) return;
+    const int r = i >> 3, j = i & 7;
+    float vals[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = j * 8 + e;
+        float v = 0.f;
+        if (c < 48) {
+            const float w = wp[r * P + (c & 15)];
+            const float hi = __bfloat162float(__float2bfloat16_rn(w));
+            v = (c < 32) ? hi : (w - hi);
+        }
+        vals[e] = v;
+    }
+    uint4 u;
+    u.x = pack_bf16(vals[0], vals[1]); u.y = pack_bf16(vals[2], vals[3]);
+    u.z = pack_bf16(vals[4], vals[5]); u.w = pack_bf16(vals[6], vals[7]);
+    *reinterpret_cast<uint4*>(dst + sw128_off(r, j)) = u;
+}
+
+size_t encoder_bf16_bytes(int layers) { return (size_t)(1 + layers * CHUNKS_PER_LAYER) * CHUNK; }
 
 int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_section, void* bf16_section, cudaStream_t st) {
-    (void)p; (void)fp32_section; (void)bf16_section; (void)st;
+    (void)fp32_section;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(bf16_section);
+    int c = 0;
+    auto put = [&](const float* src, int ld, int row0, int col0, int ncols, float scale) -> int {
+        pack_chunk_kernel<<<4, 256, 0, st>>>(src, ld, row0, col0, ncols, scale, dst + (size_t)c * CHUNK);
+        ++c;
+        CMHAR_LAUNCH_CHECK();
+        return CMHAR_OK;
+    };
+#define PUT(...) do { int _rc = put(__VA_ARGS__); if (_rc != CMHAR_OK) return _rc; } while (0)
+    pack_patch_chunk_kernel<<<4, 256, 0, st>>>(p->patch_weight, dst);
+    ++c;
+    CMHAR_LAUNCH_CHECK();
+    for (int l = 0; l < p->layers; ++l) {
+        const cmhar_encoder_layer_params& q = p->layer[l];
+        for (int m = 0; m < 3; ++m)                                   // Wq (x 1/4), Wk, Wv : k halves
+            for (int k = 0; k < 2; ++k) PUT(q.in_proj_weight, D, m * D, k * 64, 64, m == 0 ? 0.25f : 1.f);
+        for (int k = 0; k < 2; ++k) PUT(q.out_proj_weight, D, 0, k * 64, 64, 1.f);
+        for (int cc = 0; cc < 3; ++cc)                                // W1 chunks 0..2
+            for (int k = 0; k < 2; ++k) PUT(q.linear1_weight, D, cc * 128, k * 64, 64, 1.f);
+        for (int k = 0; k < 2; ++k) PUT(q.linear2_weight, FF, 0, k * 64, 64, 1.f);          // W2 k-chunk 0
+        for (int k = 0; k < 2; ++k) PUT(q.linear1_weight, D, 3 * 128, k * 64, 64, 1.f);     // W1 chunk 3
+        for (int kc = 1; kc < 4; ++kc)                                // W2 k-chunks 1..3
+            for (int k = 0; k < 2; ++k) PUT(q.linear2_weight, FF, 0, kc * 128 + k * 64, 64, 1.f);
+    }
+#undef PUT
+    return CMHAR_OK;
+}
+
+static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
+    static bool configured[64] = {};
+    int dev = 0;
+    CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(imu_forward_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured[dev & 63] = true;
+    }
+    const long long tiles = (args.f.n + 7) / 8;
+    const int grid = (int)((tiles < (long long)sm_count()) ? tiles : (long long)sm_count());
+    imu_forward_bf16_kernel<<<grid, NT_TC, SMEM_BYTES, stream>>>(args);
+    CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }
 
 int launch_imu_forward_bf16(const FwdArgs& a, cudaStream_t stream) {
-    (void)a; (void)stream;
-    set_error("cmhar_imu_forward: CMHAR_BF16 path not built in this version");
-    return CMHAR_ERR_UNSUPPORTED;
+    Bf16Args args{a, -1, nullptr, nullptr};
+    return launch_bf16(args, stream);
+}
+
+int launch_imu_forward_bf16_debug(const FwdArgs& a, int stage, float* dump, int* progress, cudaStream_t stream) {
+    Bf16Args args{a, stage, dump, progress};
+    return launch_bf16(args, stream);
 }
 
 }  // namespace cmhar

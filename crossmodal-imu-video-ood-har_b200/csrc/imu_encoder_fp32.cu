@@ -87,9 +87,17 @@ __device__ __forceinline__ void layer_norm_rows(float* h, const float* __restric
 
 // Classifier head (models.py:312-326,338, BN folded) + arg-max / MSP / energy (+ Mahalanobis) for
 // up to 8 feature rows held in buf[0..8*128) (rows >= wpb are zero).  Scratch lives in buf.
-__device__ __forceinline__ void head_and_scores(float* buf, int wpb, long long w0, const FwdArgs& a,
-                                                const float* head, const HeadLayout hl,
-                                                const float* maha, const MahaLayout ml) {
+template <bool NAMED>
+__device__ __forceinline__ void block_sync() {
+    if (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory");     // the 256 epilogue threads of the bf16 kernel
+    else __syncthreads();
+}
+
+template <int NTH, bool NAMED>
+__device__ __forceinline__ void head_and_scores_t(float* buf, int wpb, long long w0, const FwdArgs& a,
+                                                  const float* head, const HeadLayout hl,
+                                                  const float* maha, const MahaLayout ml) {
+    constexpr int NT = NTH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* feat = buf;                  // [8][128], filled by the caller (zero rows beyond wpb)
     float* hid1 = buf + 8 * D;          // [8][256]
@@ -111,7 +119,7 @@ __device__ __forceinline__ void head_and_scores(float* buf, int wpb, long long w
 #pragma unroll
             for (int w = 0; w < 8; ++w) hid1[w * 256 + j] = fmaxf(acc[w] + bv, 0.f);
         }
-        __syncthreads();
+        block_sync<NAMED>();
         for (int j = tid; j < hl.h2; j += NT) {          // Linear(h1->h2)+BN folded, ReLU
             float acc[8];
 #pragma unroll
@@ -126,7 +134,7 @@ __device__ __forceinline__ void head_and_scores(float* buf, int wpb, long long w
 #pragma unroll
             for (int w = 0; w < 8; ++w) hid2[w * 256 + j] = fmaxf(acc[w] + bv, 0.f);
         }
-        __syncthreads();
+        block_sync<NAMED>();
         for (int j = tid; j < hl.C; j += NT) {           // Linear(h2->classes)
             float acc[8];
 #pragma unroll
@@ -141,7 +149,7 @@ __device__ __forceinline__ void head_and_scores(float* buf, int wpb, long long w
 #pragma unroll
             for (int w = 0; w < 8; ++w) logit[w * 64 + j] = acc[w] + bv;
         }
-        __syncthreads();
+        block_sync<NAMED>();
         if (warp < wpb && w0 + warp < a.n) {             // warp w scores window w
             const long long gw = w0 + warp;
             const int C = hl.C;
@@ -177,7 +185,7 @@ __device__ __forceinline__ void head_and_scores(float* buf, int wpb, long long w
 #pragma unroll
             for (int w = 0; w < 8; ++w) white[w * D + j] = acc[w];
         }
-        __syncthreads();
+        block_sync<NAMED>();
         if (warp < wpb && w0 + warp < a.n) {
             const float4 y = *reinterpret_cast<const float4*>(white + warp * D + lane * 4);
             float best = INFINITY;
@@ -193,7 +201,8 @@ __device__ __forceinline__ void head_and_scores(float* buf, int wpb, long long w
 }
 
 __global__ void __launch_bounds__(NT, 1) imu_forward_fp32_kernel(const FwdArgs a) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) float smem_f32[];
+    float* const smem = smem_f32;
     float* h = smem;                    // [64][128]
     float* buf = smem + ROWS * D;       // [64][512]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -396,7 +405,7 @@ __global__ void __launch_bounds__(NT, 1) imu_forward_fp32_kernel(const FwdArgs a
             buf[e] = (w < wpb) ? h[(w * S) * D + (e % D)] : 0.f;
         }
         __syncthreads();
-        head_and_scores(buf, wpb, w0, a, head, hl, maha, ml);
+        head_and_scores_t<NT, false>(buf, wpb, w0, a, head, hl, maha, ml);
     }
 }
 
@@ -427,7 +436,7 @@ __global__ void __launch_bounds__(NT) head_forward_kernel(const FwdArgs a) {
             buf[e] = (r < a.n) ? __ldg(a.x + r * D + (e % D)) : 0.f;
         }
         __syncthreads();
-        head_and_scores(buf, 8, w0, a, head, hl, maha, ml);
+        head_and_scores_t<NT, false>(buf, 8, w0, a, head, hl, maha, ml);
     }
 }
 

@@ -128,6 +128,14 @@ int cmhar_imu_forward(const void* encoder_blob, const void* head_blob, const voi
                       float* maha_out       /* (n)  = min_c Mahalanobis^2     */,
                       int32_t precision, cmhar_stream_t s);
 
+/* Diagnostic hook of the bf16 tcgen05 path (used by tests/tools only): runs the encoder on
+ * n_windows and dumps the fp32 residual stream held in TMEM, (ceil(n/8)*128, 128) floats, right
+ * after `stage`: 0 = patch embedding, 1 = layer-0 attention + LayerNorm1, 2 = layer-0 output. */
+int cmhar_debug_imu_bf16(const void* encoder_blob, const float* x, int64_t n_windows,
+                         int64_t x_window_stride, int32_t stage, float* residual_dump,
+                         float* cls_out, int32_t* progress_host_mapped /* NULL or pinned [grid][16] */,
+                         cmhar_stream_t s);
+
 /* Same head + scores from stored features (row-major (n,128) fp32). */
 int cmhar_head_forward(const void* head_blob, const void* maha_blob, const float* feat, int64_t n,
                        float* logits_out, int64_t* pred_out, float* msp_out, float* energy_out,
