@@ -8,60 +8,57 @@
 
 namespace cmhar {
 
-constexpr int LT_ROWS = 64, LT_COLS = 128, LT_K = 64, LT_LDA = LT_K + 4;
+constexpr int LT_ROWS = 32, LT_COLS = 64, LT_K = 32;
 
-// y (n,N) = act(x (n,K) @ Wt (K,N) + b);  K % 4 == 0, N % 4 == 0
-__global__ void __launch_bounds__(256) linear_fp32_kernel(const float* __restrict__ Wt, const float* __restrict__ bias,
+// y (n,N) = act(x (n,K) @ Wt (K,N) + b);  K % 4 == 0, N % 4 == 0.
+// 32 x 64 output tile per CTA (128 threads, 4 x 4 register micro-tiles), both operands staged through
+// shared memory in 32-deep k slabs.  Small tiles on purpose: the callers are the projection heads at
+// batch 256 (M = 256), where a 64 x 128 tiling would leave 140 of 148 SMs idle.
+__global__ void __launch_bounds__(128) linear_fp32_kernel(const float* __restrict__ Wt, const float* __restrict__ bias,
                                                           const float* __restrict__ X, long long n, int K, int N,
                                                           int relu, float* __restrict__ Y) {
-    __shared__ __align__(16) float As[LT_ROWS * LT_LDA];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ __align__(16) float As[LT_K][LT_ROWS + 4];     // transposed: As[k][row]
+    __shared__ __align__(16) float Ws[LT_K][LT_COLS];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;        // cols tx*4.., rows ty*4..
     const long long row0 = (long long)blockIdx.x * LT_ROWS;
-    const int col = blockIdx.y * LT_COLS + lane * 4;
-    const bool col_ok = col < N;
-    float acc[8][4];
+    const int col0 = blockIdx.y * LT_COLS;
+    float acc[4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     for (int k0 = 0; k0 < K; k0 += LT_K) {
-        const int kc = min(LT_K, K - k0);
         __syncthreads();
-        for (int e = tid; e < LT_ROWS * (LT_K / 4); e += 256) {
-            const int r = e / (LT_K / 4), k4 = (e % (LT_K / 4)) * 4;
+        for (int e = tid; e < LT_ROWS * (LT_K / 4); e += 128) {       // X tile: 32 rows x 8 float4
+            const int r = e >> 3, k4 = (e & 7) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + r < n && k4 < kc) v = __ldg(reinterpret_cast<const float4*>(X + (row0 + r) * K + k0 + k4));
-            *reinterpret_cast<float4*>(As + r * LT_LDA + k4) = v;
+            if (row0 + r < n && k0 + k4 < K) v = __ldg(reinterpret_cast<const float4*>(X + (row0 + r) * K + k0 + k4));
+            As[k4][r] = v.x; As[k4 + 1][r] = v.y; As[k4 + 2][r] = v.z; As[k4 + 3][r] = v.w;
+        }
+        for (int e = tid; e < LT_K * (LT_COLS / 4); e += 128) {       // W slab: 32 k x 16 float4
+            const int k = e >> 4, c4 = (e & 15) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + k < K && col0 + c4 < N) v = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k0 + k) * N + col0 + c4));
+            *reinterpret_cast<float4*>(&Ws[k][c4]) = v;
         }
         __syncthreads();
-        if (col_ok) {
-            const float* a0 = As + warp * 8 * LT_LDA;
-            const float* w0 = Wt + (size_t)k0 * N + col;
-#pragma unroll 2
-            for (int k = 0; k < kc; k += 4) {
-                float4 w[4];
+#pragma unroll 8
+        for (int k = 0; k < LT_K; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w}, w4[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(reinterpret_cast<const float4*>(w0 + (size_t)(k + kk) * N));
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 a = *reinterpret_cast<const float4*>(a0 + i * LT_LDA + k);
-                    acc[i][0] = fmaf(a.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(a.x, w[0].y, acc[i][1]);
-                    acc[i][2] = fmaf(a.x, w[0].z, acc[i][2]); acc[i][3] = fmaf(a.x, w[0].w, acc[i][3]);
-                    acc[i][0] = fmaf(a.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(a.y, w[1].y, acc[i][1]);
-                    acc[i][2] = fmaf(a.y, w[1].z, acc[i][2]); acc[i][3] = fmaf(a.y, w[1].w, acc[i][3]);
-                    acc[i][0] = fmaf(a.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(a.z, w[2].y, acc[i][1]);
-                    acc[i][2] = fmaf(a.z, w[2].z, acc[i][2]); acc[i][3] = fmaf(a.z, w[2].w, acc[i][3]);
-                    acc[i][0] = fmaf(a.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(a.w, w[3].y, acc[i][1]);
-                    acc[i][2] = fmaf(a.w, w[3].z, acc[i][2]); acc[i][3] = fmaf(a.w, w[3].w, acc[i][3]);
-                }
-            }
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], w4[j], acc[i][j]);
         }
     }
-    if (!col_ok) return;
+    const int col = col0 + tx * 4;
+    if (col >= N) return;
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const long long r = row0 + warp * 8 + i;
+    for (int i = 0; i < 4; ++i) {
+        const long long r = row0 + ty * 4 + i;
         if (r >= n) continue;
         float4 o = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
@@ -165,7 +162,7 @@ int cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in
     if (n <= 0) return CMHAR_OK;
     const float* f = reinterpret_cast<const float*>(reinterpret_cast<const char*>(blob) + sizeof(BlobHeader));
     dim3 grid((unsigned)((n + LT_ROWS - 1) / LT_ROWS), (unsigned)((out_dim + LT_COLS - 1) / LT_COLS));
-    linear_fp32_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(f, f + (size_t)in_dim * out_dim, x, n, in_dim, out_dim, relu, y);
+    linear_fp32_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(f, f + (size_t)in_dim * out_dim, x, n, in_dim, out_dim, relu, y);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }

@@ -1,0 +1,24 @@
+"""Profiling driver (test infrastructure): a few launches of the fused IMU kernel at a given batch,
+for `ncu --set full -k regex:imu_forward`.   python tools/profile_imu.py [batch] [precision] [reps]"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import crossmodal_imu_video_ood_har_b200 as cm
+
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+torch.manual_seed(0)
+cfg = cm.default_config()
+clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg).to("cuda").eval()
+x = torch.randn(batch, 6, 250, device="cuda")
+out = {}
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for i in range(reps):
+    if i == reps - 1:
+        ev0.record()
+    clf.forward_scores(x, precision=prec, out=out)
+ev1.record()
+torch.cuda.synchronize()
+ms = ev0.elapsed_time(ev1)
+print(f"batch {batch} {prec}: {ms:.3f} ms/launch -> {batch / ms * 1e3:.0f} windows/s, {25890816 * batch / ms / 1e9:.1f} TFLOP/s")
