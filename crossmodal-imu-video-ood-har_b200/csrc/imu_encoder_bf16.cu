@@ -50,16 +50,15 @@ enum {
     B_ACC = B_WEMPTY + NSTAGE,   // [4] accumulator buffer A,B,C,R complete (tcgen05.commit)
     B_HA = B_ACC + 4,            // hA (+R) written by the epilogue        (256)
     B_QKV = B_HA + 1,            // Q,K,V^T in smem, P zeroed              (256)
-    B_SFREE = B_QKV + 1,         // [2] S buffer drained                   (128)
-    B_PREADY = B_SFREE + 2,      // P_h written                            (128)
-    B_PFREE = B_PREADY + 1,      // PV_h done reading P                    (commit)
-    B_O = B_PFREE + 1,           // O in smem                              (256)
+    B_P = B_QKV + 1,             // P (all heads) in smem                  (256)
+    B_O = B_P + 1,               // O in smem                              (256)
     B_HID = B_O + 1,             // [4] hidden chunk c in smem             (256)
     B_COUNT = B_HID + 4          // one barrier per chunk: a waiter may never fall two phases behind
 };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier area too small");
 
 constexpr uint32_t TM_A = 0, TM_B = 128, TM_C = 256, TM_R = 384;
+constexpr uint32_t TM_P = TM_B + 64;      // softmax probabilities, bf16 pairs: head h -> columns [8h, 8h+8)
 
 // ---------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,6 +101,13 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// one lane of a converged warp (the same one every time): tcgen05.mma / commit are issued under this
+// predicate while the whole warp stays converged, so descriptors live in uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major SWIZZLE_128B
@@ -112,6 +118,32 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t 
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// same, but only the 16 TMEM lanes [16*win, 16*win+16) are written (disable-output-lane mask)
+__device__ __forceinline__ void umma_rows16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int win) {
+    const uint32_t hole = ~(0xFFFFu << ((win & 1) * 16));      // no array indexing: keeps the mask in registers
+    const uint32_t m[4] = {(win >> 1) == 0 ? hole : 0xFFFFFFFFu, (win >> 1) == 1 ? hole : 0xFFFFFFFFu,
+                           (win >> 1) == 2 ? hole : 0xFFFFFFFFu, (win >> 1) == 3 ? hole : 0xFFFFFFFFu};
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %5, %6, %7}, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]) : "memory");
+}
+
+// A operand from TMEM (lane = row, one 32-bit column = two consecutive k elements), B from smem
+__device__ __forceinline__ void umma_ts_rows16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, int win) {
+    const uint32_t hole = ~(0xFFFFu << ((win & 1) * 16));      // no array indexing: keeps the mask in registers
+    const uint32_t m[4] = {(win >> 1) == 0 ? hole : 0xFFFFFFFFu, (win >> 1) == 1 ? hole : 0xFFFFFFFFu,
+                           (win >> 1) == 2 ? hole : 0xFFFFFFFFu, (win >> 1) == 3 ? hole : 0xFFFFFFFFu};
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%4, %5, %6, %7}, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]) : "memory");
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
@@ -146,6 +178,14 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
                    "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), \
                    "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), \
                    "r"(v[31])                                                                                     \
+                 : "memory")
+
+#define TMEM_ST16(addr, v)                                                                                        \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                  \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                      \
+                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
+                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
+                   "r"(v[15])                                                                                     \
                  : "memory")
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -186,7 +226,9 @@ struct Bf16Args {
     int dbg_stage;          // <0: off; else dump the residual (fp32 [128][128] per tile) after that stage
     float* dbg_out;
     volatile int* progress; // debug: host-mapped [grid][16] progress codes (survive a trap), or null
+    long long* tlog;        // debug: device [10 warps][TLOG_CAP][2] (code, clock64) of block 0, or null
 };
+constexpr int TLOG_CAP = 1024;
 
 // ======================================================================================== kernel
 __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Args args) {
@@ -200,9 +242,14 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
     const size_t fp32_bytes = (EncLayout::fp32_floats(n_layers) * sizeof(float) + 1023) / 1024 * 1024;
     const uint8_t* wchunks = reinterpret_cast<const uint8_t*>(a.enc_blob) + 1024 + fp32_bytes;
     const int n_chunks = 1 + n_layers * CHUNKS_PER_LAYER;
+    const float* bo_fold = reinterpret_cast<const float*>(wchunks + (size_t)n_chunks * CHUNK);   // [layers][128]: b_o + W_o b_v
     const long long tiles = (a.n + 7) / 8;
 
-#define PROG(code) do { if (args.progress && lane == 0) { args.progress[blockIdx.x * 16 + warp] = (code); __threadfence_system(); } } while (0)
+    int tlog_n = 0;
+#define PROG(code) do { if (lane == 0) { \
+        if (args.progress) { args.progress[blockIdx.x * 16 + warp] = (code); __threadfence_system(); } \
+        if (args.tlog && blockIdx.x == 0 && tlog_n < TLOG_CAP) { args.tlog[(warp * TLOG_CAP + tlog_n) * 2] = (code); \
+            args.tlog[(warp * TLOG_CAP + tlog_n) * 2 + 1] = clock64(); ++tlog_n; } } } while (0)
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -213,10 +260,7 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_ACC + i), 1);
         mbar_init(BAR(B_HA), NT_EPI);
         mbar_init(BAR(B_QKV), NT_EPI);
-        mbar_init(BAR(B_SFREE), 128);
-        mbar_init(BAR(B_SFREE + 1), 128);
-        mbar_init(BAR(B_PREADY), 128);
-        mbar_init(BAR(B_PFREE), 1);
+        mbar_init(BAR(B_P), NT_EPI);
         mbar_init(BAR(B_O), NT_EPI);
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_HID + i), NT_EPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -236,7 +280,7 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
             uint32_t stage = 0, parity = 1;           // fresh barriers: waiting on parity 1 passes
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 for (int c = 0; c < n_chunks; ++c) {
-                    PROG(1); mbar_wait(BAR(B_WEMPTY + stage), parity, 1);
+                    mbar_wait(BAR(B_WEMPTY + stage), parity, 1);
                     mbar_expect_tx(BAR(B_WFULL + stage), CHUNK);
                     bulk_g2s(sbase + OFF_W + stage * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(B_WFULL + stage));
                     if (++stage == NSTAGE) { stage = 0; parity ^= 1; }
@@ -244,8 +288,9 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
             }
         }
     } else if (warp == MMA_WARP) {
-        // ================================================================= MMA issuer
-        if (lane == 0) {
+        // ================================================================= MMA issuer (warp converged)
+        {
+            const bool leader = elect_one();
             Phase ph;
             uint32_t wstage = 0, wparity = 0;
             constexpr uint32_t ID128 = idesc_bf16(128, 128), ID16 = idesc_bf16(128, 16);
@@ -253,75 +298,78 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                            dVT = sw128_desc(sbase + OFF_VT), dP = sw128_desc(sbase + OFF_P);
             // one weight chunk = 64 k-columns = 4 MMAs of K=16.  `w_is_a`: weights are the A operand.
             auto gemm_chunk = [&](uint32_t d, uint64_t other_desc, bool w_is_a, bool first_acc, int ksteps) {
-                PROG(2); mbar_wait(BAR(B_WFULL + wstage), wparity, 2);
+                mbar_wait(BAR(B_WFULL + wstage), wparity, 2);
                 tc_fence_after();
                 const uint64_t dW = sw128_desc(sbase + OFF_W + wstage * CHUNK);
                 for (int k = 0; k < ksteps; ++k) {
                     const uint64_t wa = dW + (uint64_t)(2 * k), oa = other_desc + (uint64_t)(2 * k);
-                    umma(d, w_is_a ? wa : oa, w_is_a ? oa : wa, ID128, (first_acc || k > 0) ? 1u : 0u);
+                    if (leader) umma(d, w_is_a ? wa : oa, w_is_a ? oa : wa, ID128, (first_acc || k > 0) ? 1u : 0u);
                 }
-                tc_commit(BAR(B_WEMPTY + wstage));
+                if (leader) tc_commit(BAR(B_WEMPTY + wstage));
                 if (++wstage == NSTAGE) { wstage = 0; wparity ^= 1; }
             };
             const uint64_t CH = CHUNK >> 4;      // descriptor units per chunk
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 // ---- patch embedding: R(tok_bias) += patches(16 k) * Wp^T
-                PROG(3); mbar_wait(BAR(B_HA), ph.next(B_HA), 3);
+                PROG(3); mbar_wait(BAR(B_HA), ph.next(B_HA), 3); PROG(1003);
                 tc_fence_after();
                 gemm_chunk(tmem + TM_R, dHA, false, true, 3);
-                tc_commit(BAR(B_ACC + 3));
+                if (leader) tc_commit(BAR(B_ACC + 3));
                 for (int l = 0; l < n_layers; ++l) {
                     // ---- Q, K (A = hA, B = W) and V^T (A = W_v, B = hA)
-                    PROG(4); mbar_wait(BAR(B_HA), ph.next(B_HA), 4);
+                    PROG(4); mbar_wait(BAR(B_HA), ph.next(B_HA), 4); PROG(1004);
                     tc_fence_after();
                     gemm_chunk(tmem + TM_A, dHA, false, false, 4);
                     gemm_chunk(tmem + TM_A, dHA + CH, false, true, 4);
-                    tc_commit(BAR(B_ACC + 0));
+                    if (leader) tc_commit(BAR(B_ACC + 0));
                     gemm_chunk(tmem + TM_B, dHA, false, false, 4);
                     gemm_chunk(tmem + TM_B, dHA + CH, false, true, 4);
-                    tc_commit(BAR(B_ACC + 1));
+                    if (leader) tc_commit(BAR(B_ACC + 1));
                     gemm_chunk(tmem + TM_C, dHA, true, false, 4);
                     gemm_chunk(tmem + TM_C, dHA + CH, true, true, 4);
-                    tc_commit(BAR(B_ACC + 2));
+                    if (leader) tc_commit(BAR(B_ACC + 2));
                     // ---- attention
-                    PROG(5); mbar_wait(BAR(B_QKV), ph.next(B_QKV), 5);
+                    PROG(5); mbar_wait(BAR(B_QKV), ph.next(B_QKV), 5); PROG(1005);
                     tc_fence_after();
-                    auto issue_S = [&](int h) {      // S_h = Q_h K_h^T into buffer (h&1)
-                        const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)((h & 3) * 2);
-                        umma(tmem + ((h & 1) ? TM_B : TM_A), dQ + off, dK + off, ID128, 0u);
-                        tc_commit(BAR(B_ACC + (h & 1)));
-                    };
-                    issue_S(0);
-                    issue_S(1);
-                    for (int h = 0; h < H; ++h) {
-                        PROG(6); mbar_wait(BAR(B_PREADY), ph.next(B_PREADY), 6);
-                        tc_fence_after();
-                        for (int j = 0; j < 8; ++j) {     // O[:,16h..] (+)= P[:,16j..16j+15] * V^T_h[:,16j..]^T
-                            const uint64_t koff = (uint64_t)(j >> 2) * CH + (uint64_t)((j & 3) * 2);
-                            umma(tmem + TM_C + 16 * h, dP + koff, dVT + koff + (uint64_t)(h * 2 * 64), ID16, j > 0 ? 1u : 0u);
+                    // compact scores: S[r][16h + k] = q_h(r) . k_h(key k of r's own window): one 128x16x16 MMA per
+                    // (head, window) whose output is masked to the 16 rows of that window
+                    // (window outer, head inner: consecutive MMAs hit different accumulator columns)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                        for (int h = 0; h < H; ++h) {
+                            const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)((h & 3) * 2);
+                            if (leader) umma_rows16(tmem + TM_A + 16 * h, dQ + off, dK + off + (uint64_t)(j * 128), ID16, j);
                         }
-                        tc_commit(BAR(B_PFREE));
-                        PROG(7); mbar_wait(BAR(B_SFREE + (h & 1)), ph.next(B_SFREE + (h & 1)), 7);   // S_h drained
-                        tc_fence_after();
-                        if (h + 2 < H) issue_S(h + 2);
                     }
-                    tc_commit(BAR(B_ACC + 2));            // O complete
+                    if (leader) tc_commit(BAR(B_ACC + 0));
+                    // O[r][16h + d] = sum_k P[r][16h + k] * V_h[key k of r's window][d]
+                    PROG(6); mbar_wait(BAR(B_P), ph.next(B_P), 6); PROG(1006);
+                    tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint64_t koff = (uint64_t)(j >> 2) * CH + (uint64_t)((j & 3) * 2);
+#pragma unroll
+                        for (int h = 0; h < H; ++h)
+                            if (leader) umma_ts_rows16(tmem + TM_C + 16 * h, tmem + TM_P + 8 * h, dVT + koff + (uint64_t)(h * 128), ID16, j);
+                    }
+                    if (leader) tc_commit(BAR(B_ACC + 2));            // O complete
                     // ---- out-proj: R(h + b_o) += O * W_o^T
-                    PROG(8); mbar_wait(BAR(B_O), ph.next(B_O), 8);
+                    PROG(8); mbar_wait(BAR(B_O), ph.next(B_O), 8); PROG(1008);
                     tc_fence_after();
                     gemm_chunk(tmem + TM_R, dQ, false, true, 4);
                     gemm_chunk(tmem + TM_R, dQ + CH, false, true, 4);
-                    tc_commit(BAR(B_ACC + 3));
+                    if (leader) tc_commit(BAR(B_ACC + 3));
                     // ---- FFN: hidden chunk c -> buffers A,B,C,A ; R(h1 + b_2) += hidden_c * W_2[:,c]^T
-                    PROG(9); mbar_wait(BAR(B_HA), ph.next(B_HA), 9);
+                    PROG(9); mbar_wait(BAR(B_HA), ph.next(B_HA), 9); PROG(1009);
                     tc_fence_after();
                     for (int c = 0; c < 3; ++c) {
                         gemm_chunk(tmem + 128 * c, dHA, false, false, 4);
                         gemm_chunk(tmem + 128 * c, dHA + CH, false, true, 4);
-                        tc_commit(BAR(B_ACC + c));
+                        if (leader) tc_commit(BAR(B_ACC + c));
                     }
                     for (int c = 0; c < 4; ++c) {
-                        PROG(10); mbar_wait(BAR(B_HID + c), ph.next(B_HID + c), 10);     // hidden chunk c in smem (and its TMEM buffer drained)
+                        PROG(10); mbar_wait(BAR(B_HID + c), ph.next(B_HID + c), 10); PROG(1010);     // hidden chunk c in smem (and its TMEM buffer drained)
                         tc_fence_after();
                         const uint64_t dHid = sw128_desc(sbase + OFF_Q + c * 32768);
                         gemm_chunk(tmem + TM_R, dHid, false, true, 4);
@@ -329,10 +377,10 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                         if (c == 0) {                              // 4th FFN1 chunk reuses buffer A
                             gemm_chunk(tmem + TM_A, dHA, false, false, 4);
                             gemm_chunk(tmem + TM_A, dHA + CH, false, true, 4);
-                            tc_commit(BAR(B_ACC + 0));
+                            if (leader) tc_commit(BAR(B_ACC + 0));
                         }
                     }
-                    tc_commit(BAR(B_ACC + 3));
+                    if (leader) tc_commit(BAR(B_ACC + 3));
                 }
             }
         }
@@ -457,17 +505,16 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
             }
             publish(B_HA);
             // ---- h0 = R ; hA = bf16(h0) ; R = h0 + b_o(layer 0)
-            PROG(11); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 11);
+            PROG(11); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 11); PROG(1011);
             tc_fence_after();
             {
-                const float* L0 = encf + EncLayout::layers0;
 #pragma unroll
                 for (int cc = 0; cc < 64; cc += 32) {
                     TMEM_LD32(lane_base + TM_R + c0 + cc, v);
                     tc_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    write_h(f, cc, L0 + EncLayout::l_b_o);
+                    write_h(f, cc, bo_fold);
                 }
             }
             if (args.dbg_stage == 0) { tc_wait_st(); dump_R(tile); }
@@ -479,71 +526,60 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                 // ---- drain Q, K (bias per column) and V^T (bias per lane) into smem as bf16
 #pragma unroll 1
                 for (int m = 0; m < 3; ++m) {
-                    PROG(12); mbar_wait(BAR(B_ACC + m), ph.next(B_ACC + m), 12);
+                    PROG(12); mbar_wait(BAR(B_ACC + m), ph.next(B_ACC + m), 12); PROG(1012);
                     tc_fence_after();
                     uint8_t* dst = smem + OFF_Q + m * 32768 + wg * CHUNK;
-                    const float bv = (m == 2) ? __ldg(L + EncLayout::l_b_in + 2 * D + row) : 0.f;
 #pragma unroll
                     for (int cc = 0; cc < 64; cc += 32) {
                         TMEM_LD32(lane_base + 128 * m + c0 + cc, v);
                         tc_wait_ld();
-                        if (m < 2) {
+                        if (m == 0) {     // q bias (pre-scaled); the k bias cancels in the softmax, the v bias is folded into b_o
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(L + EncLayout::l_b_in + m * D + c0 + cc + i));
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(L + EncLayout::l_b_in + c0 + cc + i));
                                 f[i] = __uint_as_float(v[i]) + b.x; f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
                                 f[i + 2] = __uint_as_float(v[i + 2]) + b.z; f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
                             }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + bv;
+                            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                         }
                         store_bf16_32(dst, row, cc >> 3, f);
                     }
                 }
-                // zero P (block-diagonal operand; this thread clears its half-row except its own block)
-                {
-                    const uint4 z = make_uint4(0, 0, 0, 0);
-                    uint8_t* pc = smem + OFF_P + wg * CHUNK;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(pc + sw128_off(row, j)) = z;
-                }
                 PROG(100 + l);
                 publish(B_QKV);
-                // ---- softmax of head h on the 16x16 diagonal block; wg handles heads of its parity
-#pragma unroll 1
-                for (int h = wg; h < H; h += 2) {
-                    PROG(13); mbar_wait(BAR(B_ACC + wg), ph.next(B_ACC + wg), 13);
-                    tc_fence_after();
-                    TMEM_LD32(lane_base + 128 * wg + (warp & 3) * 32, v);     // keys 32q..32q+31 = this warp's two windows
+                // ---- softmax: this thread owns heads 4wg..4wg+3 of its row (16 compact scores each)
+                PROG(13); mbar_wait(BAR(B_ACC + 0), ph.next(B_ACC + 0), 13); PROG(1013);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 64; cc += 32) {
+                    TMEM_LD32(lane_base + TM_A + c0 + cc, v);
                     tc_wait_ld();
-                    tc_fence_before();
-                    mbar_arrive(BAR(B_SFREE + wg));
-                    float s[16];
-                    const bool hi = (lane >= 16);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) s[i] = __uint_as_float(hi ? v[16 + i] : v[i]);
-                    float m = -INFINITY;
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float m = -INFINITY;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { if (i >= S) s[i] = -INFINITY; m = fmaxf(m, s[i]); }
-                    float den = 0.f;
+                        for (int i = 0; i < 16; ++i) {
+                            const float sv = (i < S) ? __uint_as_float(v[hh * 16 + i]) : -INFINITY;
+                            f[hh * 16 + i] = sv;
+                            m = fmaxf(m, sv);
+                        }
+                        float den = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { s[i] = __expf(s[i] - m); den += s[i]; }
-                    const float inv = 1.f / den;
-                    uint4 u0, u1;
-                    u0.x = pack_bf16(s[0] * inv, s[1] * inv); u0.y = pack_bf16(s[2] * inv, s[3] * inv);
-                    u0.z = pack_bf16(s[4] * inv, s[5] * inv); u0.w = pack_bf16(s[6] * inv, s[7] * inv);
-                    u1.x = pack_bf16(s[8] * inv, s[9] * inv); u1.y = pack_bf16(s[10] * inv, s[11] * inv);
-                    u1.z = pack_bf16(s[12] * inv, s[13] * inv); u1.w = pack_bf16(s[14] * inv, s[15] * inv);
-                    if (h > 0) mbar_wait(BAR(B_PFREE), (uint32_t)((h - 1) & 1), 14);   // PV_{h-1} finished reading P
-                    uint8_t* pc = smem + OFF_P + (win >> 2) * CHUNK;
-                    *reinterpret_cast<uint4*>(pc + sw128_off(row, (win & 3) * 2)) = u0;
-                    *reinterpret_cast<uint4*>(pc + sw128_off(row, (win & 3) * 2 + 1)) = u1;
-                    fence_async_smem();
-                    mbar_arrive(BAR(B_PREADY));
+                        for (int i = 0; i < 16; ++i) { f[hh * 16 + i] = __expf(f[hh * 16 + i] - m); den += f[hh * 16 + i]; }
+                        const float inv = 1.f / den;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[hh * 16 + i] *= inv;
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+                    TMEM_ST16(lane_base + TM_P + 32 * wg + (cc >> 1), pk);
                 }
+                publish(B_P);
                 // ---- O (buffer C) -> smem (Q region) as bf16
-                PROG(15); mbar_wait(BAR(B_ACC + 2), ph.next(B_ACC + 2), 15);
+                PROG(15); mbar_wait(BAR(B_ACC + 2), ph.next(B_ACC + 2), 15); PROG(1015);
                 tc_fence_after();
 #pragma unroll
                 for (int cc = 0; cc < 64; cc += 32) {
@@ -555,7 +591,7 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                 }
                 publish(B_O);
                 // ---- LN1: h1 = LN(R) ; hA = bf16(h1) ; R = h1 + b_2
-                PROG(16); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 16);
+                PROG(16); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 16); PROG(1016);
                 tc_fence_after();
                 layer_norm_R(L + EncLayout::l_ln1, L + EncLayout::l_b2, true, nullptr);
                 if (args.dbg_stage == 1 && l == 0) { tc_wait_st(); dump_R(tile); }
@@ -564,7 +600,7 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int buf = (c == 3) ? 0 : c;
-                    PROG(17); mbar_wait(BAR(B_ACC + buf), ph.next(B_ACC + buf), 17);
+                    PROG(17); mbar_wait(BAR(B_ACC + buf), ph.next(B_ACC + buf), 17); PROG(1017);
                     PROG(170 + c);
                     tc_fence_after();
 #pragma unroll
@@ -584,10 +620,10 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                     PROG(190 + c);
                 }
                 // ---- LN2: h2 = LN(R) ; hA = bf16(h2) ; R = h2 + b_o(next layer)
-                PROG(18); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 18);
+                PROG(18); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 18); PROG(1018);
                 tc_fence_after();
                 if (!last) {
-                    layer_norm_R(L + EncLayout::l_ln2, L + EncLayout::layer_floats + EncLayout::l_b_o, true, nullptr);
+                    layer_norm_R(L + EncLayout::l_ln2, bo_fold + (l + 1) * D, true, nullptr);
                     if (args.dbg_stage == 2 && l == 0) { tc_wait_st(); dump_R(tile); }
                     publish(B_HA);
                 } else {
@@ -699,7 +735,19 @@ __global__ void pack_patch_chunk_kernel(const float* __restrict__ wp /*(128,16)*
     *reinterpret_cast<uint4*>(dst + sw128_off(r, j)) = u;
 }
 
-size_t encoder_bf16_bytes(int layers) { return (size_t)(1 + layers * CHUNKS_PER_LAYER) * CHUNK; }
+// bo_fold[n] = b_o[n] + sum_k W_o[n][k] * b_v[k]   (the value bias commutes with the softmax average)
+__global__ void fold_value_bias_kernel(const float* __restrict__ wo, const float* __restrict__ bo,
+                                       const float* __restrict__ bv, float* __restrict__ dst) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= D) return;
+    double acc = bo[n];
+    for (int k = 0; k < D; ++k) acc += (double)wo[n * D + k] * (double)bv[k];
+    dst[n] = (float)acc;
+}
+
+size_t encoder_bf16_bytes(int layers) {
+    return (size_t)(1 + layers * CHUNKS_PER_LAYER) * CHUNK + (size_t)CMHAR_MAX_LAYERS * D * sizeof(float);
+}
 
 int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_section, void* bf16_section, cudaStream_t st) {
     (void)fp32_section;
@@ -728,6 +776,12 @@ int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_secti
             for (int k = 0; k < 2; ++k) PUT(q.linear2_weight, FF, 0, kc * 128 + k * 64, 64, 1.f);
     }
 #undef PUT
+    float* fold = reinterpret_cast<float*>(dst + (size_t)c * CHUNK);
+    for (int l = 0; l < p->layers; ++l) {
+        const cmhar_encoder_layer_params& q = p->layer[l];
+        fold_value_bias_kernel<<<1, 128, 0, st>>>(q.out_proj_weight, q.out_proj_bias, q.in_proj_bias + 2 * D, fold + l * D);
+        CMHAR_LAUNCH_CHECK();
+    }
     return CMHAR_OK;
 }
 
@@ -747,12 +801,14 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
 }
 
 int launch_imu_forward_bf16(const FwdArgs& a, cudaStream_t stream) {
-    Bf16Args args{a, -1, nullptr, nullptr};
+    Bf16Args args{a, -1, nullptr, nullptr, nullptr};
     return launch_bf16(args, stream);
 }
 
 int launch_imu_forward_bf16_debug(const FwdArgs& a, int stage, float* dump, int* progress, cudaStream_t stream) {
-    Bf16Args args{a, stage, dump, progress};
+    // stage >= 100: `dump` is reinterpreted as the (10, TLOG_CAP, 2) int64 timeline buffer of block 0
+    Bf16Args args{a, stage >= 100 ? -1 : stage, stage >= 100 ? nullptr : dump, progress,
+                  stage >= 100 ? reinterpret_cast<long long*>(dump) : nullptr};
     return launch_bf16(args, stream);
 }
 

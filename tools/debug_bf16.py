@@ -58,8 +58,10 @@ def main():
     N = cm._native
     want = stages_oracle(xs, sd, dims)
     # biases folded into the residual dump: stage 0 holds h0 + b_o(0); stage 1 holds h1 + b_2(0); stage 2 h2 + b_o(1)
-    add = [sd["imu_encoder.transformer.layers.0.self_attn.out_proj.bias"], sd["imu_encoder.transformer.layers.0.linear2.bias"],
-           sd["imu_encoder.transformer.layers.1.self_attn.out_proj.bias"]]
+    def bo_fold(l):   # b_o + W_o b_v (the value bias is folded into the out-proj bias at pack time)
+        pre = f"imu_encoder.transformer.layers.{l}.self_attn."
+        return sd[pre + "out_proj.bias"] + sd[pre + "out_proj.weight"] @ sd[pre + "in_proj_bias"][256:]
+    add = [bo_fold(0), sd["imu_encoder.transformer.layers.0.linear2.bias"], bo_fold(1)]
     tiles = (n + 7) // 8
     for stage in (0, 1, 2):
         dump = torch.full((tiles * 128, 128), float("nan"), device=DEV)

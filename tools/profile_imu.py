@@ -14,11 +14,12 @@ clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg).to("cuda").eval()
 x = torch.randn(batch, 6, 250, device="cuda")
 out = {}
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+clf.forward_scores(x, precision=prec, out=out)
+torch.cuda.synchronize()
+ev0.record()
 for i in range(reps):
-    if i == reps - 1:
-        ev0.record()
     clf.forward_scores(x, precision=prec, out=out)
 ev1.record()
 torch.cuda.synchronize()
-ms = ev0.elapsed_time(ev1)
+ms = ev0.elapsed_time(ev1) / reps
 print(f"batch {batch} {prec}: {ms:.3f} ms/launch -> {batch / ms * 1e3:.0f} windows/s, {25890816 * batch / ms / 1e9:.1f} TFLOP/s")
