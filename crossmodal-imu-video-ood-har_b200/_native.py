@@ -72,8 +72,9 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "cmhar_linear_blob_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "cmhar_linear_pack": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cmhar_linear_work_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "cmhar_linear_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-                                       C.c_void_p, C.c_int32, C.c_void_p]),
+                                       C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
     "cmhar_l2_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "cmhar_video_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]),

@@ -8,40 +8,63 @@
 
 namespace cmhar {
 
-constexpr int LT_ROWS = 32, LT_COLS = 64, LT_K = 32;
+constexpr int LT_ROWS = 32, LT_COLS = 64, LT_K = 32, LT_SPLIT_MAX = 8;
 
 // y (n,N) = act(x (n,K) @ Wt (K,N) + b);  K % 4 == 0, N % 4 == 0.
-// 32 x 64 output tile per CTA (128 threads, 4 x 4 register micro-tiles), both operands staged through
-// shared memory in 32-deep k slabs.  Small tiles on purpose: the callers are the projection heads at
-// batch 256 (M = 256), where a 64 x 128 tiling would leave 140 of 148 SMs idle.
+// 32 x 64 output tile per CTA (128 threads, 4 x 4 register micro-tiles).  The callers are the
+// projection heads at batch 256 (M = 256): the problem is latency-bound, not FLOP-bound, so
+//   * tiles are small (a 64 x 128 tiling would leave 140 of 148 SMs idle),
+//   * the k loop is split over gridDim.z CTAs (each k slice lands in its own partial buffer and a
+//     fixed-order reduction adds them: deterministic, no atomics),
+//   * the next k slab is prefetched into registers while the current one is multiplied.
 __global__ void __launch_bounds__(128) linear_fp32_kernel(const float* __restrict__ Wt, const float* __restrict__ bias,
                                                           const float* __restrict__ X, long long n, int K, int N,
-                                                          int relu, float* __restrict__ Y) {
+                                                          int relu, float* __restrict__ Y, float* __restrict__ partial) {
     __shared__ __align__(16) float As[LT_K][LT_ROWS + 4];     // transposed: As[k][row]
     __shared__ __align__(16) float Ws[LT_K][LT_COLS];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;        // cols tx*4.., rows ty*4..
     const long long row0 = (long long)blockIdx.x * LT_ROWS;
     const int col0 = blockIdx.y * LT_COLS;
+    const int slabs = (K + LT_K - 1) / LT_K;
+    const int per = (slabs + gridDim.z - 1) / gridDim.z;
+    const int s_begin = blockIdx.z * per, s_end = min(slabs, s_begin + per);
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += LT_K) {
-        __syncthreads();
-        for (int e = tid; e < LT_ROWS * (LT_K / 4); e += 128) {       // X tile: 32 rows x 8 float4
-            const int r = e >> 3, k4 = (e & 7) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + r < n && k0 + k4 < K) v = __ldg(reinterpret_cast<const float4*>(X + (row0 + r) * K + k0 + k4));
-            As[k4][r] = v.x; As[k4 + 1][r] = v.y; As[k4 + 2][r] = v.z; As[k4 + 3][r] = v.w;
+    // per-thread prefetch registers: 2 float4 of X (32 rows x 8 float4 / 128 thr) and 4 float4 of W
+    float4 xa[2], wa[4];
+    auto fetch = [&](int slab) {
+        const int k0 = slab * LT_K;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int e = tid + q * 128, r = e >> 3, k4 = (e & 7) * 4;
+            xa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < n && k0 + k4 < K) xa[q] = __ldg(reinterpret_cast<const float4*>(X + (row0 + r) * K + k0 + k4));
         }
-        for (int e = tid; e < LT_K * (LT_COLS / 4); e += 128) {       // W slab: 32 k x 16 float4
-            const int k = e >> 4, c4 = (e & 15) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k0 + k < K && col0 + c4 < N) v = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k0 + k) * N + col0 + c4));
-            *reinterpret_cast<float4*>(&Ws[k][c4]) = v;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = tid + q * 128, k = e >> 4, c4 = (e & 15) * 4;
+            wa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + k < K && col0 + c4 < N) wa[q] = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k0 + k) * N + col0 + c4));
+        }
+    };
+    if (s_begin < s_end) fetch(s_begin);
+    for (int slab = s_begin; slab < s_end; ++slab) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int e = tid + q * 128, r = e >> 3, k4 = (e & 7) * 4;
+            As[k4][r] = xa[q].x; As[k4 + 1][r] = xa[q].y; As[k4 + 2][r] = xa[q].z; As[k4 + 3][r] = xa[q].w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = tid + q * 128, k = e >> 4, c4 = (e & 15) * 4;
+            *reinterpret_cast<float4*>(&Ws[k][c4]) = wa[q];
         }
         __syncthreads();
+        if (slab + 1 < s_end) fetch(slab + 1);               // in flight while this slab is multiplied
 #pragma unroll 8
         for (int k = 0; k < LT_K; ++k) {
             const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -55,6 +78,16 @@ __global__ void __launch_bounds__(128) linear_fp32_kernel(const float* __restric
     }
     const int col = col0 + tx * 4;
     if (col >= N) return;
+    if (gridDim.z > 1) {                                      // k-split: raw partial sums, finished by linear_reduce_kernel
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long r = row0 + ty * 4 + i;
+            if (r < n)
+                *reinterpret_cast<float4*>(partial + ((size_t)blockIdx.z * n + r) * N + col) =
+                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        return;
+    }
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -64,6 +97,21 @@ __global__ void __launch_bounds__(128) linear_fp32_kernel(const float* __restric
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         *reinterpret_cast<float4*>(Y + r * N + col) = o;
     }
+}
+
+// y = act(sum_z partial[z] + b), fixed summation order
+__global__ void __launch_bounds__(256) linear_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                            long long n, int N, int splits, int relu, float* __restrict__ Y) {
+    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total4 = n * N / 4;
+    if (i4 >= total4) return;
+    float4 s = __ldg(reinterpret_cast<const float4*>(bias + (i4 * 4) % N));
+    for (int z = 0; z < splits; ++z) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(partial + (size_t)z * n * N) + i4);
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+    if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+    reinterpret_cast<float4*>(Y)[i4] = s;
 }
 
 // one warp per row: y = x / max(||x||, 1e-12)
@@ -154,16 +202,36 @@ int cmhar_linear_pack(const float* weight, const float* bias, const float* bn_we
     return CMHAR_OK;
 }
 
+size_t cmhar_linear_work_bytes(int64_t n, int32_t out_dim) {
+    return (size_t)LT_SPLIT_MAX * (size_t)(n > 0 ? n : 0) * (size_t)out_dim * sizeof(float);
+}
+
 int cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in_dim, int32_t out_dim, int32_t relu,
-                         float* y, int32_t precision, cmhar_stream_t s) {
+                         float* y, void* work, size_t work_bytes, int32_t precision, cmhar_stream_t s) {
     CMHAR_REQUIRE(blob && x && y, "cmhar_linear_forward: null argument");
     CMHAR_REQUIRE(cmhar_linear_blob_bytes(in_dim, out_dim) != 0, "linear dims (%d,%d) must be multiples of 4", in_dim, out_dim);
     CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
     if (n <= 0) return CMHAR_OK;
     const float* f = reinterpret_cast<const float*>(reinterpret_cast<const char*>(blob) + sizeof(BlobHeader));
-    dim3 grid((unsigned)((n + LT_ROWS - 1) / LT_ROWS), (unsigned)((out_dim + LT_COLS - 1) / LT_COLS));
-    linear_fp32_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(f, f + (size_t)in_dim * out_dim, x, n, in_dim, out_dim, relu, y);
+    const unsigned gx = (unsigned)((n + LT_ROWS - 1) / LT_ROWS), gy = (unsigned)((out_dim + LT_COLS - 1) / LT_COLS);
+    // k-split only when the plain grid cannot fill the machine and the caller gave a workspace
+    int splits = 1;
+    if (work && (long long)gx * gy < sm_count()) {
+        const int slabs = (in_dim + LT_K - 1) / LT_K;
+        splits = (int)((2LL * sm_count() + (long long)gx * gy - 1) / ((long long)gx * gy));
+        if (splits > LT_SPLIT_MAX) splits = LT_SPLIT_MAX;
+        if (splits > slabs) splits = slabs;
+        if ((size_t)splits * n * out_dim * sizeof(float) > work_bytes) splits = 1;
+    }
+    linear_fp32_kernel<<<dim3(gx, gy, splits), 128, 0, (cudaStream_t)s>>>(f, f + (size_t)in_dim * out_dim, x, n, in_dim, out_dim,
+                                                                          relu, y, reinterpret_cast<float*>(work));
     CMHAR_LAUNCH_CHECK();
+    if (splits > 1) {
+        const long long total4 = n * out_dim / 4;
+        linear_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)s>>>(
+            reinterpret_cast<const float*>(work), f + (size_t)in_dim * out_dim, n, out_dim, splits, relu, y);
+        CMHAR_LAUNCH_CHECK();
+    }
     return CMHAR_OK;
 }
 

@@ -28,20 +28,26 @@ namespace tc {
 constexpr int CHUNK = 16384;                 // bytes of one [128 x 64] bf16 SW128 chunk
 constexpr int NSTAGE = 4;
 constexpr int CHUNKS_PER_LAYER = 24;
-constexpr int NT_EPI = 256, NT_TC = 320;
-constexpr int MMA_WARP = 8, LOAD_WARP = 9;
+// roles: 4*NQ epilogue warps (NQ = column splits per row), then the MMA warp, then the weight producer
 
 // shared memory map (bytes)
 constexpr int OFF_HA = 0;                    // h as bf16 A/B operand          [128 x 128]  2 chunks
 constexpr int OFF_Q = 32768;                 // Q (later O, hidden chunk 0)    [128 x 128]
 constexpr int OFF_K = 65536;                 // K (hidden chunk 1)
 constexpr int OFF_VT = 98304;                // V^T (hidden chunk 2)
-constexpr int OFF_P = 131072;                // P block-diagonal (hidden chunk 3)
+constexpr int OFF_P = 131072;                // parameter staging (static block | LN stats | per-layer blocks)
 constexpr int OFF_W = 163840;                // weight ring, NSTAGE chunks
 constexpr int OFF_STAT = OFF_W + NSTAGE * CHUNK;   // LN partial stats [2][128] float2 = 2 KiB
 constexpr int OFF_BAR = OFF_STAT + 2048;     // mbarriers (8 B each) + tmem pointer
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB");
+// fp32 parameters the epilogue needs, staged in shared memory by the producer (with 227 KiB of
+// shared memory the L1 is ~1 KiB, so every __ldg of a bias / LayerNorm vector was an L2 round trip
+// on the critical path).  Static block: once per CTA.  Per-layer block: double buffered.
+constexpr int SB_TOK = 0, SB_FLN = 2048, SB_BO0 = 2304, SB_FLOATS = 2432;              // tok_bias | final LN g,b | bo_fold[0]
+constexpr int PB_BQ = 0, PB_B1 = 128, PB_B2 = 640, PB_LN1 = 768, PB_LN2 = 1024, PB_BON = 1280, PB_FLOATS = 1408;
+constexpr int OFF_SB = OFF_P, OFF_LNSTAT = OFF_P + 10240, OFF_PB = OFF_P + 16384;
+static_assert(SB_FLOATS * 4 <= 10240 && OFF_PB + 2 * PB_FLOATS * 4 <= OFF_P + 32768, "parameter staging overflows the P region");
 
 // barrier indices
 enum {
@@ -52,8 +58,12 @@ enum {
     B_QKV = B_HA + 1,            // Q,K,V^T in smem, P zeroed              (256)
     B_P = B_QKV + 1,             // P (all heads) in smem                  (256)
     B_O = B_P + 1,               // O in smem                              (256)
-    B_HID = B_O + 1,             // [4] hidden chunk c in smem             (256)
-    B_COUNT = B_HID + 4          // one barrier per chunk: a waiter may never fall two phases behind
+    B_HID = B_O + 1,             // [4] hidden chunk c in smem (one barrier per chunk: a waiter may never fall two phases behind)
+    B_H0FREE = B_HID + 4,        // FFN2 k-chunk 0 done reading hidden chunk 0 (its buffer takes chunk 3)  (commit)
+    B_PBFULL = B_H0FREE + 1,     // [2] per-layer parameter block landed   (tx)
+    B_PBEMPTY = B_PBFULL + 2,    // [2] epilogue finished with the block   (epilogue warps)
+    B_STATIC = B_PBEMPTY + 2,    // static parameter block landed          (tx)
+    B_COUNT = B_STATIC + 1
 };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier area too small");
 
@@ -108,7 +118,8 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NTH>
+__device__ __forceinline__ void epi_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major SWIZZLE_128B
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
@@ -226,12 +237,15 @@ struct Bf16Args {
     int dbg_stage;          // <0: off; else dump the residual (fp32 [128][128] per tile) after that stage
     float* dbg_out;
     volatile int* progress; // debug: host-mapped [grid][16] progress codes (survive a trap), or null
-    long long* tlog;        // debug: device [10 warps][TLOG_CAP][2] (code, clock64) of block 0, or null
+    long long* tlog;        // debug: device [18 warps][TLOG_CAP][2] (code, clock64) of block 0, or null
 };
 constexpr int TLOG_CAP = 1024;
 
 // ======================================================================================== kernel
-__global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Args args) {
+template <int NQ>
+__global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(const Bf16Args args) {
+    constexpr int NT_EPI = 128 * NQ, CW = 128 / NQ, MMA_WARP = 4 * NQ, LOAD_WARP = 4 * NQ + 1;
+    auto epi_bar = [] { epi_bar_n<NT_EPI>(); };
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     uint8_t* const smem = smem_tc;
     const FwdArgs& a = args.f;
@@ -242,7 +256,8 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
     const size_t fp32_bytes = (EncLayout::fp32_floats(n_layers) * sizeof(float) + 1023) / 1024 * 1024;
     const uint8_t* wchunks = reinterpret_cast<const uint8_t*>(a.enc_blob) + 1024 + fp32_bytes;
     const int n_chunks = 1 + n_layers * CHUNKS_PER_LAYER;
-    const float* bo_fold = reinterpret_cast<const float*>(wchunks + (size_t)n_chunks * CHUNK);   // [layers][128]: b_o + W_o b_v
+    // after the chunks: static parameter block, then one parameter block per layer (see pack_param_blocks_kernel)
+    const float* gparams = reinterpret_cast<const float*>(wchunks + (size_t)n_chunks * CHUNK);
     const long long tiles = (a.n + 7) / 8;
 
     int tlog_n = 0;
@@ -258,11 +273,16 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(BAR(B_WFULL + s), 1); mbar_init(BAR(B_WEMPTY + s), 1); }
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_ACC + i), 1);
-        mbar_init(BAR(B_HA), NT_EPI);
-        mbar_init(BAR(B_QKV), NT_EPI);
-        mbar_init(BAR(B_P), NT_EPI);
-        mbar_init(BAR(B_O), NT_EPI);
-        for (int i = 0; i < 4; ++i) mbar_init(BAR(B_HID + i), NT_EPI);
+        // epilogue -> MMA barriers: ONE arrival per epilogue warp (lane 0 after __syncwarp), not per thread
+        mbar_init(BAR(B_HA), NT_EPI / 32);
+        mbar_init(BAR(B_QKV), NT_EPI / 32);
+        mbar_init(BAR(B_P), NT_EPI / 32);
+        mbar_init(BAR(B_O), NT_EPI / 32);
+        for (int i = 0; i < 4; ++i) mbar_init(BAR(B_HID + i), NT_EPI / 32);
+        mbar_init(BAR(B_H0FREE), 1);
+        mbar_init(BAR(B_PBFULL), 1); mbar_init(BAR(B_PBFULL + 1), 1);
+        mbar_init(BAR(B_PBEMPTY), NT_EPI / 32); mbar_init(BAR(B_PBEMPTY + 1), NT_EPI / 32);
+        mbar_init(BAR(B_STATIC), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -278,8 +298,19 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
         // ================================================================= weight producer
         if (lane == 0) {
             uint32_t stage = 0, parity = 1;           // fresh barriers: waiting on parity 1 passes
+            uint32_t pb_parity[2] = {1, 1};
+            mbar_expect_tx(BAR(B_STATIC), SB_FLOATS * 4);
+            bulk_g2s(sbase + OFF_SB, gparams, SB_FLOATS * 4, BAR(B_STATIC));
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 for (int c = 0; c < n_chunks; ++c) {
+                    if (c >= 1 && (c - 1) % CHUNKS_PER_LAYER == 0) {       // first chunk of layer l: stage its parameter block
+                        const int l = (c - 1) / CHUNKS_PER_LAYER, b = l & 1;
+                        mbar_wait(BAR(B_PBEMPTY + b), pb_parity[b], 19);
+                        pb_parity[b] ^= 1;
+                        mbar_expect_tx(BAR(B_PBFULL + b), PB_FLOATS * 4);
+                        bulk_g2s(sbase + OFF_PB + b * PB_FLOATS * 4, gparams + SB_FLOATS + (size_t)l * PB_FLOATS, PB_FLOATS * 4,
+                                 BAR(B_PBFULL + b));
+                    }
                     mbar_wait(BAR(B_WEMPTY + stage), parity, 1);
                     mbar_expect_tx(BAR(B_WFULL + stage), CHUNK);
                     bulk_g2s(sbase + OFF_W + stage * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(B_WFULL + stage));
@@ -371,10 +402,12 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                     for (int c = 0; c < 4; ++c) {
                         PROG(10); mbar_wait(BAR(B_HID + c), ph.next(B_HID + c), 10); PROG(1010);     // hidden chunk c in smem (and its TMEM buffer drained)
                         tc_fence_after();
-                        const uint64_t dHid = sw128_desc(sbase + OFF_Q + c * 32768);
+                        const uint64_t dHid = sw128_desc(sbase + OFF_Q + (c == 3 ? 0 : c) * 32768);   // chunk 3 lives in buffer 0
                         gemm_chunk(tmem + TM_R, dHid, false, true, 4);
                         gemm_chunk(tmem + TM_R, dHid + CH, false, true, 4);
-                        if (c == 0) {                              // 4th FFN1 chunk reuses buffer A
+                        if (c == 0) {
+                            if (leader) tc_commit(BAR(B_H0FREE));      // hidden buffer 0 may take chunk 3
+                            // 4th FFN1 chunk reuses TMEM buffer A
                             gemm_chunk(tmem + TM_A, dHA, false, false, 4);
                             gemm_chunk(tmem + TM_A, dHA + CH, false, true, 4);
                             if (leader) tc_commit(BAR(B_ACC + 0));
@@ -385,52 +418,60 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
             }
         }
     } else {
-        // ================================================================= epilogue (warps 0-7)
-        const int wg = warp >> 2;                          // column half / head parity
+        // ================================================================= epilogue (warps 0 .. 4*NQ-1)
+        const int wq = warp >> 2;                          // which CW-column slice of a 128-wide buffer
         const int row = (warp & 3) * 32 + lane;            // token row == TMEM lane
         const int win = row >> 4, tok = row & 15;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const int c0 = wg * 64;                            // this thread's 64 columns of a 128-wide buffer
-        float2* stats = reinterpret_cast<float2*>(smem + OFF_STAT);
+        const int c0 = wq * CW;                            // this thread's CW columns of a 128-wide buffer
+        // LayerNorm partial sums [NQ][128]
+        float2* stats = reinterpret_cast<float2*>(smem + OFF_LNSTAT);
+        const float* SB = reinterpret_cast<const float*>(smem + OFF_SB);       // static parameter block (smem)
+        // bf16 destination of this thread's 32-column batch starting at buffer column c: (chunk, piece)
+        auto chunk_of = [](int c) { return (c >> 6) * CHUNK; };
+        auto piece_of = [](int c) { return (c & 63) >> 3; };
         Phase ph;
         uint32_t v[32];
         float f[32];
 
+        auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };   // warp-uniform smem broadcast
         // finish a 128-wide fp32 row held in R: y -> hA (bf16), y + next_bias -> R
         auto write_h = [&](const float* y32, int cc, const float* next_bias) {
-            store_bf16_32(smem + OFF_HA + wg * CHUNK, row, (cc & 63) >> 3, y32);
+            store_bf16_32(smem + OFF_HA + chunk_of(c0 + cc), row, piece_of(c0 + cc), y32);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-                const float4 nb = __ldg(reinterpret_cast<const float4*>(next_bias + c0 + cc + i));
+                const float4 nb = ld4(next_bias + c0 + cc + i);
                 v[i] = __float_as_uint(y32[i] + nb.x); v[i + 1] = __float_as_uint(y32[i + 1] + nb.y);
                 v[i + 2] = __float_as_uint(y32[i + 2] + nb.z); v[i + 3] = __float_as_uint(y32[i + 3] + nb.w);
             }
             TMEM_ST32(lane_base + TM_R + c0 + cc, v);
         };
         // LayerNorm of the residual row in R (two threads per row exchange partial sums through smem)
-        auto layer_norm_R = [&](const float* gb, const float* next_bias, bool write_back, float* keep /*64 floats or null*/) {
+        auto layer_norm_R = [&](const float* gb, const float* next_bias, bool write_back, float* keep /*CW floats or null*/) {
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int cc = 0; cc < 64; cc += 32) {
+            for (int cc = 0; cc < CW; cc += 32) {
                 TMEM_LD32(lane_base + TM_R + c0 + cc, v);
                 tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) { const float x = __uint_as_float(v[i]); s1 += x; s2 = fmaf(x, x, s2); }
             }
-            stats[wg * 128 + row] = make_float2(s1, s2);
+            stats[wq * 128 + row] = make_float2(s1, s2);
             epi_bar();
-            const float2 o = stats[(wg ^ 1) * 128 + row];
-            const float mean = (s1 + o.x) * (1.f / D);
-            const float var = fmaxf((s2 + o.y) * (1.f / D) - mean * mean, 0.f);
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) { const float2 o = stats[q * 128 + row]; t1 += o.x; t2 += o.y; }
+            const float mean = t1 * (1.f / D);
+            const float var = fmaxf(t2 * (1.f / D) - mean * mean, 0.f);
             const float rstd = rsqrtf(var + LN_EPS);
 #pragma unroll
-            for (int cc = 0; cc < 64; cc += 32) {
+            for (int cc = 0; cc < CW; cc += 32) {
                 TMEM_LD32(lane_base + TM_R + c0 + cc, v);
                 tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(gb + c0 + cc + i));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(gb + D + c0 + cc + i));
+                    const float4 g = ld4(gb + c0 + cc + i);
+                    const float4 b = ld4(gb + D + c0 + cc + i);
                     f[i] = (__uint_as_float(v[i]) - mean) * rstd * g.x + b.x;
                     f[i + 1] = (__uint_as_float(v[i + 1]) - mean) * rstd * g.y + b.y;
                     f[i + 2] = (__uint_as_float(v[i + 2]) - mean) * rstd * g.z + b.z;
@@ -448,12 +489,13 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
             tc_wait_st();
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(BAR(bar_idx));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(bar_idx));
         };
         auto dump_R = [&](long long tile_idx) {
             float* dst = args.dbg_out + ((size_t)tile_idx * 128 + row) * D + c0;
 #pragma unroll
-            for (int cc = 0; cc < 64; cc += 32) {
+            for (int cc = 0; cc < CW; cc += 32) {
                 TMEM_LD32(lane_base + TM_R + c0 + cc, v);
                 tc_wait_ld();
 #pragma unroll
@@ -461,10 +503,12 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
             }
         };
 
+        mbar_wait(BAR(B_STATIC), 0, 20);
+        uint32_t pb_parity[2] = {0, 0};
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const long long w0 = tile * 8;
             // ---- stage patches (bf16, k = 16 -> pieces 0,1 of chunk 0 of hA) and preload R = tok_bias
-            if (wg == 0) {
+            if (wq == 0) {
                 float p16[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) p16[i] = 0.f;
@@ -491,12 +535,12 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                 }
             }
             {
-                const float* tb = encf + EncLayout::tok_bias + (tok < S ? tok : 0) * D + c0;
+                const float* tb = SB + SB_TOK + (tok < S ? tok : 0) * D + c0;
 #pragma unroll
-                for (int cc = 0; cc < 64; cc += 32) {
+                for (int cc = 0; cc < CW; cc += 32) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(tb + cc + i));
+                        const float4 t = *reinterpret_cast<const float4*>(tb + cc + i);
                         v[i] = __float_as_uint(t.x); v[i + 1] = __float_as_uint(t.y);
                         v[i + 2] = __float_as_uint(t.z); v[i + 3] = __float_as_uint(t.w);
                     }
@@ -509,34 +553,36 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
             tc_fence_after();
             {
 #pragma unroll
-                for (int cc = 0; cc < 64; cc += 32) {
+                for (int cc = 0; cc < CW; cc += 32) {
                     TMEM_LD32(lane_base + TM_R + c0 + cc, v);
                     tc_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    write_h(f, cc, bo_fold);
+                    write_h(f, cc, SB + SB_BO0);
                 }
             }
             if (args.dbg_stage == 0) { tc_wait_st(); dump_R(tile); }
             publish(B_HA);
 
             for (int l = 0; l < n_layers; ++l) {
-                const float* L = encf + EncLayout::layers0 + (size_t)l * EncLayout::layer_floats;
                 const bool last = (l + 1 == n_layers);
+                const float* PB = reinterpret_cast<const float*>(smem + OFF_PB + (l & 1) * PB_FLOATS * 4);
+                mbar_wait(BAR(B_PBFULL + (l & 1)), pb_parity[l & 1], 21);
+                pb_parity[l & 1] ^= 1;
                 // ---- drain Q, K (bias per column) and V^T (bias per lane) into smem as bf16
 #pragma unroll 1
                 for (int m = 0; m < 3; ++m) {
                     PROG(12); mbar_wait(BAR(B_ACC + m), ph.next(B_ACC + m), 12); PROG(1012);
                     tc_fence_after();
-                    uint8_t* dst = smem + OFF_Q + m * 32768 + wg * CHUNK;
+                    uint8_t* dst = smem + OFF_Q + m * 32768;
 #pragma unroll
-                    for (int cc = 0; cc < 64; cc += 32) {
+                    for (int cc = 0; cc < CW; cc += 32) {
                         TMEM_LD32(lane_base + 128 * m + c0 + cc, v);
                         tc_wait_ld();
                         if (m == 0) {     // q bias (pre-scaled); the k bias cancels in the softmax, the v bias is folded into b_o
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(L + EncLayout::l_b_in + c0 + cc + i));
+                                const float4 b = ld4(PB + PB_BQ + c0 + cc + i);
                                 f[i] = __uint_as_float(v[i]) + b.x; f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
                                 f[i + 2] = __uint_as_float(v[i + 2]) + b.z; f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
                             }
@@ -544,16 +590,16 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
 #pragma unroll
                             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                         }
-                        store_bf16_32(dst, row, cc >> 3, f);
+                        store_bf16_32(dst + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
                     }
                 }
                 PROG(100 + l);
                 publish(B_QKV);
-                // ---- softmax: this thread owns heads 4wg..4wg+3 of its row (16 compact scores each)
+                // ---- softmax: this thread owns the heads whose 16 compact scores fall into its CW columns
                 PROG(13); mbar_wait(BAR(B_ACC + 0), ph.next(B_ACC + 0), 13); PROG(1013);
                 tc_fence_after();
 #pragma unroll
-                for (int cc = 0; cc < 64; cc += 32) {
+                for (int cc = 0; cc < CW; cc += 32) {
                     TMEM_LD32(lane_base + TM_A + c0 + cc, v);
                     tc_wait_ld();
 #pragma unroll
@@ -575,25 +621,25 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
-                    TMEM_ST16(lane_base + TM_P + 32 * wg + (cc >> 1), pk);
+                    TMEM_ST16(lane_base + TM_P + ((c0 + cc) >> 1), pk);
                 }
                 publish(B_P);
                 // ---- O (buffer C) -> smem (Q region) as bf16
                 PROG(15); mbar_wait(BAR(B_ACC + 2), ph.next(B_ACC + 2), 15); PROG(1015);
                 tc_fence_after();
 #pragma unroll
-                for (int cc = 0; cc < 64; cc += 32) {
+                for (int cc = 0; cc < CW; cc += 32) {
                     TMEM_LD32(lane_base + TM_C + c0 + cc, v);
                     tc_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    store_bf16_32(smem + OFF_Q + wg * CHUNK, row, cc >> 3, f);
+                    store_bf16_32(smem + OFF_Q + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
                 }
                 publish(B_O);
                 // ---- LN1: h1 = LN(R) ; hA = bf16(h1) ; R = h1 + b_2
                 PROG(16); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 16); PROG(1016);
                 tc_fence_after();
-                layer_norm_R(L + EncLayout::l_ln1, L + EncLayout::l_b2, true, nullptr);
+                layer_norm_R(PB + PB_LN1, PB + PB_B2, true, nullptr);
                 if (args.dbg_stage == 1 && l == 0) { tc_wait_st(); dump_R(tile); }
                 publish(B_HA);
                 // ---- FFN1 chunks: relu(acc + b_1) -> hidden chunk c (bf16)
@@ -603,17 +649,18 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                     PROG(17); mbar_wait(BAR(B_ACC + buf), ph.next(B_ACC + buf), 17); PROG(1017);
                     PROG(170 + c);
                     tc_fence_after();
+                    if (c == 3) mbar_wait(BAR(B_H0FREE), ph.next(B_H0FREE), 22);     // FFN2 k-chunk 0 finished with buffer 0
 #pragma unroll
-                    for (int cc = 0; cc < 64; cc += 32) {
+                    for (int cc = 0; cc < CW; cc += 32) {
                         TMEM_LD32(lane_base + 128 * buf + c0 + cc, v);
                         tc_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(L + EncLayout::l_b1 + c * 128 + c0 + cc + i));
+                            const float4 b = ld4(PB + PB_B1 + c * 128 + c0 + cc + i);
                             f[i] = fmaxf(__uint_as_float(v[i]) + b.x, 0.f); f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
                             f[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f); f[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
                         }
-                        store_bf16_32(smem + OFF_Q + c * 32768 + wg * CHUNK, row, cc >> 3, f);
+                        store_bf16_32(smem + OFF_Q + (c == 3 ? 0 : c) * 32768 + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
                     }
                     PROG(180 + c);
                     publish(B_HID + c);
@@ -623,40 +670,46 @@ __global__ void __launch_bounds__(NT_TC, 1) imu_forward_bf16_kernel(const Bf16Ar
                 PROG(18); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 18); PROG(1018);
                 tc_fence_after();
                 if (!last) {
-                    layer_norm_R(L + EncLayout::l_ln2, bo_fold + (l + 1) * D, true, nullptr);
+                    layer_norm_R(PB + PB_LN2, PB + PB_BON, true, nullptr);
                     if (args.dbg_stage == 2 && l == 0) { tc_wait_st(); dump_R(tile); }
                     publish(B_HA);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(B_PBEMPTY + (l & 1)));        // parameter block free for layer l+2
                 } else {
                     // last layer: LN2 then the encoder's final LayerNorm (models.py:127), fp32 in registers
-                    float y[64];
-                    layer_norm_R(L + EncLayout::l_ln2, nullptr, false, y);
+                    float y[CW];
+                    layer_norm_R(PB + PB_LN2, nullptr, false, y);
                     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) { s1 += y[i]; s2 = fmaf(y[i], y[i], s2); }
-                    stats[wg * 128 + row] = make_float2(s1, s2);
+                    for (int i = 0; i < CW; ++i) { s1 += y[i]; s2 = fmaf(y[i], y[i], s2); }
+                    stats[wq * 128 + row] = make_float2(s1, s2);
                     epi_bar();
-                    const float2 o = stats[(wg ^ 1) * 128 + row];
-                    const float mean = (s1 + o.x) * (1.f / D);
-                    const float rstd = rsqrtf(fmaxf((s2 + o.y) * (1.f / D) - mean * mean, 0.f) + LN_EPS);
-                    const float* gb = encf + EncLayout::final_ln;
+                    float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) y[i] = (y[i] - mean) * rstd * __ldg(gb + c0 + i) + __ldg(gb + D + c0 + i);
+                    for (int q = 0; q < NQ; ++q) { const float2 o = stats[q * 128 + row]; t1 += o.x; t2 += o.y; }
+                    const float mean = t1 * (1.f / D);
+                    const float rstd = rsqrtf(fmaxf(t2 * (1.f / D) - mean * mean, 0.f) + LN_EPS);
+                    const float* gb = SB + SB_FLN;
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) y[i] = (y[i] - mean) * rstd * gb[c0 + i] + gb[D + c0 + i];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(B_PBEMPTY + (l & 1)));
                     const bool valid = (w0 + win < a.n);
                     if (a.tokens_out && valid && tok < S) {
                         float4* dst = reinterpret_cast<float4*>(a.tokens_out + ((w0 + win) * S + tok) * D + c0);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                        for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
                     }
                     // CLS rows -> head scratch in the (now dead) Q region: feat [8][128] fp32
                     float* feat = reinterpret_cast<float*>(smem + OFF_Q);
                     if (tok == 0) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
+                        for (int i = 0; i < CW / 4; ++i)
                             reinterpret_cast<float4*>(feat + win * D + c0)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
                         if (a.cls_out && valid) {
                             float4* dst = reinterpret_cast<float4*>(a.cls_out + (w0 + win) * D + c0);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                            for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
                         }
                     }
                     epi_bar();
@@ -745,12 +798,38 @@ __global__ void fold_value_bias_kernel(const float* __restrict__ wo, const float
     dst[n] = (float)acc;
 }
 
+// Gathers the epilogue's fp32 parameters into the staging images the producer bulk-copies into shared memory:
+// static block [tok_bias 16x128 | final LN g,b | bo_fold(0)], then per layer
+// [b_q (x1/4) | b_1 | b_2 | LN1 g,b | LN2 g,b | bo_fold(l+1)].   fp32 = the packed fp32 section, fold = bo_fold.
+__global__ void pack_param_blocks_kernel(const float* __restrict__ fp32, const float* __restrict__ fold, int layers,
+                                         float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = SB_FLOATS + layers * PB_FLOATS;
+    if (i >= total) return;
+    float v;
+    if (i < SB_FLOATS) {
+        if (i < SB_FLN) v = fp32[EncLayout::tok_bias + i];
+        else if (i < SB_BO0) v = fp32[EncLayout::final_ln + (i - SB_FLN)];
+        else v = fold[i - SB_BO0];
+    } else {
+        const int l = (i - SB_FLOATS) / PB_FLOATS, o = (i - SB_FLOATS) % PB_FLOATS;
+        const float* L = fp32 + EncLayout::layers0 + (size_t)l * EncLayout::layer_floats;
+        if (o < PB_B1) v = L[EncLayout::l_b_in + o];
+        else if (o < PB_B2) v = L[EncLayout::l_b1 + (o - PB_B1)];
+        else if (o < PB_LN1) v = L[EncLayout::l_b2 + (o - PB_B2)];
+        else if (o < PB_LN2) v = L[EncLayout::l_ln1 + (o - PB_LN1)];
+        else if (o < PB_BON) v = L[EncLayout::l_ln2 + (o - PB_LN2)];
+        else v = (l + 1 < layers) ? fold[(l + 1) * D + (o - PB_BON)] : 0.f;
+    }
+    dst[i] = v;
+}
+
 size_t encoder_bf16_bytes(int layers) {
-    return (size_t)(1 + layers * CHUNKS_PER_LAYER) * CHUNK + (size_t)CMHAR_MAX_LAYERS * D * sizeof(float);
+    return (size_t)(1 + layers * CHUNKS_PER_LAYER) * CHUNK +
+           (size_t)(SB_FLOATS + CMHAR_MAX_LAYERS * PB_FLOATS + CMHAR_MAX_LAYERS * D) * sizeof(float);
 }
 
 int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_section, void* bf16_section, cudaStream_t st) {
-    (void)fp32_section;
     uint8_t* dst = reinterpret_cast<uint8_t*>(bf16_section);
     int c = 0;
     auto put = [&](const float* src, int ld, int row0, int col0, int ncols, float scale) -> int {
@@ -776,12 +855,16 @@ int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_secti
             for (int k = 0; k < 2; ++k) PUT(q.linear2_weight, FF, 0, kc * 128 + k * 64, 64, 1.f);
     }
 #undef PUT
-    float* fold = reinterpret_cast<float*>(dst + (size_t)c * CHUNK);
+    float* params = reinterpret_cast<float*>(dst + (size_t)c * CHUNK);
+    float* fold = params + SB_FLOATS + CMHAR_MAX_LAYERS * PB_FLOATS;            // scratch behind the staging images
     for (int l = 0; l < p->layers; ++l) {
         const cmhar_encoder_layer_params& q = p->layer[l];
         fold_value_bias_kernel<<<1, 128, 0, st>>>(q.out_proj_weight, q.out_proj_bias, q.in_proj_bias + 2 * D, fold + l * D);
         CMHAR_LAUNCH_CHECK();
     }
+    const int total = SB_FLOATS + p->layers * PB_FLOATS;
+    pack_param_blocks_kernel<<<(total + 255) / 256, 256, 0, st>>>(fp32_section, fold, p->layers, params);
+    CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }
 
@@ -789,13 +872,20 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
     static bool configured[64] = {};
     int dev = 0;
     CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
+    static int nq = 0;
+    if (nq == 0) {
+        const char* e = getenv("CMHAR_EPI_WARPS");      // 8 or 16 epilogue warps (development switch)
+        nq = (e && atoi(e) == 8) ? 2 : 4;
+    }
     if (!configured[dev & 63]) {
-        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(imu_forward_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(imu_forward_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(imu_forward_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured[dev & 63] = true;
     }
     const long long tiles = (args.f.n + 7) / 8;
     const int grid = (int)((tiles < (long long)sm_count()) ? tiles : (long long)sm_count());
-    imu_forward_bf16_kernel<<<grid, NT_TC, SMEM_BYTES, stream>>>(args);
+    if (nq == 2) imu_forward_bf16_kernel<2><<<grid, 320, SMEM_BYTES, stream>>>(args);
+    else imu_forward_bf16_kernel<4><<<grid, 576, SMEM_BYTES, stream>>>(args);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }

@@ -87,9 +87,9 @@ __device__ __forceinline__ void layer_norm_rows(float* h, const float* __restric
 
 // Classifier head (models.py:312-326,338, BN folded) + arg-max / MSP / energy (+ Mahalanobis) for
 // up to 8 feature rows held in buf[0..8*128) (rows >= wpb are zero).  Scratch lives in buf.
-template <bool NAMED>
+template <int NTH, bool NAMED>
 __device__ __forceinline__ void block_sync() {
-    if (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory");     // the 256 epilogue threads of the bf16 kernel
+    if (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory");   // the epilogue threads of the bf16 kernel
     else __syncthreads();
 }
 
@@ -119,7 +119,7 @@ __device__ __forceinline__ void head_and_scores_t(float* buf, int wpb, long long
 #pragma unroll
             for (int w = 0; w < 8; ++w) hid1[w * 256 + j] = fmaxf(acc[w] + bv, 0.f);
         }
-        block_sync<NAMED>();
+        block_sync<NTH, NAMED>();
         for (int j = tid; j < hl.h2; j += NT) {          // Linear(h1->h2)+BN folded, ReLU
             float acc[8];
 #pragma unroll
@@ -134,7 +134,7 @@ __device__ __forceinline__ void head_and_scores_t(float* buf, int wpb, long long
 #pragma unroll
             for (int w = 0; w < 8; ++w) hid2[w * 256 + j] = fmaxf(acc[w] + bv, 0.f);
         }
-        block_sync<NAMED>();
+        block_sync<NTH, NAMED>();
         for (int j = tid; j < hl.C; j += NT) {           // Linear(h2->classes)
             float acc[8];
 #pragma unroll
@@ -149,7 +149,7 @@ __device__ __forceinline__ void head_and_scores_t(float* buf, int wpb, long long
 #pragma unroll
             for (int w = 0; w < 8; ++w) logit[w * 64 + j] = acc[w] + bv;
         }
-        block_sync<NAMED>();
+        block_sync<NTH, NAMED>();
         if (warp < wpb && w0 + warp < a.n) {             // warp w scores window w
             const long long gw = w0 + warp;
             const int C = hl.C;
@@ -185,7 +185,7 @@ __device__ __forceinline__ void head_and_scores_t(float* buf, int wpb, long long
 #pragma unroll
             for (int w = 0; w < 8; ++w) white[w * D + j] = acc[w];
         }
-        block_sync<NAMED>();
+        block_sync<NTH, NAMED>();
         if (warp < wpb && w0 + warp < a.n) {
             const float4 y = *reinterpret_cast<const float4*>(white + warp * D + lane * 4);
             float best = INFINITY;

@@ -320,9 +320,15 @@ class _PackedLinear:
         x = N.f32c(x)
         n = x.shape[0]
         y = out if out is not None else torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)
+        lib = N.lib()
+        work, wbytes = None, 0
+        if 0 < n <= 2048:        # small batches: workspace for the deterministic k-split
+            wbytes = lib.cmhar_linear_work_bytes(n, self.out_dim)
+            work = torch.empty(wbytes, dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
-            N.check(N.lib().cmhar_linear_forward(self.blob.data_ptr(), x.data_ptr(), n, self.in_dim, self.out_dim,
-                                                 int(relu), y.data_ptr(), _prec_code(precision), N.stream_ptr(x.device)))
+            N.check(lib.cmhar_linear_forward(self.blob.data_ptr(), x.data_ptr(), n, self.in_dim, self.out_dim,
+                                             int(relu), y.data_ptr(), N.ptr(work), wbytes, _prec_code(precision),
+                                             N.stream_ptr(x.device)))
         return y
 
 

@@ -34,6 +34,7 @@ class CrossModalOODPipeline:
             self.clf.set_mahalanobis(mahalanobis)
         self.sig = (float(sigmoid_scale), float(sigmoid_bias))
         self._host = None
+        self._side = None           # side stream: the video branch runs concurrently with the IMU kernel
 
     @torch.no_grad()
     def run(self, imu: torch.Tensor, fmap: Optional[torch.Tensor], window_stride: Optional[int] = None
@@ -41,12 +42,25 @@ class CrossModalOODPipeline:
         """imu (B,6,L) fp32 [or compact (B,live) with window_stride]; fmap (B*frames,F,h,w) bf16/fp32
         or None for the IMU-only path.  Returns device tensors: pred, msp, energy, (maha,) logits,
         cls and, with fmap, imu_proj, video_proj, loss (mean sigmoid contrastive loss, fp64 0-dim)."""
-        out = self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
         if fmap is None:
-            return out
-        vfeat = self.xm.video_encoder.forward_features(fmap, self.frames, precision=self.precision)
+            return self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
+        # fork: the HBM-bound video tail + its projection head on a side stream, the tensor-bound IMU
+        # kernel + its projection head on the current stream; join before the similarity kernel.
+        # (Captured into a CUDA graph this becomes two parallel branches.)
+        main = torch.cuda.current_stream(imu.device)
+        if self._side is None or self._side.device != imu.device:
+            self._side = torch.cuda.Stream(device=imu.device)
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            vfeat = self.xm.video_encoder.forward_features(fmap, self.frames, precision=self.precision)
+            vp = l2_normalize_native(self.xm.video_proj(vfeat))
+        out = self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
         ip = l2_normalize_native(self.xm.imu_proj(out["cls"]))
-        vp = l2_normalize_native(self.xm.video_proj(vfeat))
+        main.wait_stream(side)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in (vfeat, vp):
+                t.record_stream(main)
         res = similarity_native(ip, vp, sigmoid=self.sig, precision=self.precision)
         out.update(imu_proj=ip, video_proj=vp, loss=res["sigmoid_sum"] / float(ip.shape[0] * vp.shape[0]))
         return out

@@ -155,10 +155,13 @@ int    cmhar_linear_pack(const float* weight /*(out,in)*/, const float* bias /*(
                          const float* bn_weight, const float* bn_bias, const float* bn_mean,
                          const float* bn_var, int32_t in_dim, int32_t out_dim, void* blob,
                          cmhar_stream_t s);
-/* y (n,out) = relu?(x (n,in) @ W'^T + b');  in_dim % 4 == 0, out_dim % 4 == 0 */
+/* y (n,out) = relu?(x (n,in) @ W'^T + b');  in_dim % 4 == 0, out_dim % 4 == 0.
+ * `work` (optional, cmhar_linear_work_bytes) lets small batches split the k loop over more CTAs;
+ * partial sums are added in a fixed order, so results do not depend on scheduling. */
+size_t cmhar_linear_work_bytes(int64_t n, int32_t out_dim);
 int    cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in_dim,
-                            int32_t out_dim, int32_t relu, float* y, int32_t precision,
-                            cmhar_stream_t s);
+                            int32_t out_dim, int32_t relu, float* y, void* work, size_t work_bytes,
+                            int32_t precision, cmhar_stream_t s);
 /* rows x / max(||x||_2, 1e-12)   (F.normalize(dim=1), models.py:288-289); in place allowed */
 int    cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmhar_stream_t s);
 

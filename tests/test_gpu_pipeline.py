@@ -1,0 +1,68 @@
+"""GPU tests of the fused encode -> fuse -> score pass (pipeline.py): eager, host-buffer and
+CUDA-graph routes must agree with each other and with the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import crossmodal_imu_video_ood_har_b200 as cm
+from oracle import ood_spec, oracle, weights as W
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def tsd(sd):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+
+
+def build(seed=31):
+    cfg = cm.default_config()
+    sd_x = W.cross_modal_state(seed)
+    sd_c = W.classifier_state(seed)              # same encoder seed -> same imu_encoder.* tensors
+    clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg)
+    clf.load_state_dict(tsd(sd_c), strict=True)
+    xm = cm.CrossModalModel(cfg)
+    xm.load_state_dict(tsd(sd_x), strict=True)
+    return clf.to(DEV).eval(), xm.to(DEV).eval(), sd_c, sd_x
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_pipeline_routes_agree_with_oracle(precision, tol):
+    clf, xm, sd_c, sd_x = build()
+    B, T = 40, 16
+    imu = W.imu_windows(5, B)
+    fmap = W.video_feature_maps(6, B, T)
+    feats, labels = W.class_features(7, 2000)
+    maha = cm.MahalanobisOOD(32, DEV, ridge=1e-3).fit(torch.from_numpy(feats).to(DEV), torch.from_numpy(labels).to(DEV))
+    pipe = cm.CrossModalOODPipeline(clf, xm, maha, frames=T, precision=precision)
+    x, f = torch.from_numpy(imu).to(DEV), torch.from_numpy(fmap).to(DEV).to(torch.bfloat16)
+    eager = pipe.run(x, f)
+    torch.cuda.synchronize()
+    # oracle (float64 on the same bf16-rounded feature maps)
+    f_r = f.float().cpu().numpy()
+    want_logits, want_cls = oracle.imu_classifier(imu, sd_c, dtype=torch.float64)
+    ip, vp = oracle.cross_modal(imu, f_r, sd_x, T, dtype=torch.float64)
+    want_loss = float(oracle.sigmoid_contrastive_loss(ip, vp, dtype=torch.float64))
+    rel = lambda g, w: float(np.abs(g.detach().cpu().numpy().astype(np.float64) - w.numpy()).max() / np.abs(w.numpy()).max())
+    assert rel(eager["logits"], want_logits) < tol
+    assert rel(eager["imu_proj"], ip) < tol and rel(eager["video_proj"], vp) < tol
+    assert abs(float(eager["loss"]) - want_loss) < tol * want_loss
+    spec = ood_spec.mahalanobis_finalize(*ood_spec.mahalanobis_sufficient_stats(feats, labels, 32), ridge=1e-3)
+    want_maha = ood_spec.mahalanobis_score(want_cls.numpy(), spec)
+    assert float(np.abs(eager["maha"].cpu().numpy() - want_maha).max() / np.abs(want_maha).max()) < max(tol, 5e-3) * 3
+    if precision == "fp32":
+        assert np.array_equal(eager["pred"].cpu().numpy(), oracle.predict(want_logits))
+    # host-buffer route
+    host = pipe.run_host(torch.from_numpy(imu), f.cpu())
+    assert torch.equal(host["pred"], eager["pred"].cpu())
+    assert torch.allclose(host["energy"], eager["energy"].cpu()) and torch.allclose(host["maha"], eager["maha"].cpu())
+    assert abs(float(host["loss"]) - float(eager["loss"])) < 1e-12
+    # CUDA-graph route (two parallel branches)
+    graph, out = pipe.capture(x, f)
+    for v in out.values():
+        if v.dtype.is_floating_point:
+            v.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["pred"], eager["pred"]) and torch.equal(out["logits"], eager["logits"])
+    assert abs(float(out["loss"]) - float(eager["loss"])) < 1e-12

@@ -14,20 +14,21 @@ blob = enc.packed_blob(x.device, 16)
 N = cm._native
 CAP = 1024
 for rep in range(2):
-    tlog = torch.zeros(10 * CAP * 2, dtype=torch.int64, device="cuda")
+    tlog = torch.zeros(18 * CAP * 2, dtype=torch.int64, device="cuda")
     N.check(N.lib().cmhar_debug_imu_bf16(blob.data_ptr(), x.data_ptr(), n, x.stride(0), 100, tlog.data_ptr(), None, None, N.stream_ptr(x.device)))
     torch.cuda.synchronize()
-t = tlog.view(10, CAP, 2).cpu().numpy()
+t = tlog.view(18, CAP, 2).cpu().numpy()
 os.makedirs("gpurun_out", exist_ok=True); np.save("gpurun_out/timeline_bf16.npy", t)
 names = {3: "MMA wait HA(patch)", 4: "MMA wait HA(qkv)", 5: "MMA wait QKV smem", 6: "MMA wait P", 8: "MMA wait O", 9: "MMA wait HA(ffn)", 10: "MMA wait HID",
          11: "EPI wait R(patch)", 12: "EPI wait QKV acc", 13: "EPI wait S", 15: "EPI wait O acc", 16: "EPI wait R(outproj)", 17: "EPI wait FFN1 acc", 18: "EPI wait R(ffn2)", 2: "MMA wait Wfull", 1: "LOAD wait Wempty"}
-for warp, label in ((8, "MMA issuer"), (0, "epilogue warp 0"), (4, "epilogue warp 4")):
+NQ = 2 if os.environ.get("CMHAR_EPI_WARPS") == "8" else 4
+for warp, label in ((4 * NQ, "MMA issuer"), (0, "epilogue warp 0")):
     ev = t[warp]; ev = ev[ev[:, 1] > 0]
     if len(ev) == 0: continue
     t0 = ev[0, 1]
     print(f"== {label}: {len(ev)} events; first tile span")
     # print first tile only: until code 3/11 appears the second time
-    first = 3 if warp == 8 else 11
+    first = 3 if warp == 4 * NQ else 11
     seen = 0
     agg = {}
     prev_t = t0
