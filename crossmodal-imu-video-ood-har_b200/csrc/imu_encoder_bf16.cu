@@ -20,6 +20,8 @@
 //
 // Roles: warps 0-7 epilogue (thread = (row, column half)), warp 8 lane 0 = MMA issuer,
 // warp 9 lane 0 = weight producer.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace cmhar {
@@ -198,6 +200,18 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
                    "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
                    "r"(v[15])                                                                                     \
                  : "memory")
+
+__device__ __forceinline__ float ex2_approx(float x) {       // 2^x, one MUFU, flush-to-zero (x <= 0 here)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -598,23 +612,25 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                 // ---- softmax: this thread owns the heads whose 16 compact scores fall into its CW columns
                 PROG(13); mbar_wait(BAR(B_ACC + 0), ph.next(B_ACC + 0), 13); PROG(1013);
                 tc_fence_after();
+                auto softmax_rows = [&](auto full_tag) {      // full_tag: seq == 16, no key masking needed
 #pragma unroll
                 for (int cc = 0; cc < CW; cc += 32) {
                     TMEM_LD32(lane_base + TM_A + c0 + cc, v);
                     tc_wait_ld();
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
+                        // scores arrive pre-multiplied by log2(e)/sqrt(head_dim) (folded into W_q, b_q at pack time)
                         float m = -INFINITY;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float sv = (i < S) ? __uint_as_float(v[hh * 16 + i]) : -INFINITY;
+                            const float sv = (decltype(full_tag)::value || i < S) ? __uint_as_float(v[hh * 16 + i]) : -INFINITY;
                             f[hh * 16 + i] = sv;
                             m = fmaxf(m, sv);
                         }
                         float den = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { f[hh * 16 + i] = __expf(f[hh * 16 + i] - m); den += f[hh * 16 + i]; }
-                        const float inv = 1.f / den;
+                        for (int i = 0; i < 16; ++i) { f[hh * 16 + i] = ex2_approx(f[hh * 16 + i] - m); den += f[hh * 16 + i]; }
+                        const float inv = rcp_approx(den);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) f[hh * 16 + i] *= inv;
                     }
@@ -623,7 +639,13 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
                     TMEM_ST16(lane_base + TM_P + ((c0 + cc) >> 1), pk);
                 }
-                publish(B_P);
+                };
+                if (S == CMHAR_MAX_SEQ) softmax_rows(std::true_type{});
+                else softmax_rows(std::false_type{});
+                tc_wait_st();                 // P lives in TMEM: no shared-memory proxy fence needed
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B_P));
                 // ---- O (buffer C) -> smem (Q region) as bf16
                 PROG(15); mbar_wait(BAR(B_ACC + 2), ph.next(B_ACC + 2), 15); PROG(1015);
                 tc_fence_after();
@@ -814,7 +836,7 @@ __global__ void pack_param_blocks_kernel(const float* __restrict__ fp32, const f
     } else {
         const int l = (i - SB_FLOATS) / PB_FLOATS, o = (i - SB_FLOATS) % PB_FLOATS;
         const float* L = fp32 + EncLayout::layers0 + (size_t)l * EncLayout::layer_floats;
-        if (o < PB_B1) v = L[EncLayout::l_b_in + o];
+        if (o < PB_B1) v = L[EncLayout::l_b_in + o] * LOG2E;       // fp32 section holds b_q/4; the bf16 path wants log2(e) b_q/4
         else if (o < PB_B2) v = L[EncLayout::l_b1 + (o - PB_B1)];
         else if (o < PB_LN1) v = L[EncLayout::l_b2 + (o - PB_B2)];
         else if (o < PB_LN2) v = L[EncLayout::l_ln1 + (o - PB_LN1)];
@@ -845,7 +867,7 @@ int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_secti
     for (int l = 0; l < p->layers; ++l) {
         const cmhar_encoder_layer_params& q = p->layer[l];
         for (int m = 0; m < 3; ++m)                                   // Wq (x 1/4), Wk, Wv : k halves
-            for (int k = 0; k < 2; ++k) PUT(q.in_proj_weight, D, m * D, k * 64, 64, m == 0 ? 0.25f : 1.f);
+            for (int k = 0; k < 2; ++k) PUT(q.in_proj_weight, D, m * D, k * 64, 64, m == 0 ? 0.25f * LOG2E : 1.f);   // softmax uses 2^x
         for (int k = 0; k < 2; ++k) PUT(q.out_proj_weight, D, 0, k * 64, 64, 1.f);
         for (int cc = 0; cc < 3; ++cc)                                // W1 chunks 0..2
             for (int k = 0; k < 2; ++k) PUT(q.linear1_weight, D, cc * 128, k * 64, 64, 1.f);
@@ -874,8 +896,8 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
     CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
     static int nq = 0;
     if (nq == 0) {
-        const char* e = getenv("CMHAR_EPI_WARPS");      // 8 or 16 epilogue warps (development switch)
-        nq = (e && atoi(e) == 8) ? 2 : 4;
+        const char* e = getenv("CMHAR_EPI_WARPS");      // 8 (default) or 16 epilogue warps (development switch;
+        nq = (e && atoi(e) == 16) ? 4 : 2;              // measured equal within noise: the tile is latency-bound)
     }
     if (!configured[dev & 63]) {
         CMHAR_CHECK_CUDA(cudaFuncSetAttribute(imu_forward_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -21,7 +21,7 @@ t = tlog.view(18, CAP, 2).cpu().numpy()
 os.makedirs("gpurun_out", exist_ok=True); np.save("gpurun_out/timeline_bf16.npy", t)
 names = {3: "MMA wait HA(patch)", 4: "MMA wait HA(qkv)", 5: "MMA wait QKV smem", 6: "MMA wait P", 8: "MMA wait O", 9: "MMA wait HA(ffn)", 10: "MMA wait HID",
          11: "EPI wait R(patch)", 12: "EPI wait QKV acc", 13: "EPI wait S", 15: "EPI wait O acc", 16: "EPI wait R(outproj)", 17: "EPI wait FFN1 acc", 18: "EPI wait R(ffn2)", 2: "MMA wait Wfull", 1: "LOAD wait Wempty"}
-NQ = 2 if os.environ.get("CMHAR_EPI_WARPS") == "8" else 4
+NQ = 4 if os.environ.get("CMHAR_EPI_WARPS") == "16" else 2
 for warp, label in ((4 * NQ, "MMA issuer"), (0, "epilogue warp 0")):
     ev = t[warp]; ev = ev[ev[:, 1] > 0]
     if len(ev) == 0: continue
