@@ -201,12 +201,32 @@ def run_reference(args):
             "cpu_baseline": {"value": wps, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{iters} batches of {args.batch} windows (oracle/oracle.py on torch CPU ops, {torch.get_num_threads()} threads)"},
             "e2e": {"value": wps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner on fd 1)
+    must not add lines, so fd 1 is pointed at stderr for the whole run and the JSON line is written
+    to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    _quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -380,7 +400,7 @@ def main():
                 "launches_per_step": launches_per_step,
                 "roofline": roofline, "roofline_video_tail": roofline_video,
                 "cpu_baseline": cpu_baseline, "imu_batch_sweep": sweep}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
