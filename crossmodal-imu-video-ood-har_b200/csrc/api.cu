@@ -22,6 +22,8 @@ int cmhar_imu_forward(const void* encoder_blob, const void* head_blob, const voi
     CMHAR_REQUIRE(head_blob || !(logits_out || pred_out || msp_out || energy_out),
                   "logits/pred/msp/energy outputs need a head blob");
     CMHAR_REQUIRE(maha_blob || !maha_out, "maha_out needs a maha blob");
+    CMHAR_REQUIRE(cls_out || !(head_blob || maha_out),
+                  "cls_out is required with a head / maha blob: the head runs as a second launch on the stored CLS features");
     CMHAR_REQUIRE(x_window_stride >= 16, "x_window_stride=%lld too small", (long long)x_window_stride);
     CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
     if (n_windows <= 0) return CMHAR_OK;

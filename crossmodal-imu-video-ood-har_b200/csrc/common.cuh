@@ -84,16 +84,19 @@ struct BlobHeader {          // 64 bytes in front of every blob
 };
 static_assert(sizeof(BlobHeader) == 64, "header must stay 64 bytes");
 
-// head blob (floats after header): w0_t (128,h1) b0 h1 | w1_t (h1,h2) b1 h2 | w2_t (h2,C) b2 C
+// head blob (floats after header): w0_t (128,h1) b0 h1 | w1_t (h1,h2) b1 h2 | w2_t (h2,Cp) b2 Cp
+// h1, h2 multiples of 4; the class dimension is padded to Cp = 4*ceil(C/4) (zero columns) so every
+// matrix row starts 16-byte aligned (the head kernel streams them with cp.async.bulk).
 struct HeadLayout {
     int h1, h2, C;
+    __host__ __device__ int Cp() const { return (C + 3) & ~3; }
     __host__ __device__ size_t w0() const { return 0; }
     __host__ __device__ size_t b0() const { return w0() + (size_t)D * h1; }
     __host__ __device__ size_t w1() const { return b0() + h1; }
     __host__ __device__ size_t b1() const { return w1() + (size_t)h1 * h2; }
     __host__ __device__ size_t w2() const { return b1() + h2; }
-    __host__ __device__ size_t b2() const { return w2() + (size_t)h2 * C; }
-    __host__ __device__ size_t total() const { return b2() + C; }
+    __host__ __device__ size_t b2() const { return w2() + (size_t)h2 * Cp(); }
+    __host__ __device__ size_t total() const { return b2() + Cp(); }
 };
 
 // maha blob (floats after header): whiten (128,128) row-major [k][j], mean_w (C,128), mnorm (C)

@@ -23,6 +23,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cmhar {
 namespace tc {
@@ -72,171 +73,6 @@ static_assert(B_COUNT * 8 + 8 <= 256, "barrier area too small");
 constexpr uint32_t TM_A = 0, TM_B = 128, TM_C = 256, TM_R = 384;
 constexpr uint32_t TM_P = TM_B + 64;      // softmax probabilities, bf16 pairs: head h -> columns [8h, 8h+8)
 
-// ---------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0) {
-    uint32_t ok, spins = 0;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok && ++spins > (1u << 22)) {       // watchdog: a protocol bug must fail loudly, never hang the GPU
-            if (spins == (1u << 22) + 1 && (threadIdx.x & 31) == 0 && blockIdx.x == 0)
-                printf("cmhar bf16 kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u site %d)\n",
-                       (int)blockIdx.x, (int)threadIdx.x, (bar & 0xffu) >> 3, parity, site);
-            if (spins > (1u << 26)) __trap();
-        }
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// one lane of a converged warp (the same one every time): tcgen05.mma / commit are issued under this
-// predicate while the whole warp stays converged, so descriptors live in uniform registers
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-template <int NTH>
-__device__ __forceinline__ void epi_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major SWIZZLE_128B
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-
-// same, but only the 16 TMEM lanes [16*win, 16*win+16) are written (disable-output-lane mask)
-__device__ __forceinline__ void umma_rows16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int win) {
-    const uint32_t hole = ~(0xFFFFu << ((win & 1) * 16));      // no array indexing: keeps the mask in registers
-    const uint32_t m[4] = {(win >> 1) == 0 ? hole : 0xFFFFFFFFu, (win >> 1) == 1 ? hole : 0xFFFFFFFFu,
-                           (win >> 1) == 2 ? hole : 0xFFFFFFFFu, (win >> 1) == 3 ? hole : 0xFFFFFFFFu};
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %5, %6, %7}, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]) : "memory");
-}
-
-// A operand from TMEM (lane = row, one 32-bit column = two consecutive k elements), B from smem
-__device__ __forceinline__ void umma_ts_rows16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, int win) {
-    const uint32_t hole = ~(0xFFFFu << ((win & 1) * 16));      // no array indexing: keeps the mask in registers
-    const uint32_t m[4] = {(win >> 1) == 0 ? hole : 0xFFFFFFFFu, (win >> 1) == 1 ? hole : 0xFFFFFFFFu,
-                           (win >> 1) == 2 ? hole : 0xFFFFFFFFu, (win >> 1) == 3 ? hole : 0xFFFFFFFFu};
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%4, %5, %6, %7}, p;\n\t"
-        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]) : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-// start>>4 [0,14) | LBO=1 [16,30) | SBO=1024>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-// instruction descriptor, kind::f16: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-#define TMEM_LD32(addr, v)                                                                                        \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                        \
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25," \
-                 "%26,%27,%28,%29,%30,%31}, [%32];"                                                               \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),       \
-                   "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),     \
-                   "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),     \
-                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                          \
-                 : "r"(addr)                                                                                      \
-                 : "memory")
-
-#define TMEM_ST32(addr, v)                                                                                        \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                  \
-                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26," \
-                 "%27,%28,%29,%30,%31,%32};"                                                                      \
-                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
-                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
-                   "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), \
-                   "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), \
-                   "r"(v[31])                                                                                     \
-                 : "memory")
-
-#define TMEM_ST16(addr, v)                                                                                        \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                  \
-                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                      \
-                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
-                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
-                   "r"(v[15])                                                                                     \
-                 : "memory")
-
-__device__ __forceinline__ float ex2_approx(float x) {       // 2^x, one MUFU, flush-to-zero (x <= 0 here)
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-constexpr float LOG2E = 1.4426950408889634f;
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&t);
-}
-
-// byte offset of the 16-byte piece holding columns [8j, 8j+8) of row r inside a [128 x 64] SW128 chunk
-__device__ __forceinline__ uint32_t sw128_off(int r, int j) {
-    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-}
-
-// store 32 consecutive columns (fp32 in v, already finished) of row r as bf16 into chunk `chunk_base`
-// at 16-byte pieces j0..j0+3
-__device__ __forceinline__ void store_bf16_32(uint8_t* chunk_base, int r, int j0, const float* v) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-        u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-        u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-        u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-        *reinterpret_cast<uint4*>(chunk_base + sw128_off(r, j0 + q)) = u;
-    }
-}
-
 struct Phase {       // parity bookkeeping: one bit per barrier index
     uint32_t bits = 0;
     __device__ __forceinline__ uint32_t next(int i) { const uint32_t p = (bits >> i) & 1u; bits ^= (1u << i); return p; }
@@ -252,7 +88,9 @@ struct Bf16Args {
     float* dbg_out;
     volatile int* progress; // debug: host-mapped [grid][16] progress codes (survive a trap), or null
     long long* tlog;        // debug: device [18 warps][TLOG_CAP][2] (code, clock64) of block 0, or null
+    int ablate;             // development: CMHAR_ABLATE bit mask (timing experiments; results are WRONG when set)
 };
+enum { ABL_NO_TMA = 1, ABL_NO_STS = 2, ABL_NO_SOFTMAX = 4, ABL_NO_LN = 8, ABL_NO_ATTN_MMA = 16, ABL_NO_DENSE_MMA = 32 };
 constexpr int TLOG_CAP = 1024;
 
 // ======================================================================================== kernel
@@ -326,8 +164,11 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                                  BAR(B_PBFULL + b));
                     }
                     mbar_wait(BAR(B_WEMPTY + stage), parity, 1);
+                    if ((args.ablate & ABL_NO_TMA) && tile != blockIdx.x) { mbar_arrive(BAR(B_WFULL + stage)); }
+                    else {
                     mbar_expect_tx(BAR(B_WFULL + stage), CHUNK);
                     bulk_g2s(sbase + OFF_W + stage * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(B_WFULL + stage));
+                    }
                     if (++stage == NSTAGE) { stage = 0; parity ^= 1; }
                 }
             }
@@ -348,7 +189,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                 const uint64_t dW = sw128_desc(sbase + OFF_W + wstage * CHUNK);
                 for (int k = 0; k < ksteps; ++k) {
                     const uint64_t wa = dW + (uint64_t)(2 * k), oa = other_desc + (uint64_t)(2 * k);
-                    if (leader) umma(d, w_is_a ? wa : oa, w_is_a ? oa : wa, ID128, (first_acc || k > 0) ? 1u : 0u);
+                    if (leader && !(args.ablate & ABL_NO_DENSE_MMA)) umma(d, w_is_a ? wa : oa, w_is_a ? oa : wa, ID128, (first_acc || k > 0) ? 1u : 0u);
                 }
                 if (leader) tc_commit(BAR(B_WEMPTY + wstage));
                 if (++wstage == NSTAGE) { wstage = 0; wparity ^= 1; }
@@ -384,7 +225,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
 #pragma unroll
                         for (int h = 0; h < H; ++h) {
                             const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)((h & 3) * 2);
-                            if (leader) umma_rows16(tmem + TM_A + 16 * h, dQ + off, dK + off + (uint64_t)(j * 128), ID16, j);
+                            if (leader && !(args.ablate & ABL_NO_ATTN_MMA)) umma_rows16(tmem + TM_A + 16 * h, dQ + off, dK + off + (uint64_t)(j * 128), ID16, j);
                         }
                     }
                     if (leader) tc_commit(BAR(B_ACC + 0));
@@ -396,7 +237,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                         const uint64_t koff = (uint64_t)(j >> 2) * CH + (uint64_t)((j & 3) * 2);
 #pragma unroll
                         for (int h = 0; h < H; ++h)
-                            if (leader) umma_ts_rows16(tmem + TM_C + 16 * h, tmem + TM_P + 8 * h, dVT + koff + (uint64_t)(h * 128), ID16, j);
+                            if (leader && !(args.ablate & ABL_NO_ATTN_MMA)) umma_ts_rows16(tmem + TM_C + 16 * h, tmem + TM_P + 8 * h, dVT + koff + (uint64_t)(h * 128), ID16, j);
                     }
                     if (leader) tc_commit(BAR(B_ACC + 2));            // O complete
                     // ---- out-proj: R(h + b_o) += O * W_o^T
@@ -451,7 +292,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
         auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };   // warp-uniform smem broadcast
         // finish a 128-wide fp32 row held in R: y -> hA (bf16), y + next_bias -> R
         auto write_h = [&](const float* y32, int cc, const float* next_bias) {
-            store_bf16_32(smem + OFF_HA + chunk_of(c0 + cc), row, piece_of(c0 + cc), y32);
+            if (!(args.ablate & ABL_NO_STS)) store_bf16_32(smem + OFF_HA + chunk_of(c0 + cc), row, piece_of(c0 + cc), y32);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 const float4 nb = ld4(next_bias + c0 + cc + i);
@@ -463,6 +304,21 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
         // LayerNorm of the residual row in R (two threads per row exchange partial sums through smem)
         auto layer_norm_R = [&](const float* gb, const float* next_bias, bool write_back, float* keep /*CW floats or null*/) {
             float s1 = 0.f, s2 = 0.f;
+            if (args.ablate & ABL_NO_LN) {
+#pragma unroll
+                for (int cc = 0; cc < CW; cc += 32) {
+                    TMEM_LD32(lane_base + TM_R + c0 + cc, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    if (keep) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) keep[cc + i] = f[i];
+                    }
+                    if (write_back) write_h(f, cc, next_bias);
+                }
+                return;
+            }
 #pragma unroll
             for (int cc = 0; cc < CW; cc += 32) {
                 TMEM_LD32(lane_base + TM_R + c0 + cc, v);
@@ -604,7 +460,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
 #pragma unroll
                             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                         }
-                        store_bf16_32(dst + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
+                        if (!(args.ablate & ABL_NO_STS)) store_bf16_32(dst + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
                     }
                 }
                 PROG(100 + l);
@@ -619,6 +475,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     tc_wait_ld();
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
+                        if (args.ablate & ABL_NO_SOFTMAX) { for (int i = 0; i < 16; ++i) f[hh * 16 + i] = __uint_as_float(v[hh * 16 + i]); continue; }
                         // scores arrive pre-multiplied by log2(e)/sqrt(head_dim) (folded into W_q, b_q at pack time)
                         float m = -INFINITY;
 #pragma unroll
@@ -655,7 +512,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     tc_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    store_bf16_32(smem + OFF_Q + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
+                    if (!(args.ablate & ABL_NO_STS)) store_bf16_32(smem + OFF_Q + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
                 }
                 publish(B_O);
                 // ---- LN1: h1 = LN(R) ; hA = bf16(h1) ; R = h1 + b_2
@@ -682,7 +539,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                             f[i] = fmaxf(__uint_as_float(v[i]) + b.x, 0.f); f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
                             f[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f); f[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
                         }
-                        store_bf16_32(smem + OFF_Q + (c == 3 ? 0 : c) * 32768 + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
+                        if (!(args.ablate & ABL_NO_STS)) store_bf16_32(smem + OFF_Q + (c == 3 ? 0 : c) * 32768 + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
                     }
                     PROG(180 + c);
                     publish(B_HID + c);
@@ -722,39 +579,14 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
 #pragma unroll
                         for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
                     }
-                    // CLS rows -> head scratch in the (now dead) Q region: feat [8][128] fp32
-                    float* feat = reinterpret_cast<float*>(smem + OFF_Q);
                     if (tok == 0) {
-#pragma unroll
-                        for (int i = 0; i < CW / 4; ++i)
-                            reinterpret_cast<float4*>(feat + win * D + c0)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
                         if (a.cls_out && valid) {
                             float4* dst = reinterpret_cast<float4*>(a.cls_out + (w0 + win) * D + c0);
 #pragma unroll
                             for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
                         }
                     }
-                    epi_bar();
                 }
-            }
-            // ---- classifier head + scores (fp32 CUDA cores, shared with the fp32 path) on the 8 CLS rows
-            {
-                const float* head = nullptr;
-                const float* maha = nullptr;
-                HeadLayout hl{0, 0, 0};
-                MahaLayout ml{0};
-                if (a.head_blob) {
-                    const BlobHeader* hh = reinterpret_cast<const BlobHeader*>(a.head_blob);
-                    hl = HeadLayout{hh->a, hh->b, hh->c};
-                    head = reinterpret_cast<const float*>(a.head_blob + sizeof(BlobHeader));
-                }
-                if (a.maha_blob) {
-                    const BlobHeader* mh = reinterpret_cast<const BlobHeader*>(a.maha_blob);
-                    ml = MahaLayout{mh->a};
-                    maha = reinterpret_cast<const float*>(a.maha_blob + sizeof(BlobHeader));
-                }
-                if (head || maha) head_and_scores_t<NT_EPI, true>(reinterpret_cast<float*>(smem + OFF_Q), 8, w0, a, head, hl, maha, ml);
-                epi_bar();      // scratch (Q region) is rewritten by the next tile's QKV drain
             }
         }
     }
@@ -909,18 +741,26 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
     if (nq == 2) imu_forward_bf16_kernel<2><<<grid, 320, SMEM_BYTES, stream>>>(args);
     else imu_forward_bf16_kernel<4><<<grid, 576, SMEM_BYTES, stream>>>(args);
     CMHAR_LAUNCH_CHECK();
-    return CMHAR_OK;
+    return launch_head_after_encoder(args.f, stream);
 }
 
+static int ablate_mask() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("CMHAR_ABLATE"); m = e ? atoi(e) : 0; }
+    return m;
+}
+
+int launch_head_after_encoder(const FwdArgs& a, cudaStream_t stream);     // imu_encoder_fp32.cu
+
 int launch_imu_forward_bf16(const FwdArgs& a, cudaStream_t stream) {
-    Bf16Args args{a, -1, nullptr, nullptr, nullptr};
+    Bf16Args args{a, -1, nullptr, nullptr, nullptr, ablate_mask()};
     return launch_bf16(args, stream);
 }
 
 int launch_imu_forward_bf16_debug(const FwdArgs& a, int stage, float* dump, int* progress, cudaStream_t stream) {
     // stage >= 100: `dump` is reinterpreted as the (10, TLOG_CAP, 2) int64 timeline buffer of block 0
     Bf16Args args{a, stage >= 100 ? -1 : stage, stage >= 100 ? nullptr : dump, progress,
-                  stage >= 100 ? reinterpret_cast<long long*>(dump) : nullptr};
+                  stage >= 100 ? reinterpret_cast<long long*>(dump) : nullptr, 0};
     return launch_bf16(args, stream);
 }
 

@@ -85,121 +85,6 @@ __device__ __forceinline__ void layer_norm_rows(float* h, const float* __restric
     }
 }
 
-// Classifier head (models.py:312-326,338, BN folded) + arg-max / MSP / energy (+ Mahalanobis) for
-// up to 8 feature rows held in buf[0..8*128) (rows >= wpb are zero).  Scratch lives in buf.
-template <int NTH, bool NAMED>
-__device__ __forceinline__ void block_sync() {
-    if (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory");   // the epilogue threads of the bf16 kernel
-    else __syncthreads();
-}
-
-template <int NTH, bool NAMED>
-__device__ __forceinline__ void head_and_scores_t(float* buf, int wpb, long long w0, const FwdArgs& a,
-                                                  const float* head, const HeadLayout hl,
-                                                  const float* maha, const MahaLayout ml) {
-    constexpr int NT = NTH;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float* feat = buf;                  // [8][128], filled by the caller (zero rows beyond wpb)
-    float* hid1 = buf + 8 * D;          // [8][256]
-    float* hid2 = hid1 + 8 * 256;       // [8][256]
-    float* logit = hid2 + 8 * 256;      // [8][64]
-    float* white = logit + 8 * 64;      // [8][128]
-    if (head) {
-        for (int j = tid; j < hl.h1; j += NT) {          // Linear(128->h1)+BN folded, ReLU
-            float acc[8];
-#pragma unroll
-            for (int w = 0; w < 8; ++w) acc[w] = 0.f;
-            const float* wt = head + hl.w0() + j;
-            for (int k = 0; k < D; ++k) {
-                const float wv = __ldg(wt + (size_t)k * hl.h1);
-#pragma unroll
-                for (int w = 0; w < 8; ++w) acc[w] = fmaf(feat[w * D + k], wv, acc[w]);
-            }
-            const float bv = __ldg(head + hl.b0() + j);
-#pragma unroll
-            for (int w = 0; w < 8; ++w) hid1[w * 256 + j] = fmaxf(acc[w] + bv, 0.f);
-        }
-        block_sync<NTH, NAMED>();
-        for (int j = tid; j < hl.h2; j += NT) {          // Linear(h1->h2)+BN folded, ReLU
-            float acc[8];
-#pragma unroll
-            for (int w = 0; w < 8; ++w) acc[w] = 0.f;
-            const float* wt = head + hl.w1() + j;
-            for (int k = 0; k < hl.h1; ++k) {
-                const float wv = __ldg(wt + (size_t)k * hl.h2);
-#pragma unroll
-                for (int w = 0; w < 8; ++w) acc[w] = fmaf(hid1[w * 256 + k], wv, acc[w]);
-            }
-            const float bv = __ldg(head + hl.b1() + j);
-#pragma unroll
-            for (int w = 0; w < 8; ++w) hid2[w * 256 + j] = fmaxf(acc[w] + bv, 0.f);
-        }
-        block_sync<NTH, NAMED>();
-        for (int j = tid; j < hl.C; j += NT) {           // Linear(h2->classes)
-            float acc[8];
-#pragma unroll
-            for (int w = 0; w < 8; ++w) acc[w] = 0.f;
-            const float* wt = head + hl.w2() + j;
-            for (int k = 0; k < hl.h2; ++k) {
-                const float wv = __ldg(wt + (size_t)k * hl.C);
-#pragma unroll
-                for (int w = 0; w < 8; ++w) acc[w] = fmaf(hid2[w * 256 + k], wv, acc[w]);
-            }
-            const float bv = __ldg(head + hl.b2() + j);
-#pragma unroll
-            for (int w = 0; w < 8; ++w) logit[w * 64 + j] = acc[w] + bv;
-        }
-        block_sync<NTH, NAMED>();
-        if (warp < wpb && w0 + warp < a.n) {             // warp w scores window w
-            const long long gw = w0 + warp;
-            const int C = hl.C;
-            const float z0 = (lane < C) ? logit[warp * 64 + lane] : -INFINITY;
-            const float z1 = (lane + 32 < C) ? logit[warp * 64 + lane + 32] : -INFINITY;
-            if (a.logits_out) {
-                if (lane < C) a.logits_out[gw * C + lane] = z0;
-                if (lane + 32 < C) a.logits_out[gw * C + lane + 32] = z1;
-            }
-            const float m = warp_max(fmaxf(z0, z1));
-            int idx = (z0 == m) ? lane : ((z1 == m) ? lane + 32 : 0x7fffffff);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, o));
-            const float se = warp_sum(((lane < C) ? expf(z0 - m) : 0.f) + ((lane + 32 < C) ? expf(z1 - m) : 0.f));
-            if (lane == 0) {
-                if (a.pred_out) a.pred_out[gw] = idx;
-                if (a.msp_out) a.msp_out[gw] = -1.f / se;
-                if (a.energy_out) a.energy_out[gw] = -(m + logf(se));
-            }
-        }
-    }
-    if (maha && a.maha_out) {
-        for (int j = tid; j < D; j += NT) {              // y = feat @ whiten
-            float acc[8];
-#pragma unroll
-            for (int w = 0; w < 8; ++w) acc[w] = 0.f;
-            const float* wt = maha + ml.whiten() + j;
-            for (int k = 0; k < D; ++k) {
-                const float wv = __ldg(wt + (size_t)k * D);
-#pragma unroll
-                for (int w = 0; w < 8; ++w) acc[w] = fmaf(feat[w * D + k], wv, acc[w]);
-            }
-#pragma unroll
-            for (int w = 0; w < 8; ++w) white[w * D + j] = acc[w];
-        }
-        block_sync<NTH, NAMED>();
-        if (warp < wpb && w0 + warp < a.n) {
-            const float4 y = *reinterpret_cast<const float4*>(white + warp * D + lane * 4);
-            float best = INFINITY;
-            for (int c = 0; c < ml.C; ++c) {
-                const float4 mu = __ldg(reinterpret_cast<const float4*>(maha + ml.mean_w() + (size_t)c * D + lane * 4));
-                const float dx = y.x - mu.x, dy = y.y - mu.y, dz = y.z - mu.z, dw = y.w - mu.w;
-                const float dist = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw);
-                if (__ldg(maha + ml.valid() + c) > 0.f) best = fminf(best, dist);
-            }
-            if (lane == 0) a.maha_out[w0 + warp] = best;
-        }
-    }
-}
-
 __global__ void __launch_bounds__(NT, 1) imu_forward_fp32_kernel(const FwdArgs a) {
     extern __shared__ __align__(16) float smem_f32[];
     float* const smem = smem_f32;
@@ -216,20 +101,6 @@ __global__ void __launch_bounds__(NT, 1) imu_forward_fp32_kernel(const FwdArgs a
     const int nrows = wpb * S;
     const long long tiles = (a.n + wpb - 1) / wpb;
     const float* enc = reinterpret_cast<const float*>(a.enc_blob + 1024);
-    const float* head = nullptr;
-    const float* maha = nullptr;
-    HeadLayout hl{0, 0, 0};
-    MahaLayout ml{0};
-    if (a.head_blob) {
-        const BlobHeader* hh = reinterpret_cast<const BlobHeader*>(a.head_blob);
-        hl = HeadLayout{hh->a, hh->b, hh->c};
-        head = reinterpret_cast<const float*>(a.head_blob + sizeof(BlobHeader));
-    }
-    if (a.maha_blob) {
-        const BlobHeader* mh = reinterpret_cast<const BlobHeader*>(a.maha_blob);
-        ml = MahaLayout{mh->a};
-        maha = reinterpret_cast<const float*>(a.maha_blob + sizeof(BlobHeader));
-    }
 
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long w0 = tile * wpb;
@@ -399,45 +270,21 @@ __global__ void __launch_bounds__(NT, 1) imu_forward_fp32_kernel(const FwdArgs a
                         reinterpret_cast<const float4*>(h + (w * S) * D)[c4];
             }
         }
-        // ---- classifier head + scores on the wpb (<= 8) CLS rows; scratch in buf
-        for (int e = tid; e < 8 * D; e += NT) {
-            const int w = e / D;
-            buf[e] = (w < wpb) ? h[(w * S) * D + (e % D)] : 0.f;
-        }
-        __syncthreads();
-        head_and_scores_t<NT, false>(buf, wpb, w0, a, head, hl, maha, ml);
+        __syncthreads();       // h is rewritten by the next tile
     }
 }
 
-// head + scores from stored features: 8 rows per CTA iteration
-__global__ void __launch_bounds__(NT) head_forward_kernel(const FwdArgs a) {
-    __shared__ __align__(16) float buf[8 * D + 2 * 8 * 256 + 8 * 64 + 8 * D];
-    const int tid = threadIdx.x;
-    const float* head = nullptr;
-    const float* maha = nullptr;
-    HeadLayout hl{0, 0, 0};
-    MahaLayout ml{0};
-    if (a.head_blob) {
-        const BlobHeader* hh = reinterpret_cast<const BlobHeader*>(a.head_blob);
-        hl = HeadLayout{hh->a, hh->b, hh->c};
-        head = reinterpret_cast<const float*>(a.head_blob + sizeof(BlobHeader));
-    }
-    if (a.maha_blob) {
-        const BlobHeader* mh = reinterpret_cast<const BlobHeader*>(a.maha_blob);
-        ml = MahaLayout{mh->a};
-        maha = reinterpret_cast<const float*>(a.maha_blob + sizeof(BlobHeader));
-    }
-    const long long tiles = (a.n + 7) / 8;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long long w0 = tile * 8;
-        __syncthreads();
-        for (int e = tid; e < 8 * D; e += NT) {
-            const long long r = w0 + e / D;
-            buf[e] = (r < a.n) ? __ldg(a.x + r * D + (e % D)) : 0.f;
-        }
-        __syncthreads();
-        head_and_scores_t<NT, false>(buf, 8, w0, a, head, hl, maha, ml);
-    }
+int launch_head_forward(const FwdArgs& a, cudaStream_t stream);     // head.cu
+
+// The classifier head and the OOD scores run as a second launch on the CLS features the encoder just
+// wrote (head.cu): on the 8 CLS rows of one tile the head is latency-bound on its 344 KB of weights and
+// used to cost 30 % of the fused kernel; batched over 32-row tiles it is 6 %.
+int launch_head_after_encoder(const FwdArgs& a, cudaStream_t stream) {
+    if (!a.head_blob && !(a.maha_blob && a.maha_out)) return CMHAR_OK;
+    FwdArgs h = a;
+    h.x = a.cls_out; h.xstride = D;
+    h.cls_out = nullptr; h.tokens_out = nullptr;
+    return launch_head_forward(h, stream);
 }
 
 int launch_imu_forward_fp32(const FwdArgs& a, cudaStream_t stream) {
@@ -454,17 +301,7 @@ int launch_imu_forward_fp32(const FwdArgs& a, cudaStream_t stream) {
     const int grid = (int)((tiles < (long long)sm_count()) ? tiles : (long long)sm_count());
     imu_forward_fp32_kernel<<<grid, NT, smem, stream>>>(a);
     CMHAR_LAUNCH_CHECK();
-    return CMHAR_OK;
+    return launch_head_after_encoder(a, stream);
 }
 
-}  // namespace cmhar
-
-namespace cmhar {
-int launch_head_forward(const FwdArgs& a, cudaStream_t stream) {
-    const long long tiles = (a.n + 7) / 8;
-    const int grid = (int)((tiles < 8LL * sm_count()) ? tiles : 8LL * sm_count());
-    head_forward_kernel<<<grid, NT, 0, stream>>>(a);
-    CMHAR_LAUNCH_CHECK();
-    return CMHAR_OK;
-}
 }  // namespace cmhar

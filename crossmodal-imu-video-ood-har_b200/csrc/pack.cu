@@ -152,7 +152,7 @@ int cmhar_imu_encoder_pack(const cmhar_imu_encoder_params* p, void* blob, cmhar_
 }
 
 size_t cmhar_head_blob_bytes(int32_t h1, int32_t h2, int32_t C) {
-    if (h1 < 4 || h1 > 256 || h2 < 4 || h2 > 256 || C < 2 || C > CMHAR_MAX_CLASSES) return 0;
+    if (h1 < 4 || h1 > 256 || (h1 & 3) || h2 < 4 || h2 > 256 || (h2 & 3) || C < 2 || C > CMHAR_MAX_CLASSES) return 0;
     HeadLayout hl{h1, h2, C};
     return sizeof(BlobHeader) + hl.total() * sizeof(float);
 }
@@ -160,7 +160,7 @@ size_t cmhar_head_blob_bytes(int32_t h1, int32_t h2, int32_t C) {
 int cmhar_head_pack(const cmhar_head_params* p, void* blob, cmhar_stream_t s) {
     CMHAR_REQUIRE(p && blob, "cmhar_head_pack: null argument");
     CMHAR_REQUIRE(cmhar_head_blob_bytes(p->hidden1, p->hidden2, p->classes) != 0,
-                  "unsupported head dims (%d,%d,%d): hidden <= 256, classes <= %d", p->hidden1, p->hidden2, p->classes, CMHAR_MAX_CLASSES);
+                  "unsupported head dims (%d,%d,%d): hidden <= 256 and a multiple of 4, classes <= %d", p->hidden1, p->hidden2, p->classes, CMHAR_MAX_CLASSES);
     cudaStream_t st = (cudaStream_t)s;
     HeadLayout hl{p->hidden1, p->hidden2, p->classes};
     float* f = reinterpret_cast<float*>(reinterpret_cast<char*>(blob) + sizeof(BlobHeader));
@@ -168,7 +168,8 @@ int cmhar_head_pack(const cmhar_head_params* p, void* blob, cmhar_stream_t s) {
     TRY(bias_fold(p->b0, hl.h1, f + hl.b0(), 0, 1.f, p->bn0_weight, p->bn0_bias, p->bn0_mean, p->bn0_var, st));
     TRY(transpose_fold(p->w1, hl.h2, hl.h1, f + hl.w1(), hl.h2, 0, 1.f, p->bn1_weight, p->bn1_var, st));
     TRY(bias_fold(p->b1, hl.h2, f + hl.b1(), 0, 1.f, p->bn1_weight, p->bn1_bias, p->bn1_mean, p->bn1_var, st));
-    TRY(transpose_fold(p->w2, hl.C, hl.h2, f + hl.w2(), hl.C, 0, 1.f, nullptr, nullptr, st));
+    CMHAR_CHECK_CUDA(cudaMemsetAsync(f + hl.w2(), 0, ((size_t)hl.h2 * hl.Cp() + hl.Cp()) * sizeof(float), st));   // zero pad columns
+    TRY(transpose_fold(p->w2, hl.C, hl.h2, f + hl.w2(), hl.Cp(), 0, 1.f, nullptr, nullptr, st));
     TRY(bias_fold(p->b2, hl.C, f + hl.b2(), 0, 1.f, nullptr, nullptr, nullptr, nullptr, st));
     BlobHeader h{};
     h.magic = HEAD_MAGIC; h.a = hl.h1; h.b = hl.h2; h.c = hl.C;

@@ -281,7 +281,8 @@ def imu_forward_native(encoder: "IMUEncoder", head_blob: Optional[torch.Tensor],
             t = torch.empty(shape, dtype=dtype, device=dev)
             out[name] = t
         return t
-    cls = buf("cls", want_cls, (B, encoder.d_model))
+    # the head / score launch reads the CLS features the encoder launch wrote: always materialised then
+    cls = buf("cls", want_cls or head_blob is not None or maha_blob is not None, (B, encoder.d_model))
     tokens = buf("tokens", want_tokens, (B, S, encoder.d_model))
     logits = buf("logits", want_logits, (B, classes))
     pred = buf("pred", want_pred, (B,), torch.int64)

@@ -106,7 +106,8 @@ int    cmhar_maha_pack(const float* whiten /*(128,128): dist=||f@whiten - mu_w||
                        const float* class_count /*(classes) or NULL; count<=0 => class skipped*/,
                        int32_t classes, void* blob, cmhar_stream_t s);
 
-/* One fused launch: windows -> encoder -> [head -> logits, arg-max, MSP, energy] [-> Mahalanobis].
+/* Windows -> encoder -> [head -> logits, arg-max, MSP, energy] [-> Mahalanobis]: the fused encoder launch,
+ * followed (when a head / maha blob is given) by the head + scores launch on the CLS features it wrote.
  * Replaces IMUEncoder.forward / IMUClassifier.forward (models.py:100-132,328-339) and the per-batch
  * body of Evaluator.predict (src/eval/evaluator.py:44-45).
  *   x            channel-0 samples of window 0; window w starts at x + w*x_window_stride (floats);
@@ -119,7 +120,7 @@ int    cmhar_maha_pack(const float* whiten /*(128,128): dist=||f@whiten - mu_w||
  */
 int cmhar_imu_forward(const void* encoder_blob, const void* head_blob, const void* maha_blob,
                       const float* x, int64_t n_windows, int64_t x_window_stride,
-                      float* cls_out        /* (n,128)      */,
+                      float* cls_out        /* (n,128); required with head_blob / maha_out */,
                       float* tokens_out     /* (n,seq,128)  */,
                       float* logits_out     /* (n,classes)  */,
                       int64_t* pred_out     /* (n)          */,
