@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_P));
+                PROG(14);
                 // ---- O (buffer C) -> smem (Q region) as bf16
                 PROG(15); mbar_wait(BAR(B_ACC + 2), ph.next(B_ACC + 2), 15); PROG(1015);
                 tc_fence_after();
@@ -515,12 +516,14 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     if (!(args.ablate & ABL_NO_STS)) store_bf16_32(smem + OFF_Q + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
                 }
                 publish(B_O);
+                PROG(150);
                 // ---- LN1: h1 = LN(R) ; hA = bf16(h1) ; R = h1 + b_2
                 PROG(16); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 16); PROG(1016);
                 tc_fence_after();
                 layer_norm_R(PB + PB_LN1, PB + PB_B2, true, nullptr);
                 if (args.dbg_stage == 1 && l == 0) { tc_wait_st(); dump_R(tile); }
                 publish(B_HA);
+                PROG(160);
                 // ---- FFN1 chunks: relu(acc + b_1) -> hidden chunk c (bf16)
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
@@ -722,6 +725,12 @@ int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_secti
     return CMHAR_OK;
 }
 
+static int ablate_mask() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("CMHAR_ABLATE"); m = e ? atoi(e) : 0; }
+    return m;
+}
+
 static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
     static bool configured[64] = {};
     int dev = 0;
@@ -744,12 +753,6 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
     return launch_head_after_encoder(args.f, stream);
 }
 
-static int ablate_mask() {
-    static int m = -1;
-    if (m < 0) { const char* e = getenv("CMHAR_ABLATE"); m = e ? atoi(e) : 0; }
-    return m;
-}
-
 int launch_head_after_encoder(const FwdArgs& a, cudaStream_t stream);     // imu_encoder_fp32.cu
 
 int launch_imu_forward_bf16(const FwdArgs& a, cudaStream_t stream) {
@@ -760,7 +763,7 @@ int launch_imu_forward_bf16(const FwdArgs& a, cudaStream_t stream) {
 int launch_imu_forward_bf16_debug(const FwdArgs& a, int stage, float* dump, int* progress, cudaStream_t stream) {
     // stage >= 100: `dump` is reinterpreted as the (10, TLOG_CAP, 2) int64 timeline buffer of block 0
     Bf16Args args{a, stage >= 100 ? -1 : stage, stage >= 100 ? nullptr : dump, progress,
-                  stage >= 100 ? reinterpret_cast<long long*>(dump) : nullptr, 0};
+                  stage >= 100 ? reinterpret_cast<long long*>(dump) : nullptr, ablate_mask()};
     return launch_bf16(args, stream);
 }
 

@@ -1,5 +1,6 @@
-"""Development aid: per-warp (code, clock64) timeline of block 0 of the bf16 kernel.
-   python tools/timeline_bf16.py [n_windows]"""
+"""Development aid: per-warp (code, clock64) timeline of block 0 of the bf16 kernel, merged over the
+MMA-issuer warp and epilogue warp 0 for one steady-state layer.
+   [CMHAR_ABLATE=mask] python tools/timeline_bf16.py [n_windows]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,32 +19,26 @@ for rep in range(2):
     N.check(N.lib().cmhar_debug_imu_bf16(blob.data_ptr(), x.data_ptr(), n, x.stride(0), 100, tlog.data_ptr(), None, None, N.stream_ptr(x.device)))
     torch.cuda.synchronize()
 t = tlog.view(18, CAP, 2).cpu().numpy()
-os.makedirs("gpurun_out", exist_ok=True); np.save("gpurun_out/timeline_bf16.npy", t)
-names = {3: "MMA wait HA(patch)", 4: "MMA wait HA(qkv)", 5: "MMA wait QKV smem", 6: "MMA wait P", 8: "MMA wait O", 9: "MMA wait HA(ffn)", 10: "MMA wait HID",
-         11: "EPI wait R(patch)", 12: "EPI wait QKV acc", 13: "EPI wait S", 15: "EPI wait O acc", 16: "EPI wait R(outproj)", 17: "EPI wait FFN1 acc", 18: "EPI wait R(ffn2)", 2: "MMA wait Wfull", 1: "LOAD wait Wempty"}
+os.makedirs("gpurun_out", exist_ok=True); np.save(f"gpurun_out/timeline_bf16_a{os.environ.get('CMHAR_ABLATE', '0')}.npy", t)
+names = {3: "M wait HA(patch)", 4: "M wait HA(qkv)", 5: "M wait QKV smem", 6: "M wait P", 8: "M wait O", 9: "M wait HA(ffn)", 10: "M wait HID",
+         11: "E wait R(patch)", 12: "E wait QKV acc", 13: "E wait S", 14: "E P published", 15: "E wait O acc", 150: "E O published", 16: "E wait R(outproj)",
+         160: "E LN1 published", 17: "E wait FFN1 acc", 18: "E wait R(ffn2)"}
 NQ = 4 if os.environ.get("CMHAR_EPI_WARPS") == "16" else 2
-for warp, label in ((4 * NQ, "MMA issuer"), (0, "epilogue warp 0")):
-    ev = t[warp]; ev = ev[ev[:, 1] > 0]
-    if len(ev) == 0: continue
-    t0 = ev[0, 1]
-    print(f"== {label}: {len(ev)} events; first tile span")
-    # print first tile only: until code 3/11 appears the second time
-    first = 3 if warp == 4 * NQ else 11
-    seen = 0
-    agg = {}
-    prev_t = t0
-    for code, clk in ev:
-        if code == first:
-            seen += 1
-            if seen == 3: break
-        if seen == 2:      # second tile (steady state)
-            key = int(code)
-            dt = clk - prev_t
-            agg.setdefault(key, [0, 0]); agg[key][0] += dt; agg[key][1] += 1
-        prev_t = clk
-    tot = sum(v[0] for v in agg.values())
-    print(f"   steady-state tile: {tot} cycles")
-    for key, (dt, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-        kind = "time WAITING at" if key >= 1000 else "work BEFORE reaching"
-        nm = names.get(key % 1000, str(key % 1000))
-        print(f"   {dt:9d} cyc {100 * dt / tot:5.1f}%  x{cnt:3d}  {kind} [{nm}]")
+ev = []
+for warp, tag in ((4 * NQ, "M"), (0, "E")):
+    e = t[warp]; e = e[e[:, 1] > 0]
+    ev += [(int(clk), tag, int(code)) for code, clk in e]
+ev.sort()
+# steady state: second tile of the MMA warp = between the 2nd and 3rd occurrence of code 3
+starts = [clk for clk, tag, code in ev if tag == "M" and code == 3]
+qk = [clk for clk, tag, code in ev if tag == "M" and code == 4 and clk > starts[1]]
+print(f"ablate={os.environ.get('CMHAR_ABLATE', '0')}  tile span {starts[2] - starts[1]} cycles; layer spans {[qk[i + 1] - qk[i] for i in range(3)]}")
+lo, hi = qk[1], qk[2]
+prev = {"M": lo, "E": lo}
+for clk, tag, code in ev:
+    if clk < lo or clk > hi: continue
+    nm = names.get(code % 1000, str(code % 1000))
+    arrived = " (passed)" if code >= 1000 and code % 1000 in names else ""
+    pad = "" if tag == "M" else " " * 44
+    print(f"{clk - lo:7d} {pad}{tag} +{clk - prev[tag]:5d} {nm}{arrived}")
+    prev[tag] = clk
