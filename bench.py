@@ -5,11 +5,12 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the path's CPU implementation on the host cores
 
-One step = one pass of the hot path over one batch (per GPU) of the configs[1] workload:
-B IMU windows (B,6,250) fp32 + the video trunk's feature maps (B*16,512,4,4) bf16 ->
-IMU encoder + classifier head + arg-max/MSP/energy/Mahalanobis (one launch), video tail
-(pool + projection), both projection heads, L2 normalisation, B x B similarity with the fused
-sigmoid contrastive loss.  Weak scaling: every rank owns its own batch, no data-path collective.
+One step = one pass of the hot path over one batch (per GPU) of the configs[1] workload
+("IMU+video late-fusion classifier", batch 256): B IMU windows (B,6,250) fp32 + the video trunk's
+feature maps (B*16,512,4,4) bf16 -> IMU encoder (one tcgen05 launch), video tail (pool + projection),
+late-fusion concat-MLP + classifier head + arg-max/MSP/energy/Mahalanobis, both projection heads, L2
+normalisation, B x B similarity with the fused sigmoid contrastive loss.  Weak scaling: every rank owns
+its own batch, no data-path collective.
 
 Timing: W warm-up steps, K timed steps bracketed by barrier + synchronize, CUDA events on the
 launching stream, max over ranks.  Inputs rotate over enough distinct batches that the set exceeds
@@ -30,10 +31,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "fused encode->fuse->OOD-score windows/sec"
+WORKLOAD = ("configs[1] IMU+video late-fusion classifier, batch {B}/GPU: IMU (B,6,250) fp32 + trunk feature maps (B*16,512,4,4) bf16 -> IMU encoder, video tail, late-fusion concat-MLP + head + MSP/energy/Mahalanobis, projection heads, L2-norm, BxB similarity + sigmoid loss")
 UNIT = "windows/s"
 FRAMES, FEAT_C, FEAT_HW, WINDOW = 16, 512, 4, 250
 # algorithmic work per window (dead channels 1-5 never counted)
 FLOP_IMU = 25_890_816           # patch embed + 4 encoder layers (16 tokens) + classifier head
+FLOP_ENC = FLOP_IMU - 139_264   # the encoder launch alone (the head + scores run as a second, CUDA-core launch)
 BYTES_VIDEO = FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2 + 768 * 4     # bf16 fmap in + pooled-projected feature out
 
 
@@ -61,14 +64,15 @@ def build_modules(device, seed=0):
     clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg)
     xm = cm.CrossModalModel(cfg)
     xm.imu_encoder.load_state_dict(clf.imu_encoder.state_dict())
+    fus = cm.LateFusionClassifier(clf.imu_encoder, xm.video_encoder, cfg)       # shares both encoders
     g = torch.Generator().manual_seed(seed + 1)
-    for mod in list(clf.modules()) + list(xm.modules()):
+    for mod in list(clf.modules()) + list(xm.modules()) + list(fus.modules()):
         if isinstance(mod, torch.nn.BatchNorm1d):
             mod.running_mean.copy_(torch.randn(mod.num_features, generator=g))
             mod.running_var.copy_(torch.rand(mod.num_features, generator=g) * 1.5 + 0.5)
             mod.weight.data.copy_(torch.randn(mod.num_features, generator=g))
             mod.bias.data.copy_(torch.randn(mod.num_features, generator=g))
-    return cfg, clf.to(device).eval(), xm.to(device).eval()
+    return cfg, clf.to(device).eval(), xm.to(device).eval(), fus.to(device).eval()
 
 
 def synth_inputs(device, batch, n_sets, rank):
@@ -136,7 +140,7 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------- CPU baseline / reference arm
-def cpu_workload(clf, xm, batch, budget_s=15.0, min_iters=3):
+def cpu_workload(clf, xm, fus, batch, budget_s=15.0, min_iters=3):
     """The oracle port (oracle/oracle.py = CPU restatement of the reference modules, torch CPU ops,
     all host threads) on the same workload: one sample = one full batch of `batch` windows.
     Returns (windows_per_s, cores, n_iters)."""
@@ -145,6 +149,7 @@ def cpu_workload(clf, xm, batch, budget_s=15.0, min_iters=3):
     from oracle import ood_spec, oracle, weights as W
     sd_c = {k: v.detach().cpu().numpy() for k, v in clf.state_dict().items()}
     sd_x = {k: v.detach().cpu().numpy() for k, v in xm.state_dict().items()}
+    sd_f = {k: v.detach().cpu().numpy() for k, v in fus.state_dict().items()}
     dims = W.Dims()
     rs = np.random.RandomState(99)
     imu = rs.standard_normal((batch, 6, WINDOW)).astype(np.float32)
@@ -157,13 +162,16 @@ def cpu_workload(clf, xm, batch, budget_s=15.0, min_iters=3):
 
     def one():
         with torch.no_grad():
-            logits, cls = oracle.imu_classifier(imu, sd_c, dims)
+            cls, _ = oracle.imu_encoder(imu, sd_c, dims, "imu_encoder.")
+            vf = oracle.video_tail(fmap, sd_x, FRAMES)
+            fused = torch.relu(oracle._bn_eval(torch.cat([cls, vf], 1) @ oracle._t(sd_f, "fusion.0.weight", torch.float32).T
+                                               + oracle._t(sd_f, "fusion.0.bias", torch.float32), sd_f, "fusion.1", torch.float32))
+            logits = oracle.classifier_head(fused, sd_f, dims)
             oracle.predict(logits)
             z = logits - logits.max(1, keepdim=True)[0]
             (-1.0 / z.exp().sum(1)); (-torch.logsumexp(logits, 1))
-            y = cls @ whiten
+            y = fused @ whiten
             ((y[:, None, :] - mw[None]) ** 2).sum(-1).min(1)
-            vf = oracle.video_tail(fmap, sd_x, FRAMES)
             ip = oracle.l2_normalize(oracle.projection_head(cls, sd_x, "imu_proj."))
             vp = oracle.l2_normalize(oracle.projection_head(vf, sd_x, "video_proj."))
             oracle.sigmoid_contrastive_loss(ip, vp)
@@ -184,19 +192,19 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    cfg, clf, xm = build_modules("cpu")
+    cfg, clf, xm, fus = build_modules("cpu")
     # K timed steps, each one bounded sample (one batch) of the workload
     import numpy as np
     from oracle import weights as W  # noqa
     per = []
-    wps, cores, _ = cpu_workload(clf, xm, args.batch, budget_s=0.0, min_iters=max(1, args.warmup))
+    wps, cores, _ = cpu_workload(clf, xm, fus, args.batch, budget_s=0.0, min_iters=max(1, args.warmup))
     t0 = time.perf_counter()
-    wps, cores, iters = cpu_workload(clf, xm, args.batch, budget_s=0.0, min_iters=max(1, min(args.steps, 50)))
+    wps, cores, iters = cpu_workload(clf, xm, fus, args.batch, budget_s=0.0, min_iters=max(1, min(args.steps, 50)))
     ms = args.batch / wps * 1e3
     line = {"impl": "reference", "metric": METRIC, "value": wps, "unit": UNIT, "n_gpus": args.gpus, "steps": iters,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"configs[1] cross-modal batch {args.batch}: IMU (B,6,250) fp32 + trunk feature maps (B*16,512,4,4) -> encoder+head+MSP/energy/Mahalanobis, video tail, projection heads, similarity + sigmoid loss",
+            "config": {"workload": WORKLOAD.format(B=args.batch),
                        "batch_per_gpu": args.batch},
             "cpu_baseline": {"value": wps, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{iters} batches of {args.batch} windows (oracle/oracle.py on torch CPU ops, {torch.get_num_threads()} threads)"},
@@ -248,7 +256,7 @@ def main():
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
-    cfg, clf, xm = build_modules(dev)
+    cfg, clf, xm, fus = build_modules(dev)
     precision = args.precision
     if precision == "auto":
         try:
@@ -257,13 +265,16 @@ def main():
         except RuntimeError:
             precision = "fp32"
     B = args.batch
-    # Mahalanobis state: fitted (untimed) on this rank's shard of synthetic ID features, all-reduced
-    fit_x = torch.randn(4096, 6, WINDOW, device=dev, generator=torch.Generator(device=dev).manual_seed(77 + rank))
-    fit_y = torch.randint(0, 32, (4096,), device=dev, generator=torch.Generator(device=dev).manual_seed(78 + rank))
+    # Mahalanobis state: fitted (untimed) on this rank's shard of synthetic ID fused features, all-reduced
+    gfit = torch.Generator(device=dev).manual_seed(77 + rank)
+    fit_x = torch.randn(2048, 6, WINDOW, device=dev, generator=gfit)
+    fit_f = torch.relu(torch.randn(2048 * FRAMES, FEAT_C, FEAT_HW, FEAT_HW, device=dev, generator=gfit)).to(torch.bfloat16)
+    fit_y = torch.randint(0, 32, (2048,), device=dev, generator=gfit)
     maha = cm.MahalanobisOOD(32, dev, ridge=1e-3)
-    maha.accumulate(clf.forward_scores(fit_x, precision=precision, want_cls=True)["cls"], fit_y)
+    maha.accumulate(fus.forward_scores(fit_x, fit_f, FRAMES, precision=precision)["fused"], fit_y)
     maha.finalize()
-    pipe = cm.CrossModalOODPipeline(clf, xm, maha, frames=FRAMES, precision=precision)
+    del fit_f
+    pipe = cm.CrossModalOODPipeline(clf, xm, maha, frames=FRAMES, precision=precision, fusion=fus)
 
     bytes_per_set = B * (6 * WINDOW * 4 + FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2)
     n_sets = max(2, -(-300_000_000 // bytes_per_set))           # rotate over > 2x L2 worth of inputs
@@ -300,14 +311,16 @@ def main():
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- dominant kernel alone (roofline): the fused IMU launch, timed with CUDA events
+    from crossmodal_imu_video_ood_har_b200.models import imu_forward_native
     k_iters = max(20, min(args.steps, 200))
     outs = [dict() for _ in range(n_sets)]
+    enc_only = lambda i: imu_forward_native(clf.imu_encoder, None, None, sets[i][0], want_cls=True, precision=precision, out=outs[i])
     for i in range(n_sets):
-        clf.forward_scores(sets[i][0], precision=precision, want_cls=True, out=outs[i])
+        enc_only(i)
     torch.cuda.synchronize(dev)
     e0.record(stream)
     for i in range(k_iters):
-        clf.forward_scores(sets[i % n_sets][0], precision=precision, want_cls=True, out=outs[i % n_sets])
+        enc_only(i % n_sets)
     e1.record(stream)
     torch.cuda.synchronize(dev)
     imu_ms = e0.elapsed_time(e1) / k_iters
@@ -321,11 +334,11 @@ def main():
     torch.cuda.synchronize(dev)
     pool_ms = e0.elapsed_time(e1) / k_iters
     peaks = measured_peaks()
-    tf = FLOP_IMU * B / (imu_ms * 1e-3) / 1e12
+    tf = FLOP_ENC * B / (imu_ms * 1e-3) / 1e12
     gbs = (B * FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2 + B * FEAT_C * 4) / (pool_ms * 1e-3) / 1e9
     roofline = {"kernel": f"imu_forward_{precision}_kernel", "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " burst (kernel timed alone)",
-                "launch_ms": imu_ms, "flop_per_window": FLOP_IMU}
+                "launch_ms": imu_ms, "flop_per_window": FLOP_ENC, "windows_per_launch": B}
     roofline_video = {"kernel": "video_pool_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                       "frac": gbs / peaks["hbm_gbs"], "traffic": None, "launch_ms": pool_ms}
 
@@ -349,12 +362,13 @@ def main():
     e2e_value = world * B * e2e_steps / (float(t) * 1e-3)
     h2d, d2h = pipe.host_bytes_per_step(B, WINDOW, fmap_host)
     # IMU-only end to end (the reference Evaluator.predict path: windows in, labels + scores out)
+    pipe_imu = cm.CrossModalOODPipeline(clf, xm, None, frames=FRAMES, precision=precision)
     for _ in range(3):
-        pipe.run_host(imu_host, None)
+        pipe_imu.run_host(imu_host, None)
     torch.cuda.synchronize(dev)
     e0.record(stream)
     for _ in range(e2e_steps):
-        pipe.run_host(imu_host, None)
+        pipe_imu.run_host(imu_host, None)
     e1.record(stream)
     torch.cuda.synchronize(dev)
     e2e_imu = B * e2e_steps / (e0.elapsed_time(e1) * 1e-3)
@@ -365,22 +379,26 @@ def main():
         for nb in (256, 4096, 65536):
             xs = [torch.randn(nb, 6, WINDOW, device=dev) for _ in range(max(2, min(8, 200_000_000 // (nb * 6000))))]
             so = [dict() for _ in xs]
-            for i, x in enumerate(xs):
-                clf.forward_scores(x, precision=precision, out=so[i])
             reps = max(3, min(50, 2_000_000 // nb))
-            torch.cuda.synchronize(dev)
-            e0.record(stream)
-            for i in range(reps):
-                clf.forward_scores(xs[i % len(xs)], precision=precision, out=so[i % len(xs)])
-            e1.record(stream)
-            torch.cuda.synchronize(dev)
-            ms = e0.elapsed_time(e1) / reps
-            sweep[str(nb)] = {"windows_per_s": nb / (ms * 1e-3), "tflops": FLOP_IMU * nb / (ms * 1e-3) / 1e12}
+            entry = {}
+            for name, fn, flop in (("encoder", lambda i: imu_forward_native(clf.imu_encoder, None, None, xs[i], want_cls=True, precision=precision, out=so[i]), FLOP_ENC),
+                                   ("encoder+head+scores", lambda i: clf.forward_scores(xs[i], precision=precision, out=so[i]), FLOP_IMU)):
+                for i in range(len(xs)):
+                    fn(i)
+                torch.cuda.synchronize(dev)
+                e0.record(stream)
+                for i in range(reps):
+                    fn(i % len(xs))
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / reps
+                entry[name] = {"windows_per_s": nb / (ms * 1e-3), "tflops": flop * nb / (ms * 1e-3) / 1e12}
+            sweep[str(nb)] = entry
             del xs, so
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        wps, cores, iters = cpu_workload(clf, xm, B, budget_s=12.0)
+        wps, cores, iters = cpu_workload(clf, xm, fus, B, budget_s=12.0)
         cpu_baseline = {"value": wps, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{iters} batches of {B} windows of the same workload (oracle/oracle.py, torch CPU ops)"}
     if world > 1:
@@ -389,7 +407,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": precision, "data": "synthetic",
-                "config": {"workload": f"configs[1] cross-modal batch {B}/GPU: IMU (B,6,250) fp32 + trunk feature maps (B*16,512,4,4) bf16 -> IMU encoder+head+MSP/energy/Mahalanobis, video tail, projection heads, L2-norm, BxB similarity + sigmoid loss",
+                "config": {"workload": WORKLOAD.format(B=B),
                            "batch_per_gpu": B, "global_batch": B * world, "frames": FRAMES, "parallelism": f"dp{world} (windows sharded by rank, no collective)",
                            "l2_policy": f"inputs_larger_than_L2: {n_sets} rotating input sets, {n_sets * bytes_per_set / 1e6:.0f} MB",
                            "cuda_graph": True},

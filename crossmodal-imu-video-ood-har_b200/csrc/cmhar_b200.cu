@@ -9,5 +9,6 @@ namespace cmhar { struct FwdArgs; }
 #include "head.cu"
 #include "dense.cu"
 #include "similarity.cu"
+#include "fusion.cu"
 #include "ood.cu"
 #include "api.cu"

@@ -17,8 +17,11 @@ constexpr int LT_ROWS = 32, LT_COLS = 64, LT_K = 32, LT_SPLIT_MAX = 8;
 //   * the k loop is split over gridDim.z CTAs (each k slice lands in its own partial buffer and a
 //     fixed-order reduction adds them: deterministic, no atomics),
 //   * the next k slab is prefetched into registers while the current one is multiplied.
+// X2 != nullptr: the input row is the concatenation [X (K1 columns) | X2 (K - K1 columns)] (late-fusion
+// concat-MLP: the concatenated feature is never materialised).
 __global__ void __launch_bounds__(128) linear_fp32_kernel(const float* __restrict__ Wt, const float* __restrict__ bias,
-                                                          const float* __restrict__ X, long long n, int K, int N,
+                                                          const float* __restrict__ X, const float* __restrict__ X2, int K1,
+                                                          long long n, int K, int N,
                                                           int relu, float* __restrict__ Y, float* __restrict__ partial) {
     __shared__ __align__(16) float As[LT_K][LT_ROWS + 4];     // transposed: As[k][row]
     __shared__ __align__(16) float Ws[LT_K][LT_COLS];
@@ -41,7 +44,10 @@ __global__ void __launch_bounds__(128) linear_fp32_kernel(const float* __restric
         for (int q = 0; q < 2; ++q) {
             const int e = tid + q * 128, r = e >> 3, k4 = (e & 7) * 4;
             xa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + r < n && k0 + k4 < K) xa[q] = __ldg(reinterpret_cast<const float4*>(X + (row0 + r) * K + k0 + k4));
+            const int k = k0 + k4;
+            if (row0 + r < n && k < K)
+                xa[q] = (k < K1) ? __ldg(reinterpret_cast<const float4*>(X + (row0 + r) * K1 + k))
+                                 : __ldg(reinterpret_cast<const float4*>(X2 + (row0 + r) * (K - K1) + (k - K1)));
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -206,8 +212,9 @@ size_t cmhar_linear_work_bytes(int64_t n, int32_t out_dim) {
     return (size_t)LT_SPLIT_MAX * (size_t)(n > 0 ? n : 0) * (size_t)out_dim * sizeof(float);
 }
 
-int cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in_dim, int32_t out_dim, int32_t relu,
-                         float* y, void* work, size_t work_bytes, int32_t precision, cmhar_stream_t s) {
+static int linear_forward_impl(const void* blob, const float* x, const float* x2, int32_t in_dim1, int64_t n, int32_t in_dim,
+                               int32_t out_dim, int32_t relu, float* y, void* work, size_t work_bytes, int32_t precision,
+                               cmhar_stream_t s) {
     CMHAR_REQUIRE(blob && x && y, "cmhar_linear_forward: null argument");
     CMHAR_REQUIRE(cmhar_linear_blob_bytes(in_dim, out_dim) != 0, "linear dims (%d,%d) must be multiples of 4", in_dim, out_dim);
     CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
@@ -223,8 +230,8 @@ int cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in
         if (splits > slabs) splits = slabs;
         if ((size_t)splits * n * out_dim * sizeof(float) > work_bytes) splits = 1;
     }
-    linear_fp32_kernel<<<dim3(gx, gy, splits), 128, 0, (cudaStream_t)s>>>(f, f + (size_t)in_dim * out_dim, x, n, in_dim, out_dim,
-                                                                          relu, y, reinterpret_cast<float*>(work));
+    linear_fp32_kernel<<<dim3(gx, gy, splits), 128, 0, (cudaStream_t)s>>>(f, f + (size_t)in_dim * out_dim, x, x2, x2 ? in_dim1 : in_dim,
+                                                                          n, in_dim, out_dim, relu, y, reinterpret_cast<float*>(work));
     CMHAR_LAUNCH_CHECK();
     if (splits > 1) {
         const long long total4 = n * out_dim / 4;
@@ -233,6 +240,19 @@ int cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in
         CMHAR_LAUNCH_CHECK();
     }
     return CMHAR_OK;
+}
+
+int cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in_dim, int32_t out_dim, int32_t relu,
+                         float* y, void* work, size_t work_bytes, int32_t precision, cmhar_stream_t s) {
+    return linear_forward_impl(blob, x, nullptr, in_dim, n, in_dim, out_dim, relu, y, work, work_bytes, precision, s);
+}
+
+int cmhar_concat_linear_forward(const void* blob, const float* x1, int32_t in_dim1, const float* x2, int32_t in_dim2, int64_t n,
+                                int32_t out_dim, int32_t relu, float* y, void* work, size_t work_bytes, int32_t precision,
+                                cmhar_stream_t s) {
+    CMHAR_REQUIRE(x2 && in_dim1 >= 4 && in_dim2 >= 4 && !(in_dim1 & 3) && !(in_dim2 & 3),
+                  "cmhar_concat_linear_forward: both inputs need a multiple-of-4 width (%d, %d)", in_dim1, in_dim2);
+    return linear_forward_impl(blob, x1, x2, in_dim1, n, in_dim1 + in_dim2, out_dim, relu, y, work, work_bytes, precision, s);
 }
 
 int cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmhar_stream_t s) {

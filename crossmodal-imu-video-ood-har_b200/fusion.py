@@ -1,0 +1,235 @@
+"""Cross-modal fusion classifiers (north-star item 3: "cross-attention or
+concat-MLP").
+
+SPEC-DEFINED -- NOT IN THE REFERENCE.  /root/reference has no fusion classifier: its only
+cross-modal coupling is two projection heads and the similarity matrix inside the loss.  BASELINE.json's
+configs[1] ("IMU+video late-fusion classifier") and configs[2] ("cross-attention fusion") name these blocks
+anyway, so they are defined here explicitly, built from the reference's own pieces (its ``IMUEncoder``,
+``VideoEncoder`` tail and classifier-head layout), with a plain-PyTorch restatement in
+``oracle/fusion_spec.py``.  Every result is "self-consistent with the in-repo spec", never reference parity.
+
+``LateFusionClassifier``     f = ReLU(BN(Linear([imu_cls (128) | video_feat (768)] -> 128)))  (concat-MLP)
+                              logits = classifier_head(f)      head = the reference's layout
+                              (src/models/models.py:312-326: [Linear, BN, ReLU, Dropout] x 2, Linear)
+``CrossAttentionFusionClassifier``
+                              q = Linear(imu_tokens), [k|v] = Linear(frame_feats); 8-head attention of the S IMU
+                              tokens over the T frame tokens; y = LayerNorm(imu_tokens + Linear(attn));
+                              f = mean_s y; logits = classifier_head(f)
+
+Inference (eval + no_grad, CUDA tensors) runs only hand-written kernels: the fused IMU encoder, the video
+pooling kernel, ``cmhar_concat_linear_forward`` / ``cmhar_linear_forward``, ``cmhar_cross_attention``,
+``cmhar_residual_ln_pool`` and the head + OOD-score kernel.  Training routes through differentiable torch ops
+on the same parameters, exactly like the other modules of this package.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native as N
+from .models import (IMUEncoder, VideoEncoder, _PackedLinear, _PackedMixin, _native_mode, _prec_code,
+                     imu_forward_native, pack_head_blob)
+
+__all__ = ["LateFusionClassifier", "CrossAttentionFusionClassifier", "head_scores_native"]
+
+
+def _head(in_dim: int, config) -> nn.Sequential:
+    m = config.model
+    layers = []
+    for hidden in m.classifier_hidden_dims:
+        layers += [nn.Linear(in_dim, hidden), nn.BatchNorm1d(hidden), nn.ReLU(inplace=True), nn.Dropout(m.classifier_dropout)]
+        in_dim = hidden
+    layers.append(nn.Linear(in_dim, m.num_classes))
+    return nn.Sequential(*layers)
+
+
+def head_scores_native(head_blob: torch.Tensor, maha_blob: Optional[torch.Tensor], feat: torch.Tensor, classes: int,
+                       out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """Classifier head + arg-max / MSP / energy (+ Mahalanobis) on stored (n,128) features: one launch."""
+    feat = N.f32c(feat)
+    n, dev = feat.shape[0], feat.device
+    out = {} if out is None else out
+
+    def buf(name, shape, dtype=torch.float32):
+        t = out.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            out[name] = t
+        return t
+    logits, pred = buf("logits", (n, classes)), buf("pred", (n,), torch.int64)
+    msp, energy = buf("msp", (n,)), buf("energy", (n,))
+    maha = buf("maha", (n,)) if maha_blob is not None else None
+    with torch.cuda.device(dev):
+        N.check(N.lib().cmhar_head_forward(head_blob.data_ptr(), N.ptr(maha_blob), feat.data_ptr(), n, logits.data_ptr(),
+                                           pred.data_ptr(), msp.data_ptr(), energy.data_ptr(), N.ptr(maha), N.stream_ptr(dev)))
+    return out
+
+
+class _FusionBase(_PackedMixin, nn.Module):
+    def __init__(self, imu_encoder: IMUEncoder, video_encoder: VideoEncoder, config):
+        super().__init__()
+        self.imu_encoder, self.video_encoder, self.config = imu_encoder, video_encoder, config
+        self.d_model = config.model.imu_d_model
+        self.num_classes = config.model.num_classes
+        self.classifier = _head(self.d_model, config)
+        self._maha_state = None
+
+    def set_mahalanobis(self, maha) -> None:
+        """Attach a fitted ``ood.MahalanobisOOD`` (on the fused 128-d feature)."""
+        self._maha_state = maha
+
+    def _head_blob(self, device) -> torch.Tensor:
+        key = ("head", str(device))
+        if key not in self._packed:
+            self._packed[key] = pack_head_blob(self.classifier, device)
+        return self._packed[key]
+
+    def _check(self):
+        if self.training:
+            raise RuntimeError("forward_scores is an inference entry point: call .eval() first")
+        if self.d_model != 128:
+            raise NotImplementedError("native fusion kernels are specialised to a 128-d fused feature")
+
+    def _scores(self, fused: torch.Tensor, out: Optional[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
+        dev = fused.device
+        maha_blob = self._maha_state.blob(dev) if self._maha_state is not None else None
+        res = head_scores_native(self._head_blob(dev), maha_blob, fused, self.num_classes, out)
+        res["fused"] = fused
+        return res
+
+
+class LateFusionClassifier(_FusionBase):
+    """concat-MLP late fusion (spec-defined, see the module docstring).
+
+    ``forward(imu (B,6,L), video (B,T,3,H,W)) -> logits (B, num_classes)``;
+    ``forward_scores(imu, fmap (B*T,F,h,w), frames)`` is the fused inference entry used by the pipeline."""
+
+    def __init__(self, imu_encoder: IMUEncoder, video_encoder: VideoEncoder, config):
+        super().__init__(imu_encoder, video_encoder, config)
+        m = config.model
+        self.fusion = nn.Sequential(nn.Linear(m.imu_d_model + m.video_d_model, self.d_model),
+                                    nn.BatchNorm1d(self.d_model), nn.ReLU(inplace=True), nn.Dropout(m.classifier_dropout))
+        self._init_packed()
+
+    def _fusion_packed(self, device) -> _PackedLinear:
+        key = ("fusion", str(device))
+        if key not in self._packed:
+            self._packed[key] = _PackedLinear(self.fusion[0], self.fusion[1], device)
+        return self._packed[key]
+
+    def fuse_native(self, imu_cls: torch.Tensor, video_feat: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+        """ReLU(BN(Linear([imu_cls | video_feat]))) without materialising the concatenation."""
+        pl = self._fusion_packed(imu_cls.device)
+        a, b = N.f32c(imu_cls), N.f32c(video_feat)
+        n = a.shape[0]
+        y = torch.empty((n, pl.out_dim), dtype=torch.float32, device=a.device)
+        lib = N.lib()
+        work, wbytes = None, 0
+        if 0 < n <= 2048:
+            wbytes = lib.cmhar_linear_work_bytes(n, pl.out_dim)
+            work = torch.empty(wbytes, dtype=torch.uint8, device=a.device)
+        with torch.cuda.device(a.device):
+            N.check(lib.cmhar_concat_linear_forward(pl.blob.data_ptr(), a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], n,
+                                                    pl.out_dim, 1, y.data_ptr(), N.ptr(work), wbytes, _prec_code(precision),
+                                                    N.stream_ptr(a.device)))
+        return y
+
+    @torch.no_grad()
+    def forward_scores(self, imu, fmap, frames: int, *, precision: Optional[str] = None, window_stride: Optional[int] = None,
+                       imu_cls: Optional[torch.Tensor] = None, video_feat: Optional[torch.Tensor] = None,
+                       out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """logits, pred, msp, energy (maha) of the fused classifier.  ``imu_cls`` / ``video_feat`` may be passed
+        when the caller already holds them (the pipeline shares them with the contrastive branch)."""
+        self._check()
+        if imu_cls is None:
+            imu_cls = imu_forward_native(self.imu_encoder, None, None, imu, want_cls=True, precision=precision,
+                                         window_stride=window_stride)["cls"]
+        if video_feat is None:
+            video_feat = self.video_encoder.forward_features(fmap, frames, precision=precision)
+        return self._scores(self.fuse_native(imu_cls, video_feat, precision), out)
+
+    def forward(self, imu, video):
+        if _native_mode(self):
+            N.require_cuda(imu, "LateFusionClassifier")
+            cls = imu_forward_native(self.imu_encoder, None, None, imu, want_cls=True)["cls"]
+            vfeat = self.video_encoder(video)
+            return self._scores(self.fuse_native(cls, vfeat), None)["logits"]
+        cls, _ = self.imu_encoder(imu)
+        vfeat = self.video_encoder(video)
+        return self.classifier(self.fusion(torch.cat([cls, vfeat], dim=1)))
+
+
+class CrossAttentionFusionClassifier(_FusionBase):
+    """Cross-attention fusion (spec-defined): the S IMU tokens attend over the T per-frame video tokens."""
+
+    def __init__(self, imu_encoder: IMUEncoder, video_encoder: VideoEncoder, config):
+        super().__init__(imu_encoder, video_encoder, config)
+        m = config.model
+        d = self.d_model
+        self.nhead = m.imu_nhead
+        self.q_proj = nn.Linear(d, d)
+        self.kv_proj = nn.Linear(m.video_d_model, 2 * d)
+        self.out_proj = nn.Linear(d, d)
+        self.norm = nn.LayerNorm(d)
+        self._init_packed()
+
+    def _packed_linears(self, device):
+        key = ("xattn", str(device))
+        if key not in self._packed:
+            self._packed[key] = tuple(_PackedLinear(l, None, device) for l in (self.q_proj, self.kv_proj, self.out_proj))
+        return self._packed[key]
+
+    def fuse_native(self, tokens: torch.Tensor, frame_feats: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+        """tokens (B,S,128), frame_feats (B,T,video_d_model) -> fused (B,128)."""
+        if self.nhead != 8 or self.d_model != 128:
+            raise NotImplementedError("native cross-attention is specialised to 8 heads of 16")
+        B, S, d = tokens.shape
+        T = frame_feats.shape[1]
+        dev = tokens.device
+        ql, kvl, ol = self._packed_linears(dev)
+        tok2 = N.f32c(tokens).reshape(B * S, d)
+        q = ql(tok2, relu=False, precision=precision)
+        kv = kvl(N.f32c(frame_feats).reshape(B * T, -1), relu=False, precision=precision)
+        attn = torch.empty((B * S, d), dtype=torch.float32, device=dev)
+        fused = torch.empty((B, d), dtype=torch.float32, device=dev)
+        lib = N.lib()
+        with torch.cuda.device(dev):
+            N.check(lib.cmhar_cross_attention(q.data_ptr(), kv.data_ptr(), B, S, T, attn.data_ptr(), N.stream_ptr(dev)))
+            o = ol(attn, relu=False, precision=precision)
+            g, b = N.f32c(self.norm.weight.detach()), N.f32c(self.norm.bias.detach())
+            N.check(lib.cmhar_residual_ln_pool(tok2.data_ptr(), o.data_ptr(), g.data_ptr(), b.data_ptr(), B, S,
+                                               float(self.norm.eps), fused.data_ptr(), N.stream_ptr(dev)))
+        return fused
+
+    @torch.no_grad()
+    def forward_scores(self, imu, fmap, frames: int, *, precision: Optional[str] = None,
+                       out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        self._check()
+        tokens = imu_forward_native(self.imu_encoder, None, None, imu, want_tokens=True, precision=precision)["tokens"]
+        frame_feats = self.video_encoder.forward_frame_features(fmap, precision=precision)
+        B = tokens.shape[0]
+        return self._scores(self.fuse_native(tokens, frame_feats.view(B, frames, -1), precision), out)
+
+    def _fuse_autograd(self, tokens, frame_feats):
+        B, S, d = tokens.shape
+        H = self.nhead
+        q = self.q_proj(tokens).view(B, S, H, d // H).transpose(1, 2)
+        k, v = self.kv_proj(frame_feats).chunk(2, dim=-1)
+        k = k.reshape(B, -1, H, d // H).transpose(1, 2)
+        v = v.reshape(B, -1, H, d // H).transpose(1, 2)
+        a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, d)
+        return self.norm(tokens + self.out_proj(a)).mean(dim=1)
+
+    def forward(self, imu, video):
+        B, T = video.shape[0], video.shape[1]
+        if _native_mode(self):
+            N.require_cuda(imu, "CrossAttentionFusionClassifier")
+            tokens = imu_forward_native(self.imu_encoder, None, None, imu, want_tokens=True)["tokens"]
+            frame_feats = self.video_encoder.frame_features(video)
+            return self._scores(self.fuse_native(tokens, frame_feats), None)["logits"]
+        _, tokens = self.imu_encoder(imu)
+        frame_feats = self.video_encoder.frame_features(video)
+        return self.classifier(self._fuse_autograd(tokens, frame_feats))

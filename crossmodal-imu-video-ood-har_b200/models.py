@@ -30,7 +30,7 @@ import torch.nn.functional as F
 from . import _native as N
 
 __all__ = ["PatchEmbedding", "IMUEncoder", "VideoEncoder", "ProjectionHead", "CrossModalModel",
-           "IMUClassifier", "set_default_precision", "get_default_precision"]
+           "IMUClassifier", "set_default_precision", "get_default_precision", "pack_head_blob"]
 
 _DEFAULT_PRECISION = "fp32"
 
@@ -405,6 +405,30 @@ class VideoEncoder(_PackedMixin, nn.Module):
                                              pooled.data_ptr(), N.stream_ptr(fmap.device)))
         return self._packed_projection(fmap.device)(pooled, relu=False, precision=precision)
 
+    def forward_frame_features(self, fmap: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+        """Per-frame tail (cross-attention fusion needs frame tokens): fmap (B*T, F, h, w) -> (B*T, video_d_model),
+        i.e. the reference's spatial average pool + ``projection`` (models.py:210-213) WITHOUT the temporal mean."""
+        N.require_cuda(fmap, "VideoEncoder")
+        if fmap.dtype not in (torch.float32, torch.bfloat16):
+            fmap = fmap.float()
+        fmap = fmap.contiguous()
+        BT, Fd = fmap.shape[0], fmap.shape[1]
+        pooled = torch.empty((BT, Fd), dtype=torch.float32, device=fmap.device)
+        with torch.cuda.device(fmap.device):
+            N.check(N.lib().cmhar_video_pool(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), BT, 1, Fd, fmap[0, 0].numel(),
+                                             pooled.data_ptr(), N.stream_ptr(fmap.device)))
+        return self._packed_projection(fmap.device)(pooled, relu=False, precision=precision)
+
+    def frame_features(self, x):
+        """(B, T, 3, H, W) -> per-frame features (B, T, video_d_model); CNN trunks only."""
+        if self.is_videomae:
+            raise NotImplementedError("frame_features needs a per-frame (CNN) trunk")
+        B, T = x.shape[0], x.shape[1]
+        fmap = self.backbone(x.reshape(B * T, *x.shape[2:]))
+        if _native_mode(self):
+            return self.forward_frame_features(fmap).view(B, T, -1)
+        return self.projection(fmap.mean(dim=(2, 3))).view(B, T, -1)
+
     def forward(self, x):
         B, T = x.shape[0], x.shape[1]
         native = _native_mode(self)
@@ -484,6 +508,34 @@ class CrossModalModel(_PackedMixin, nn.Module):
 
 
 # =============================================================================== classifier
+def pack_head_blob(classifier: nn.Sequential, device) -> torch.Tensor:
+    """Packs a head of the reference layout ([Linear, BN, ReLU, Dropout] x 2, Linear on a 128-d feature,
+    src/models/models.py:312-326) into the device blob ``cmhar_head_forward`` / ``cmhar_imu_forward`` take."""
+    mods = list(classifier)
+    if len(mods) != 9 or mods[0].in_features != 128:
+        raise NotImplementedError("native head supports the reference layout: 2 hidden blocks on a 128-d feature")
+    lib = N.lib()
+    p = N.HeadParams()
+    p.hidden1, p.hidden2, p.classes = mods[0].out_features, mods[4].out_features, mods[8].out_features
+    keep = []
+
+    def dp(t):
+        t = N.f32c(t.detach())
+        keep.append(t)
+        return t.data_ptr()
+    for i, (lin, bn) in enumerate(((mods[0], mods[1]), (mods[4], mods[5]))):
+        setattr(p, f"w{i}", dp(lin.weight)); setattr(p, f"b{i}", dp(lin.bias))
+        setattr(p, f"bn{i}_weight", dp(bn.weight)); setattr(p, f"bn{i}_bias", dp(bn.bias))
+        setattr(p, f"bn{i}_mean", dp(bn.running_mean)); setattr(p, f"bn{i}_var", dp(bn.running_var))
+    p.w2, p.b2 = dp(mods[8].weight), dp(mods[8].bias)
+    blob = N.alloc_blob(lib.cmhar_head_blob_bytes(p.hidden1, p.hidden2, p.classes), device)
+    with torch.cuda.device(device):
+        N.check(lib.cmhar_head_pack(C.byref(p), blob.data_ptr(), N.stream_ptr(device)))
+        torch.cuda.current_stream(device).synchronize()       # the fp32 staging copies in `keep` may be freed on return
+    del keep
+    return blob
+
+
 class IMUClassifier(_PackedMixin, nn.Module):
     """IMU encoder + MLP head (reference src/models/models.py:296-348).
 
@@ -520,31 +572,9 @@ class IMUClassifier(_PackedMixin, nn.Module):
     # ------------------------------------------------------------------ packing
     def _head_blob(self, device) -> torch.Tensor:
         key = ("head", str(device))
-        blob = self._packed.get(key)
-        if blob is None:
-            mods = list(self.classifier)
-            if len(mods) != 9 or mods[0].in_features != 128:
-                raise NotImplementedError("native head supports the reference layout: 2 hidden blocks on a 128-d feature")
-            lib = N.lib()
-            p = N.HeadParams()
-            p.hidden1, p.hidden2, p.classes = mods[0].out_features, mods[4].out_features, mods[8].out_features
-            keep = []
-
-            def dp(t):
-                t = N.f32c(t.detach())
-                keep.append(t)
-                return t.data_ptr()
-            for i, (lin, bn) in enumerate(((mods[0], mods[1]), (mods[4], mods[5]))):
-                setattr(p, f"w{i}", dp(lin.weight)); setattr(p, f"b{i}", dp(lin.bias))
-                setattr(p, f"bn{i}_weight", dp(bn.weight)); setattr(p, f"bn{i}_bias", dp(bn.bias))
-                setattr(p, f"bn{i}_mean", dp(bn.running_mean)); setattr(p, f"bn{i}_var", dp(bn.running_var))
-            p.w2, p.b2 = dp(mods[8].weight), dp(mods[8].bias)
-            blob = N.alloc_blob(lib.cmhar_head_blob_bytes(p.hidden1, p.hidden2, p.classes), device)
-            with torch.cuda.device(device):
-                N.check(lib.cmhar_head_pack(C.byref(p), blob.data_ptr(), N.stream_ptr(device)))
-            del keep
-            self._packed[key] = blob
-        return blob
+        if key not in self._packed:
+            self._packed[key] = pack_head_blob(self.classifier, device)
+        return self._packed[key]
 
     def set_mahalanobis(self, maha) -> None:
         """Attach a fitted ``ood.MahalanobisOOD`` so ``forward_scores`` also emits its score."""

@@ -3,12 +3,15 @@
 ``CrossModalOODPipeline.run`` is the call a user makes for a batch of IMU windows plus the video
 trunk's feature maps:
 
-    IMU windows --(1 launch)--> CLS feature, logits, arg-max, MSP, energy, Mahalanobis
+    IMU windows --(encoder launch)--> CLS feature
     feature maps --(pool + GEMM)--> video feature
+    both --> late-fusion concat-MLP --> head --> logits, arg-max, MSP, energy, Mahalanobis   (configs[1])
     both --> projection heads --> L2 normalise --> B x B similarity with fused sigmoid loss
+(without a fusion classifier the IMU-only head of ``IMUClassifier`` is scored instead; without feature maps
+the pass is the reference's ``Evaluator.predict`` body).
 
 Every stage is a kernel of ``libcmhar_b200.so``; nothing is computed by torch ops.  ``capture``
-records the whole pass into a CUDA graph (10 launches -> one graph launch), which is what the
+records the whole pass into a CUDA graph (one graph launch with two parallel branches), which is what the
 throughput benchmark replays.
 """
 from __future__ import annotations
@@ -19,7 +22,8 @@ import torch
 
 from . import _native as N
 from .losses import similarity_native
-from .models import CrossModalModel, IMUClassifier, l2_normalize_native
+from .fusion import LateFusionClassifier
+from .models import CrossModalModel, IMUClassifier, imu_forward_native, l2_normalize_native
 from .ood import MahalanobisOOD
 
 __all__ = ["CrossModalOODPipeline"]
@@ -28,10 +32,14 @@ __all__ = ["CrossModalOODPipeline"]
 class CrossModalOODPipeline:
     def __init__(self, classifier: IMUClassifier, cross_modal: CrossModalModel,
                  mahalanobis: Optional[MahalanobisOOD] = None, frames: int = 16,
-                 precision: Optional[str] = None, sigmoid_scale: float = 10.0, sigmoid_bias: float = -10.0):
+                 precision: Optional[str] = None, sigmoid_scale: float = 10.0, sigmoid_bias: float = -10.0,
+                 fusion: Optional[LateFusionClassifier] = None):
+        """``mahalanobis`` is attached to the classifier that gets scored: the fusion classifier when one is
+        given (it must have been fitted on FUSED features), else the IMU-only classifier."""
         self.clf, self.xm, self.frames, self.precision = classifier.eval(), cross_modal.eval(), frames, precision
+        self.fusion = fusion.eval() if fusion is not None else None
         if mahalanobis is not None:
-            self.clf.set_mahalanobis(mahalanobis)
+            (self.fusion if self.fusion is not None else self.clf).set_mahalanobis(mahalanobis)
         self.sig = (float(sigmoid_scale), float(sigmoid_bias))
         self._host = None
         self._side = None           # side stream: the video branch runs concurrently with the IMU kernel
@@ -43,6 +51,8 @@ class CrossModalOODPipeline:
         or None for the IMU-only path.  Returns device tensors: pred, msp, energy, (maha,) logits,
         cls and, with fmap, imu_proj, video_proj, loss (mean sigmoid contrastive loss, fp64 0-dim)."""
         if fmap is None:
+            if self.fusion is not None:
+                raise ValueError("a pipeline with a fusion classifier needs the video feature maps")
             return self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
         # fork: the HBM-bound video tail + its projection head on a side stream, the tensor-bound IMU
         # kernel + its projection head on the current stream; join before the similarity kernel.
@@ -55,12 +65,19 @@ class CrossModalOODPipeline:
         with torch.cuda.stream(side):
             vfeat = self.xm.video_encoder.forward_features(fmap, self.frames, precision=self.precision)
             vp = l2_normalize_native(self.xm.video_proj(vfeat))
-        out = self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
+        if self.fusion is None:
+            out = self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
+        else:
+            out = imu_forward_native(self.clf.imu_encoder, None, None, imu, want_cls=True, precision=self.precision,
+                                     window_stride=window_stride)
         ip = l2_normalize_native(self.xm.imu_proj(out["cls"]))
         main.wait_stream(side)
         if not torch.cuda.is_current_stream_capturing():
             for t in (vfeat, vp):
                 t.record_stream(main)
+        if self.fusion is not None:
+            out.update(self.fusion.forward_scores(None, None, self.frames, precision=self.precision, imu_cls=out["cls"],
+                                                  video_feat=vfeat))
         res = similarity_native(ip, vp, sigmoid=self.sig, precision=self.precision)
         out.update(imu_proj=ip, video_proj=vp, loss=res["sigmoid_sum"] / float(ip.shape[0] * vp.shape[0]))
         return out
@@ -128,5 +145,6 @@ class CrossModalOODPipeline:
     def host_bytes_per_step(self, B: int, L: int, fmap_host: Optional[torch.Tensor]):
         live = 16 * (self.clf.imu_encoder._check_native_dims(L) - 1)
         h2d = B * live * 4 + (fmap_host.numel() * fmap_host.element_size() if fmap_host is not None else 0)
-        d2h = B * (8 + 4 + 4 + (4 if self.clf._maha_state is not None else 0)) + (8 if fmap_host is not None else 0)
+        scored = self.fusion if self.fusion is not None else self.clf
+        d2h = B * (8 + 4 + 4 + (4 if scored._maha_state is not None else 0)) + (8 if fmap_host is not None else 0)
         return h2d, d2h

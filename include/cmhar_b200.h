@@ -163,8 +163,25 @@ size_t cmhar_linear_work_bytes(int64_t n, int32_t out_dim);
 int    cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in_dim,
                             int32_t out_dim, int32_t relu, float* y, void* work, size_t work_bytes,
                             int32_t precision, cmhar_stream_t s);
+/* Late-fusion concat-MLP first layer (spec row A6, no reference implementation):
+ * y = relu?([x1 | x2] @ W'^T + b') with W' (out, in_dim1 + in_dim2); the concatenation is never materialised. */
+int    cmhar_concat_linear_forward(const void* blob, const float* x1, int32_t in_dim1, const float* x2,
+                                   int32_t in_dim2, int64_t n, int32_t out_dim, int32_t relu, float* y,
+                                   void* work, size_t work_bytes, int32_t precision, cmhar_stream_t s);
 /* rows x / max(||x||_2, 1e-12)   (F.normalize(dim=1), models.py:288-289); in place allowed */
 int    cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmhar_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-attention fusion block (spec row A6 -- the reference has no fusion block; defined in
+ * fusion.py, oracle oracle/fusion_spec.py: self-consistency, not reference parity)
+ * ------------------------------------------------------------------------------------------ */
+/* q (n*s_len,128) = projected IMU tokens, kv (n*t_len,256) = [K | V] projected frame tokens ->
+ * out (n*s_len,128) = concat_h softmax(q_h k_h^T / 4) v_h, 8 heads of 16.  s_len <= 16, t_len <= 32. */
+int cmhar_cross_attention(const float* q, const float* kv, int64_t n, int32_t s_len, int32_t t_len,
+                          float* out, cmhar_stream_t s);
+/* pooled (n,128) = mean_s LayerNorm(x[n,s,:] + a[n,s,:]; gamma, beta, eps) */
+int cmhar_residual_ln_pool(const float* x, const float* a, const float* gamma, const float* beta,
+                           int64_t n, int32_t s_len, float eps, float* pooled, cmhar_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Video tail (replaces VideoEncoder.forward after the trunk, models.py:210-216:

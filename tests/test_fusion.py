@@ -1,0 +1,93 @@
+"""Fusion classifiers (SURVEY.md section 8a row A6 -- SPEC-DEFINED, the reference has no fusion block):
+late-fusion concat-MLP and cross-attention fusion against the in-repo spec ``oracle/fusion_spec.py``.
+CPU: the autograd route; GPU: the native kernels through the C ABI.  Self-consistency, not reference parity."""
+import numpy as np
+import pytest
+import torch
+
+import crossmodal_imu_video_ood_har_b200 as cm
+from oracle import fusion_spec, ood_spec, oracle, weights as W
+
+T = 16
+
+
+def tsd(sd):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+
+
+def build(kind, seed=41):
+    cfg = cm.default_config()
+    sd = fusion_spec.fusion_state(seed)
+    cls = cm.LateFusionClassifier if kind == "late" else cm.CrossAttentionFusionClassifier
+    model = cls(cm.IMUEncoder(cfg), cm.VideoEncoder(cfg), cfg)
+    own = set(model.state_dict().keys())
+    missing = own - set(sd.keys())
+    assert not missing, missing
+    model.load_state_dict({k: v for k, v in tsd(sd).items() if k in own}, strict=True)
+    return model.eval(), sd
+
+
+def inputs(B, seed=3):
+    return W.imu_windows(seed, B), W.video_feature_maps(seed + 1, B, T)
+
+
+@pytest.mark.parametrize("kind", ["late", "xattn"])
+def test_autograd_route_matches_spec(kind):
+    model, sd = build(kind)
+    imu, fmap = inputs(6)
+    spec = fusion_spec.late_fusion if kind == "late" else fusion_spec.cross_attention_fusion
+    want, _ = spec(imu, fmap, sd, T)
+    video = torch.from_numpy(fmap).view(6, T, *fmap.shape[1:])          # identity trunk: "video" = feature maps
+    got = model(torch.from_numpy(imu), video)
+    assert got.requires_grad
+    np.testing.assert_allclose(got.detach().numpy(), want.numpy(), atol=2e-4, rtol=0)
+    got.sum().backward()
+    assert model.imu_encoder.patch_embed.projections[0].weight.grad.abs().sum() > 0
+
+
+def test_native_route_refuses_cpu_tensors():
+    model, _ = build("late")
+    imu, fmap = inputs(2)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.from_numpy(imu), torch.from_numpy(fmap).view(2, T, *fmap.shape[1:]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["late", "xattn"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_native_fusion_matches_spec(kind, precision, tol):
+    model, sd = build(kind)
+    model = model.to("cuda:0")
+    B = 77
+    imu, fmap = inputs(B, 9)
+    f_dev = torch.from_numpy(fmap).to("cuda:0").to(torch.bfloat16)
+    f_r = f_dev.float().cpu().numpy()                       # the oracle sees the same bf16-rounded feature maps
+    spec = fusion_spec.late_fusion if kind == "late" else fusion_spec.cross_attention_fusion
+    want, want_f = spec(imu, f_r, sd, T, dtype=torch.float64)
+    feats, labels = W.class_features(7, 2000)
+    maha = cm.MahalanobisOOD(32, "cuda:0", ridge=1e-3).fit(torch.from_numpy(feats).cuda(), torch.from_numpy(labels).cuda())
+    model.set_mahalanobis(maha)
+    out = model.forward_scores(torch.from_numpy(imu).cuda(), f_dev, T, precision=precision)
+    torch.cuda.synchronize()
+    rel = lambda g, w: float(np.abs(g.detach().cpu().numpy().astype(np.float64) - w.numpy()).max() / np.abs(w.numpy()).max())
+    assert rel(out["fused"], want_f) < tol
+    assert rel(out["logits"], want) < tol
+    got_logits = out["logits"].cpu().numpy()
+    # scores are functions of the logits the kernel produced
+    np.testing.assert_array_equal(out["pred"].cpu().numpy(), got_logits.argmax(1))
+    np.testing.assert_allclose(out["energy"].cpu().numpy(), ood_spec.energy_score(got_logits), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(out["msp"].cpu().numpy(), ood_spec.msp_score(got_logits), rtol=1e-4, atol=1e-5)
+    if precision == "fp32":
+        assert np.array_equal(out["pred"].cpu().numpy(), oracle.predict(want))
+        st = ood_spec.mahalanobis_finalize(*ood_spec.mahalanobis_sufficient_stats(feats, labels, 32), ridge=1e-3)
+        want_m = ood_spec.mahalanobis_score(want_f.numpy(), st)
+        assert float(np.abs(out["maha"].cpu().numpy() - want_m).max() / np.abs(want_m).max()) < 5e-3
+    # the module's forward (video through the identity trunk) returns the same logits
+    with torch.no_grad():
+        cm.set_default_precision(precision)
+        try:
+            video = f_dev.view(B, T, *f_dev.shape[1:])
+            logits = model(torch.from_numpy(imu).cuda(), video)
+        finally:
+            cm.set_default_precision("fp32")
+    assert torch.equal(logits, out["logits"])

@@ -66,3 +66,34 @@ def test_pipeline_routes_agree_with_oracle(precision, tol):
     torch.cuda.synchronize()
     assert torch.equal(out["pred"], eager["pred"]) and torch.equal(out["logits"], eager["logits"])
     assert abs(float(out["loss"]) - float(eager["loss"])) < 1e-12
+
+
+def test_late_fusion_pipeline_matches_spec():
+    """configs[1]: the pass with the (spec-defined) late-fusion classifier scored instead of the IMU-only head."""
+    from oracle import fusion_spec
+    cfg = cm.default_config()
+    sd = fusion_spec.fusion_state(41)
+    sd_x = W.cross_modal_state(41)
+    xm = cm.CrossModalModel(cfg)
+    xm.load_state_dict(tsd(sd_x), strict=True)
+    clf = cm.IMUClassifier(xm.imu_encoder, cfg)
+    fus = cm.LateFusionClassifier(xm.imu_encoder, xm.video_encoder, cfg)
+    own = set(fus.state_dict().keys())
+    fus.load_state_dict({k: v for k, v in tsd(sd).items() if k in own}, strict=True)
+    xm, clf, fus = xm.to(DEV).eval(), clf.to(DEV).eval(), fus.to(DEV).eval()
+    B, T = 40, 16
+    imu = W.imu_windows(5, B)
+    f = torch.from_numpy(W.video_feature_maps(6, B, T)).to(DEV).to(torch.bfloat16)
+    pipe = cm.CrossModalOODPipeline(clf, xm, None, frames=T, precision="fp32", fusion=fus)
+    out = pipe.run(torch.from_numpy(imu).to(DEV), f)
+    torch.cuda.synchronize()
+    want, want_f = fusion_spec.late_fusion(imu, f.float().cpu().numpy(), sd, T, dtype=torch.float64)
+    rel = lambda g, w: float(np.abs(g.detach().cpu().numpy().astype(np.float64) - w.numpy()).max() / np.abs(w.numpy()).max())
+    assert rel(out["logits"], want) < 1e-3 and rel(out["fused"], want_f) < 1e-3
+    assert np.array_equal(out["pred"].cpu().numpy(), oracle.predict(want))
+    ip, vp = oracle.cross_modal(imu, f.float().cpu().numpy(), sd_x, T, dtype=torch.float64)
+    assert abs(float(out["loss"]) - float(oracle.sigmoid_contrastive_loss(ip, vp, dtype=torch.float64))) < 1e-3 * float(out["loss"])
+    graph, gout = pipe.capture(torch.from_numpy(imu).to(DEV), f)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(gout["logits"], out["logits"]) and torch.equal(gout["pred"], out["pred"])
