@@ -43,13 +43,14 @@ BYTES_VIDEO = FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2 + 768 * 4     # bf16 fmap 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--batch", type=int, default=256, help="windows per GPU per step (configs[1]: 256)")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--lanes", type=int, default=8, help="CUDA streams independent steps are pipelined over (1 = serial)")
     return ap.parse_args()
 
 
@@ -87,48 +88,57 @@ def synth_inputs(device, batch, n_sets, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML polled every ~2 ms from a thread;
+    `nvidia-smi -lms` is too coarse for a region of a few tens of milliseconds)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.mx, self._stop, self.t = index, [], set(), None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if i < len(ids) and ids[i].strip().isdigit():
+                return int(ids[i])
+        return i
+
+    def _poll(self):
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        while not self._stop:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in names:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        if self.nv is None:
+            return
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None or self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self._stop = True
+        self.t.join(timeout=1.0)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def measured_peaks():
@@ -278,7 +288,7 @@ def main():
 
     bytes_per_set = B * (6 * WINDOW * 4 + FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2)
     n_sets = max(2, -(-300_000_000 // bytes_per_set))           # rotate over > 2x L2 worth of inputs
-    n_sets = min(n_sets, 64)
+    n_sets = min(max(n_sets, args.lanes), 64)
     sets = synth_inputs(dev, B, n_sets, rank)
     graphs = [pipe.capture(imu, fmap) for imu, fmap in sets]
     l0 = cm._native.launch_count()
@@ -286,17 +296,45 @@ def main():
     launches_per_step = cm._native.launch_count() - l0
     stream = torch.cuda.current_stream(dev)
 
-    def run_steps(k, offset=0):
+    # Independent batches are pipelined over a few CUDA streams ("lanes"): a 256-window step is a ~20-launch
+    # dependency chain that keeps 32 of the 148 SMs busy, so back-to-back steps on ONE stream measure latency,
+    # not throughput.  Input set s (and the graph that owns its output buffers) always replays on lane
+    # s % n_lanes, so a graph never overlaps itself.  Every one of the K steps starts after e0 and ends before e1.
+    n_lanes = max(1, min(args.lanes, n_sets))
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
+    lane_done = [torch.cuda.Event() for _ in range(n_lanes)]
+
+    def run_steps(k, offset=0, pipelined=True):
+        if not pipelined or n_lanes == 1:
+            for i in range(k):
+                graphs[(offset + i) % n_sets][0].replay()
+            return
+        start = torch.cuda.Event()
+        start.record(stream)
+        for ln in lanes:
+            ln.wait_event(start)
         for i in range(k):
-            graphs[(offset + i) % n_sets][0].replay()
+            g = (offset + i) % n_sets
+            with torch.cuda.stream(lanes[g % n_lanes]):
+                graphs[g][0].replay()
+        for ln, ev in zip(lanes, lane_done):
+            ev.record(ln)
+            stream.wait_event(ev)
 
     # ---- device-resident throughput
     run_steps(max(args.warmup, 3))
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # latency of one step (single stream, back to back), reported beside the throughput
+    lat_steps = max(5, min(args.steps, 50))
+    e0.record(stream)
+    run_steps(lat_steps, pipelined=False)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    step_latency_ms = e0.elapsed_time(e1) / lat_steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     run_steps(args.steps, offset=args.warmup)
@@ -410,7 +448,8 @@ def main():
                 "config": {"workload": WORKLOAD.format(B=B),
                            "batch_per_gpu": B, "global_batch": B * world, "frames": FRAMES, "parallelism": f"dp{world} (windows sharded by rank, no collective)",
                            "l2_policy": f"inputs_larger_than_L2: {n_sets} rotating input sets, {n_sets * bytes_per_set / 1e6:.0f} MB",
-                           "cuda_graph": True},
+                           "cuda_graph": True, "lanes": n_lanes,
+                           "step_latency_ms": step_latency_ms},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "imu_only_value": e2e_imu, "note": "pinned host buffers; fmap H2D (262 KB/clip) dominates"},

@@ -29,17 +29,20 @@ namespace cmhar {
 namespace tc {
 
 constexpr int CHUNK = 16384;                 // bytes of one [128 x 64] bf16 SW128 chunk
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 6;
 constexpr int CHUNKS_PER_LAYER = 24;
 // roles: 4*NQ epilogue warps (NQ = column splits per row), then the MMA warp, then the weight producer
 
 // shared memory map (bytes)
+// Only the operands that MUST be in shared memory live there: h (A operand of QKV / FFN1 and the B operand of
+// the V^T GEMM) and K, V^T (B operands of the attention MMAs).  Q, P, O and the FFN hidden chunks are written
+// by the epilogue as bf16 straight back into TMEM, over the accumulator they were read from, and consumed as
+// TMEM A operands: no shared-memory store, no proxy fence, no operand read from shared memory for those GEMMs.
 constexpr int OFF_HA = 0;                    // h as bf16 A/B operand          [128 x 128]  2 chunks
-constexpr int OFF_Q = 32768;                 // Q (later O, hidden chunk 0)    [128 x 128]
-constexpr int OFF_K = 65536;                 // K (hidden chunk 1)
-constexpr int OFF_VT = 98304;                // V^T (hidden chunk 2)
-constexpr int OFF_P = 131072;                // parameter staging (static block | LN stats | per-layer blocks)
-constexpr int OFF_W = 163840;                // weight ring, NSTAGE chunks
+constexpr int OFF_K = 32768;                 // K
+constexpr int OFF_VT = 65536;                // V^T
+constexpr int OFF_P = 98304;                 // parameter staging (static block | LN stats | per-layer blocks)
+constexpr int OFF_W = 131072;                // weight ring, NSTAGE chunks
 constexpr int OFF_STAT = OFF_W + NSTAGE * CHUNK;   // LN partial stats [2][128] float2 = 2 KiB
 constexpr int OFF_BAR = OFF_STAT + 2048;     // mbarriers (8 B each) + tmem pointer
 constexpr int SMEM_BYTES = OFF_BAR + 256;
@@ -62,8 +65,7 @@ enum {
     B_P = B_QKV + 1,             // P (all heads) in smem                  (256)
     B_O = B_P + 1,               // O in smem                              (256)
     B_HID = B_O + 1,             // [4] hidden chunk c in smem (one barrier per chunk: a waiter may never fall two phases behind)
-    B_H0FREE = B_HID + 4,        // FFN2 k-chunk 0 done reading hidden chunk 0 (its buffer takes chunk 3)  (commit)
-    B_PBFULL = B_H0FREE + 1,     // [2] per-layer parameter block landed   (tx)
+    B_PBFULL = B_HID + 4,        // [2] per-layer parameter block landed   (tx)
     B_PBEMPTY = B_PBFULL + 2,    // [2] epilogue finished with the block   (epilogue warps)
     B_STATIC = B_PBEMPTY + 2,    // static parameter block landed          (tx)
     B_COUNT = B_STATIC + 1
@@ -71,7 +73,11 @@ enum {
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier area too small");
 
 constexpr uint32_t TM_A = 0, TM_B = 128, TM_C = 256, TM_R = 384;
-constexpr uint32_t TM_P = TM_B + 64;      // softmax probabilities, bf16 pairs: head h -> columns [8h, 8h+8)
+// bf16 A operands written back over the fp32 accumulator they came from: the epilogue thread that owns columns
+// [CW q, CW q + CW) of a 128-column buffer packs them into columns [CW q, CW q + CW/2) (two bf16 per column), so
+// element k of the row sits at column CW*(k/CW) + (k%CW)/2 and a K=16 MMA step reads 8 columns.
+template <int CW>
+__host__ __device__ constexpr uint32_t tm_bf16_col(int k) { return (uint32_t)(CW * (k / CW) + (k % CW) / 2); }
 
 struct Phase {       // parity bookkeeping: one bit per barrier index
     uint32_t bits = 0;
@@ -131,7 +137,6 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
         mbar_init(BAR(B_P), NT_EPI / 32);
         mbar_init(BAR(B_O), NT_EPI / 32);
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_HID + i), NT_EPI / 32);
-        mbar_init(BAR(B_H0FREE), 1);
         mbar_init(BAR(B_PBFULL), 1); mbar_init(BAR(B_PBFULL + 1), 1);
         mbar_init(BAR(B_PBEMPTY), NT_EPI / 32); mbar_init(BAR(B_PBEMPTY + 1), NT_EPI / 32);
         mbar_init(BAR(B_STATIC), 1);
@@ -180,8 +185,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
             Phase ph;
             uint32_t wstage = 0, wparity = 0;
             constexpr uint32_t ID128 = idesc_bf16(128, 128), ID16 = idesc_bf16(128, 16);
-            const uint64_t dHA = sw128_desc(sbase + OFF_HA), dQ = sw128_desc(sbase + OFF_Q), dK = sw128_desc(sbase + OFF_K),
-                           dVT = sw128_desc(sbase + OFF_VT), dP = sw128_desc(sbase + OFF_P);
+            const uint64_t dHA = sw128_desc(sbase + OFF_HA), dK = sw128_desc(sbase + OFF_K), dVT = sw128_desc(sbase + OFF_VT);
             // one weight chunk = 64 k-columns = 4 MMAs of K=16.  `w_is_a`: weights are the A operand.
             auto gemm_chunk = [&](uint32_t d, uint64_t other_desc, bool w_is_a, bool first_acc, int ksteps) {
                 mbar_wait(BAR(B_WFULL + wstage), wparity, 2);
@@ -191,6 +195,16 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     const uint64_t wa = dW + (uint64_t)(2 * k), oa = other_desc + (uint64_t)(2 * k);
                     if (leader && !(args.ablate & ABL_NO_DENSE_MMA)) umma(d, w_is_a ? wa : oa, w_is_a ? oa : wa, ID128, (first_acc || k > 0) ? 1u : 0u);
                 }
+                if (leader) tc_commit(BAR(B_WEMPTY + wstage));
+                if (++wstage == NSTAGE) { wstage = 0; wparity ^= 1; }
+            };
+            // same, activations as the A operand straight from TMEM: the chunk covers k in [64*kc, 64*kc+64)
+            auto gemm_chunk_ts = [&](uint32_t d, uint32_t a_buf, int kc) {
+                mbar_wait(BAR(B_WFULL + wstage), wparity, 2);
+                tc_fence_after();
+                const uint64_t dW = sw128_desc(sbase + OFF_W + wstage * CHUNK);
+                for (int k = 0; k < 4; ++k)
+                    if (leader && !(args.ablate & ABL_NO_DENSE_MMA)) umma_ts(d, a_buf + tm_bf16_col<CW>(64 * kc + 16 * k), dW + (uint64_t)(2 * k), ID128, 1u);
                 if (leader) tc_commit(BAR(B_WEMPTY + wstage));
                 if (++wstage == NSTAGE) { wstage = 0; wparity ^= 1; }
             };
@@ -225,10 +239,11 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
 #pragma unroll
                         for (int h = 0; h < H; ++h) {
                             const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)((h & 3) * 2);
-                            if (leader && !(args.ablate & ABL_NO_ATTN_MMA)) umma_rows16(tmem + TM_A + 16 * h, dQ + off, dK + off + (uint64_t)(j * 128), ID16, j);
+                            if (leader && !(args.ablate & ABL_NO_ATTN_MMA))
+                                umma_ts_rows16(tmem + TM_B + 16 * h, tmem + TM_A + tm_bf16_col<CW>(16 * h), dK + off + (uint64_t)(j * 128), ID16, j);
                         }
                     }
-                    if (leader) tc_commit(BAR(B_ACC + 0));
+                    if (leader) tc_commit(BAR(B_ACC + 1));
                     // O[r][16h + d] = sum_k P[r][16h + k] * V_h[key k of r's window][d]
                     PROG(6); mbar_wait(BAR(B_P), ph.next(B_P), 6); PROG(1006);
                     tc_fence_after();
@@ -237,14 +252,14 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                         const uint64_t koff = (uint64_t)(j >> 2) * CH + (uint64_t)((j & 3) * 2);
 #pragma unroll
                         for (int h = 0; h < H; ++h)
-                            if (leader && !(args.ablate & ABL_NO_ATTN_MMA)) umma_ts_rows16(tmem + TM_C + 16 * h, tmem + TM_P + 8 * h, dVT + koff + (uint64_t)(h * 128), ID16, j);
+                            if (leader && !(args.ablate & ABL_NO_ATTN_MMA)) umma_ts_rows16(tmem + TM_C + 16 * h, tmem + TM_B + tm_bf16_col<CW>(16 * h), dVT + koff + (uint64_t)(h * 128), ID16, j);
                     }
                     if (leader) tc_commit(BAR(B_ACC + 2));            // O complete
                     // ---- out-proj: R(h + b_o) += O * W_o^T
                     PROG(8); mbar_wait(BAR(B_O), ph.next(B_O), 8); PROG(1008);
                     tc_fence_after();
-                    gemm_chunk(tmem + TM_R, dQ, false, true, 4);
-                    gemm_chunk(tmem + TM_R, dQ + CH, false, true, 4);
+                    gemm_chunk_ts(tmem + TM_R, tmem + TM_C, 0);
+                    gemm_chunk_ts(tmem + TM_R, tmem + TM_C, 1);
                     if (leader) tc_commit(BAR(B_ACC + 3));
                     // ---- FFN: hidden chunk c -> buffers A,B,C,A ; R(h1 + b_2) += hidden_c * W_2[:,c]^T
                     PROG(9); mbar_wait(BAR(B_HA), ph.next(B_HA), 9); PROG(1009);
@@ -255,14 +270,14 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                         if (leader) tc_commit(BAR(B_ACC + c));
                     }
                     for (int c = 0; c < 4; ++c) {
-                        PROG(10); mbar_wait(BAR(B_HID + c), ph.next(B_HID + c), 10); PROG(1010);     // hidden chunk c in smem (and its TMEM buffer drained)
+                        PROG(10); mbar_wait(BAR(B_HID + c), ph.next(B_HID + c), 10); PROG(1010);     // hidden chunk c (bf16) back in its TMEM buffer
                         tc_fence_after();
-                        const uint64_t dHid = sw128_desc(sbase + OFF_Q + (c == 3 ? 0 : c) * 32768);   // chunk 3 lives in buffer 0
-                        gemm_chunk(tmem + TM_R, dHid, false, true, 4);
-                        gemm_chunk(tmem + TM_R, dHid + CH, false, true, 4);
+                        const uint32_t hid = tmem + 128 * (c == 3 ? 0 : c);                          // chunk 3 lives in buffer A
+                        gemm_chunk_ts(tmem + TM_R, hid, 0);
+                        gemm_chunk_ts(tmem + TM_R, hid, 1);
                         if (c == 0) {
-                            if (leader) tc_commit(BAR(B_H0FREE));      // hidden buffer 0 may take chunk 3
-                            // 4th FFN1 chunk reuses TMEM buffer A
+                            // 4th FFN1 chunk reuses TMEM buffer A: the tensor pipe executes MMAs in issue order, so these
+                            // overwrite the buffer only after FFN2's k-chunk 0 has read hidden chunk 0 from it
                             gemm_chunk(tmem + TM_A, dHA, false, false, 4);
                             gemm_chunk(tmem + TM_A, dHA + CH, false, true, 4);
                             if (leader) tc_commit(BAR(B_ACC + 0));
@@ -355,6 +370,19 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
             }
             epi_bar();          // stats buffer reusable
         };
+        // 32 finished fp32 values -> 16 columns of packed bf16 pairs in TMEM
+        auto store_tmem_bf16 = [&](uint32_t taddr, const float* y32) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(y32[2 * i], y32[2 * i + 1]);
+            TMEM_ST16(taddr, pk);
+        };
+        auto publish_tmem = [&](int bar_idx) {   // TMEM-only hand-off: no shared-memory proxy fence needed
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(bar_idx));
+        };
         auto publish = [&](int bar_idx) {   // make generic-proxy smem writes + TMEM accesses visible, then arrive
             tc_wait_st();
             fence_async_smem();
@@ -439,12 +467,12 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                 const float* PB = reinterpret_cast<const float*>(smem + OFF_PB + (l & 1) * PB_FLOATS * 4);
                 mbar_wait(BAR(B_PBFULL + (l & 1)), pb_parity[l & 1], 21);
                 pb_parity[l & 1] ^= 1;
-                // ---- drain Q, K (bias per column) and V^T (bias per lane) into smem as bf16
+                // ---- drain Q (+ bias) back into TMEM as bf16 (A operand of the score MMAs), K and V^T into smem
 #pragma unroll 1
                 for (int m = 0; m < 3; ++m) {
                     PROG(12); mbar_wait(BAR(B_ACC + m), ph.next(B_ACC + m), 12); PROG(1012);
                     tc_fence_after();
-                    uint8_t* dst = smem + OFF_Q + m * 32768;
+                    uint8_t* dst = smem + OFF_K + (m - 1) * 32768;
 #pragma unroll
                     for (int cc = 0; cc < CW; cc += 32) {
                         TMEM_LD32(lane_base + 128 * m + c0 + cc, v);
@@ -460,18 +488,19 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
 #pragma unroll
                             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                         }
-                        if (!(args.ablate & ABL_NO_STS)) store_bf16_32(dst + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
+                        if (m == 0) store_tmem_bf16(lane_base + TM_A + c0 + (cc >> 1), f);
+                        else if (!(args.ablate & ABL_NO_STS)) store_bf16_32(dst + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
                     }
                 }
                 PROG(100 + l);
                 publish(B_QKV);
                 // ---- softmax: this thread owns the heads whose 16 compact scores fall into its CW columns
-                PROG(13); mbar_wait(BAR(B_ACC + 0), ph.next(B_ACC + 0), 13); PROG(1013);
+                PROG(13); mbar_wait(BAR(B_ACC + 1), ph.next(B_ACC + 1), 13); PROG(1013);
                 tc_fence_after();
                 auto softmax_rows = [&](auto full_tag) {      // full_tag: seq == 16, no key masking needed
 #pragma unroll
                 for (int cc = 0; cc < CW; cc += 32) {
-                    TMEM_LD32(lane_base + TM_A + c0 + cc, v);
+                    TMEM_LD32(lane_base + TM_B + c0 + cc, v);
                     tc_wait_ld();
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
@@ -491,10 +520,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
 #pragma unroll
                         for (int i = 0; i < 16; ++i) f[hh * 16 + i] *= inv;
                     }
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
-                    TMEM_ST16(lane_base + TM_P + ((c0 + cc) >> 1), pk);
+                    store_tmem_bf16(lane_base + TM_B + c0 + (cc >> 1), f);       // P over the scores it came from
                 }
                 };
                 if (S == CMHAR_MAX_SEQ) softmax_rows(std::true_type{});
@@ -504,7 +530,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_P));
                 PROG(14);
-                // ---- O (buffer C) -> smem (Q region) as bf16
+                // ---- O (buffer C) -> bf16 back into buffer C (A operand of the out-projection)
                 PROG(15); mbar_wait(BAR(B_ACC + 2), ph.next(B_ACC + 2), 15); PROG(1015);
                 tc_fence_after();
 #pragma unroll
@@ -513,9 +539,9 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     tc_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    if (!(args.ablate & ABL_NO_STS)) store_bf16_32(smem + OFF_Q + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
+                    store_tmem_bf16(lane_base + TM_C + c0 + (cc >> 1), f);
                 }
-                publish(B_O);
+                publish_tmem(B_O);
                 PROG(150);
                 // ---- LN1: h1 = LN(R) ; hA = bf16(h1) ; R = h1 + b_2
                 PROG(16); mbar_wait(BAR(B_ACC + 3), ph.next(B_ACC + 3), 16); PROG(1016);
@@ -531,7 +557,6 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     PROG(17); mbar_wait(BAR(B_ACC + buf), ph.next(B_ACC + buf), 17); PROG(1017);
                     PROG(170 + c);
                     tc_fence_after();
-                    if (c == 3) mbar_wait(BAR(B_H0FREE), ph.next(B_H0FREE), 22);     // FFN2 k-chunk 0 finished with buffer 0
 #pragma unroll
                     for (int cc = 0; cc < CW; cc += 32) {
                         TMEM_LD32(lane_base + 128 * buf + c0 + cc, v);
@@ -542,10 +567,10 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                             f[i] = fmaxf(__uint_as_float(v[i]) + b.x, 0.f); f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
                             f[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f); f[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
                         }
-                        if (!(args.ablate & ABL_NO_STS)) store_bf16_32(smem + OFF_Q + (c == 3 ? 0 : c) * 32768 + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
+                        store_tmem_bf16(lane_base + 128 * buf + c0 + (cc >> 1), f);      // hidden chunk over its own accumulator
                     }
                     PROG(180 + c);
-                    publish(B_HID + c);
+                    publish_tmem(B_HID + c);
                     PROG(190 + c);
                 }
                 // ---- LN2: h2 = LN(R) ; hA = bf16(h2) ; R = h2 + b_o(next layer)

@@ -67,6 +67,17 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t 
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T : A from tensor memory (lane = row, one 32-bit column = two consecutive
+// bf16 k elements, a K=16 step reads 8 columns), B K-major SWIZZLE_128B in shared memory
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
 // same, but only the 16 TMEM lanes [16*win, 16*win+16) are written (disable-output-lane mask)
 __device__ __forceinline__ void umma_rows16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int win) {
     const uint32_t hole = ~(0xFFFFu << ((win & 1) * 16));      // no array indexing: keeps the mask in registers
