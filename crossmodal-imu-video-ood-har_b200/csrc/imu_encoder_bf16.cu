@@ -52,8 +52,8 @@ static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB");
 // on the critical path).  Static block: once per CTA.  Per-layer block: double buffered.
 constexpr int SB_TOK = 0, SB_FLN = 2048, SB_BO0 = 2304, SB_FLOATS = 2432;              // tok_bias | final LN g,b | bo_fold[0]
 constexpr int PB_BQ = 0, PB_B1 = 128, PB_B2 = 640, PB_LN1 = 768, PB_LN2 = 1024, PB_BON = 1280, PB_FLOATS = 1408;
-constexpr int OFF_SB = OFF_P, OFF_LNSTAT = OFF_P + 10240, OFF_PB = OFF_P + 16384;
-static_assert(SB_FLOATS * 4 <= 10240 && OFF_PB + 2 * PB_FLOATS * 4 <= OFF_P + 32768, "parameter staging overflows the P region");
+constexpr int OFF_SB = OFF_P, OFF_LNSTAT = OFF_P + 10240, OFF_PB = OFF_P + 18432;     // LN stats: 2 x [NQ <= 4][128] float2 = 8 KiB
+static_assert(SB_FLOATS * 4 <= 10240 && OFF_LNSTAT + 8192 <= OFF_PB && OFF_PB + 2 * PB_FLOATS * 4 <= OFF_P + 32768, "parameter staging overflows the P region");
 
 // barrier indices
 enum {
@@ -302,7 +302,13 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
         auto piece_of = [](int c) { return (c & 63) >> 3; };
         Phase ph;
         uint32_t v[32];
+        uint32_t vv[CW];     // this thread's CW-column slice of an accumulator: all its TMEM loads in flight before one wait
         float f[32];
+        auto load_slice = [&](uint32_t taddr) {
+#pragma unroll
+            for (int cc = 0; cc < CW; cc += 32) TMEM_LD32(taddr + cc, (vv + cc));
+            tc_wait_ld();
+        };
 
         auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };   // warp-uniform smem broadcast
         // finish a 128-wide fp32 row held in R: y -> hA (bf16), y + next_bias -> R
@@ -316,51 +322,41 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
             }
             TMEM_ST32(lane_base + TM_R + c0 + cc, v);
         };
-        // LayerNorm of the residual row in R (two threads per row exchange partial sums through smem)
+        // LayerNorm of the residual row in R.  The row's CW-column slices are owned by NQ threads of different
+        // warps (same lane quarter), which exchange partial sums through smem and a named barrier of just those
+        // warps.  The slice stays in registers between the statistics and the normalisation (one TMEM read).
+        uint32_t ln_flip = 0;           // alternates the statistics buffer so one barrier per LayerNorm suffices
+        auto quarter_bar = [&] { asm volatile("bar.sync %0, %1;" ::"r"(2 + (warp & 3)), "n"(32 * NQ) : "memory"); };
         auto layer_norm_R = [&](const float* gb, const float* next_bias, bool write_back, float* keep /*CW floats or null*/) {
-            float s1 = 0.f, s2 = 0.f;
-            if (args.ablate & ABL_NO_LN) {
+            uint32_t x[CW];
 #pragma unroll
-                for (int cc = 0; cc < CW; cc += 32) {
-                    TMEM_LD32(lane_base + TM_R + c0 + cc, v);
-                    tc_wait_ld();
+            for (int cc = 0; cc < CW; cc += 32) TMEM_LD32(lane_base + TM_R + c0 + cc, (x + cc));
+            tc_wait_ld();
+            float mean = 0.f, rstd = 1.f;
+            if (!(args.ablate & ABL_NO_LN)) {
+                float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    if (keep) {
+                for (int i = 0; i < CW; ++i) { const float xv = __uint_as_float(x[i]); s1 += xv; s2 = fmaf(xv, xv, s2); }
+                float2* st = stats + ln_flip * (NQ * 128);
+                ln_flip ^= 1;
+                st[wq * 128 + row] = make_float2(s1, s2);
+                quarter_bar();
+                float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) keep[cc + i] = f[i];
-                    }
-                    if (write_back) write_h(f, cc, next_bias);
-                }
-                return;
+                for (int q = 0; q < NQ; ++q) { const float2 o = st[q * 128 + row]; t1 += o.x; t2 += o.y; }
+                mean = t1 * (1.f / D);
+                rstd = rsqrtf(fmaxf(t2 * (1.f / D) - mean * mean, 0.f) + LN_EPS);
             }
 #pragma unroll
             for (int cc = 0; cc < CW; cc += 32) {
-                TMEM_LD32(lane_base + TM_R + c0 + cc, v);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { const float x = __uint_as_float(v[i]); s1 += x; s2 = fmaf(x, x, s2); }
-            }
-            stats[wq * 128 + row] = make_float2(s1, s2);
-            epi_bar();
-            float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) { const float2 o = stats[q * 128 + row]; t1 += o.x; t2 += o.y; }
-            const float mean = t1 * (1.f / D);
-            const float var = fmaxf(t2 * (1.f / D) - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + LN_EPS);
-#pragma unroll
-            for (int cc = 0; cc < CW; cc += 32) {
-                TMEM_LD32(lane_base + TM_R + c0 + cc, v);
-                tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 g = ld4(gb + c0 + cc + i);
                     const float4 b = ld4(gb + D + c0 + cc + i);
-                    f[i] = (__uint_as_float(v[i]) - mean) * rstd * g.x + b.x;
-                    f[i + 1] = (__uint_as_float(v[i + 1]) - mean) * rstd * g.y + b.y;
-                    f[i + 2] = (__uint_as_float(v[i + 2]) - mean) * rstd * g.z + b.z;
-                    f[i + 3] = (__uint_as_float(v[i + 3]) - mean) * rstd * g.w + b.w;
+                    f[i] = (__uint_as_float(x[cc + i]) - mean) * rstd * g.x + b.x;
+                    f[i + 1] = (__uint_as_float(x[cc + i + 1]) - mean) * rstd * g.y + b.y;
+                    f[i + 2] = (__uint_as_float(x[cc + i + 2]) - mean) * rstd * g.z + b.z;
+                    f[i + 3] = (__uint_as_float(x[cc + i + 3]) - mean) * rstd * g.w + b.w;
                 }
                 if (keep) {
 #pragma unroll
@@ -368,7 +364,6 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                 }
                 if (write_back) write_h(f, cc, next_bias);
             }
-            epi_bar();          // stats buffer reusable
         };
         // 32 finished fp32 values -> 16 columns of packed bf16 pairs in TMEM
         auto store_tmem_bf16 = [&](uint32_t taddr, const float* y32) {
@@ -473,20 +468,19 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     PROG(12); mbar_wait(BAR(B_ACC + m), ph.next(B_ACC + m), 12); PROG(1012);
                     tc_fence_after();
                     uint8_t* dst = smem + OFF_K + (m - 1) * 32768;
+                    load_slice(lane_base + 128 * m + c0);
 #pragma unroll
                     for (int cc = 0; cc < CW; cc += 32) {
-                        TMEM_LD32(lane_base + 128 * m + c0 + cc, v);
-                        tc_wait_ld();
                         if (m == 0) {     // q bias (pre-scaled); the k bias cancels in the softmax, the v bias is folded into b_o
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
                                 const float4 b = ld4(PB + PB_BQ + c0 + cc + i);
-                                f[i] = __uint_as_float(v[i]) + b.x; f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
-                                f[i + 2] = __uint_as_float(v[i + 2]) + b.z; f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+                                f[i] = __uint_as_float(vv[cc + i]) + b.x; f[i + 1] = __uint_as_float(vv[cc + i + 1]) + b.y;
+                                f[i + 2] = __uint_as_float(vv[cc + i + 2]) + b.z; f[i + 3] = __uint_as_float(vv[cc + i + 3]) + b.w;
                             }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(vv[cc + i]);
                         }
                         if (m == 0) store_tmem_bf16(lane_base + TM_A + c0 + (cc >> 1), f);
                         else if (!(args.ablate & ABL_NO_STS)) store_bf16_32(dst + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
@@ -497,11 +491,11 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                 // ---- softmax: this thread owns the heads whose 16 compact scores fall into its CW columns
                 PROG(13); mbar_wait(BAR(B_ACC + 1), ph.next(B_ACC + 1), 13); PROG(1013);
                 tc_fence_after();
+                load_slice(lane_base + TM_B + c0);
                 auto softmax_rows = [&](auto full_tag) {      // full_tag: seq == 16, no key masking needed
 #pragma unroll
                 for (int cc = 0; cc < CW; cc += 32) {
-                    TMEM_LD32(lane_base + TM_B + c0 + cc, v);
-                    tc_wait_ld();
+                    const uint32_t* v = vv + cc;
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         if (args.ablate & ABL_NO_SOFTMAX) { for (int i = 0; i < 16; ++i) f[hh * 16 + i] = __uint_as_float(v[hh * 16 + i]); continue; }
@@ -533,12 +527,11 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                 // ---- O (buffer C) -> bf16 back into buffer C (A operand of the out-projection)
                 PROG(15); mbar_wait(BAR(B_ACC + 2), ph.next(B_ACC + 2), 15); PROG(1015);
                 tc_fence_after();
+                load_slice(lane_base + TM_C + c0);
 #pragma unroll
                 for (int cc = 0; cc < CW; cc += 32) {
-                    TMEM_LD32(lane_base + TM_C + c0 + cc, v);
-                    tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(vv[cc + i]);
                     store_tmem_bf16(lane_base + TM_C + c0 + (cc >> 1), f);
                 }
                 publish_tmem(B_O);
@@ -557,15 +550,14 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     PROG(17); mbar_wait(BAR(B_ACC + buf), ph.next(B_ACC + buf), 17); PROG(1017);
                     PROG(170 + c);
                     tc_fence_after();
+                    load_slice(lane_base + 128 * buf + c0);
 #pragma unroll
                     for (int cc = 0; cc < CW; cc += 32) {
-                        TMEM_LD32(lane_base + 128 * buf + c0 + cc, v);
-                        tc_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 b = ld4(PB + PB_B1 + c * 128 + c0 + cc + i);
-                            f[i] = fmaxf(__uint_as_float(v[i]) + b.x, 0.f); f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
-                            f[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f); f[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
+                            f[i] = fmaxf(__uint_as_float(vv[cc + i]) + b.x, 0.f); f[i + 1] = fmaxf(__uint_as_float(vv[cc + i + 1]) + b.y, 0.f);
+                            f[i + 2] = fmaxf(__uint_as_float(vv[cc + i + 2]) + b.z, 0.f); f[i + 3] = fmaxf(__uint_as_float(vv[cc + i + 3]) + b.w, 0.f);
                         }
                         store_tmem_bf16(lane_base + 128 * buf + c0 + (cc >> 1), f);      // hidden chunk over its own accumulator
                     }
@@ -589,11 +581,13 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                     for (int i = 0; i < CW; ++i) { s1 += y[i]; s2 = fmaf(y[i], y[i], s2); }
-                    stats[wq * 128 + row] = make_float2(s1, s2);
-                    epi_bar();
+                    float2* st = stats + ln_flip * (NQ * 128);
+                    ln_flip ^= 1;
+                    st[wq * 128 + row] = make_float2(s1, s2);
+                    quarter_bar();
                     float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) { const float2 o = stats[q * 128 + row]; t1 += o.x; t2 += o.y; }
+                    for (int q = 0; q < NQ; ++q) { const float2 o = st[q * 128 + row]; t1 += o.x; t2 += o.y; }
                     const float mean = t1 * (1.f / D);
                     const float rstd = rsqrtf(fmaxf(t2 * (1.f / D) - mean * mean, 0.f) + LN_EPS);
                     const float* gb = SB + SB_FLN;

@@ -167,6 +167,67 @@ __global__ void __launch_bounds__(160, 1) bench(long long* out) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// ---- weight-ring test with a real TMA producer: producer lane issues 16 KiB cp.async.bulk copies from an
+// L2-resident buffer into an NS-stage ring; the MMA warp waits, issues 4 MMAs (SS or TS), commits the stage.
+template <int NS, bool TS>
+__global__ void __launch_bounds__(96, 1) ring_bench(const uint8_t* __restrict__ wsrc, int n_src_chunks, long long* out, int slot) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[32];
+    __shared__ uint32_t tslot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    const uint32_t b0 = smem_u32(bars);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 32; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b0 + 8 * i), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) { asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512)); asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = tslot;
+    const uint32_t sb = smem_u32(smem);
+    const uint64_t dA = sw128_desc(sb);
+    constexpr int NCH = 256;
+    if (warp == 0) {
+        const bool leader = elect_one();
+        uint32_t stage = 0, parity = 0;
+        long long t0 = clock64();
+        for (int c = 0; c < NCH; ++c) {
+            wait(b0 + 8 * stage, parity);
+            fence_after();
+            const uint64_t dW = sw128_desc(sb + 65536 + stage * 16384);
+            if (leader) {
+                for (int k = 0; k < 4; ++k) {
+                    if (TS) mma_ts(tmem, tmem + 448 + 8 * k, dW + (uint64_t)(2 * k), idesc(128, 128), 1);
+                    else mma_ss(tmem, dA + (uint64_t)(2 * k), dW + (uint64_t)(2 * k), idesc(128, 128), 1);
+                }
+                commit(b0 + 8 * (8 + stage));
+            }
+            if (++stage == NS) { stage = 0; parity ^= 1; }
+        }
+        __syncwarp();
+        long long t1 = clock64();
+        if (leader) commit(b0 + 8 * 31);
+        wait(b0 + 8 * 31, 0);
+        long long t2 = clock64();
+        if (lane == 0) { out[2 * slot] = (t1 - t0); out[2 * slot + 1] = (t2 - t0); }
+    } else if (warp == 1 && lane == 0) {
+        uint32_t stage = 0, parity = 1;
+        for (int c = 0; c < NCH; ++c) {
+            wait(b0 + 8 * (8 + stage), parity);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b0 + 8 * stage), "r"(16384) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sb + 65536 + stage * 16384), "l"(wsrc + (size_t)(c % n_src_chunks) * 16384), "r"(16384), "r"(b0 + 8 * stage) : "memory");
+            if (++stage == NS) { stage = 0; parity ^= 1; }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 int main() {
     long long* d; cudaMalloc(&d, 64 * sizeof(long long));
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
@@ -176,5 +237,21 @@ int main() {
     for (int rep = 0; rep < 2; ++rep) { bench<<<1, 160, 196608>>>(d); cudaError_t e = cudaDeviceSynchronize(); if (e) { printf("err %s\n", cudaGetErrorString(e)); return 1; } }
     long long h[64]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     for (int t = 0; t < 14; ++t) printf("%-26s issue %7.1f cyc/op   issue+complete %7.1f cyc/op\n", names[t], h[2 * t] / (double)REP, h[2 * t + 1] / (double)REP);
+    // TMA-fed ring: one CTA, then 148 CTAs (all SMs streaming the same 1.5 MB from L2)
+    uint8_t* w; cudaMalloc(&w, 96 * 16384); cudaMemset(w, 0x3c, 96 * 16384);
+    auto run = [&](auto kern, int smem_bytes, int grid, const char* name) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        for (int rep = 0; rep < 2; ++rep) { kern<<<grid, 96, smem_bytes>>>(w, 96, d, 20); cudaError_t e = cudaDeviceSynchronize(); if (e) { printf("err %s\n", cudaGetErrorString(e)); return; } }
+        long long r[2]; cudaMemcpy(r, d + 40, sizeof(r), cudaMemcpyDeviceToHost);
+        printf("%-44s grid %3d: %6.1f cyc/chunk (4 MMAs)  drained %6.1f\n", name, grid, r[0] / 256.0, r[1] / 256.0);
+    };
+    for (int grid : {1, 148}) {
+        run(ring_bench<4, false>, 65536 + 4 * 16384, grid, "TMA ring 4 stages, SS (A,B from smem)");
+        run(ring_bench<6, false>, 65536 + 6 * 16384, grid, "TMA ring 6 stages, SS");
+        run(ring_bench<8, false>, 65536 + 8 * 16384, grid, "TMA ring 8 stages, SS");
+        run(ring_bench<4, true>, 65536 + 4 * 16384, grid, "TMA ring 4 stages, TS (A from TMEM)");
+        run(ring_bench<6, true>, 65536 + 6 * 16384, grid, "TMA ring 6 stages, TS");
+        run(ring_bench<8, true>, 65536 + 8 * 16384, grid, "TMA ring 8 stages, TS");
+    }
     return 0;
 }
