@@ -83,7 +83,7 @@ _SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "cmhar_video_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]),
-    "cmhar_similarity_work_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "cmhar_similarity_work_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "cmhar_similarity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
                                    C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -9,6 +9,7 @@ namespace cmhar { struct FwdArgs; }
 #include "head.cu"
 #include "dense.cu"
 #include "similarity.cu"
+#include "similarity_tc.cu"
 #include "fusion.cu"
 #include "ood.cu"
 #include "api.cu"

@@ -165,15 +165,30 @@ __global__ void lse_merge_kernel(const float2* __restrict__ part, long long n, i
     lse[i] = m + logf(s);
 }
 
+int launch_lse_merge(const float2* part, long long n, int parts, float* lse, cudaStream_t st) {
+    lse_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, n, parts, lse);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+size_t similarity_tc_work_bytes(long long na, long long nb, int dim);                                   // similarity_tc.cu
+int launch_similarity_tc(const float* a, const float* b, long long na, long long nb, int dim, long long diag_offset,
+                         float* sim_out, float sig_scale, float sig_bias, double* sigmoid_sum_out, float lse_scale,
+                         float* row_lse_out, float* col_lse_out, float* diag_out, void* work, cudaStream_t st);
+
+static bool tc_eligible(int64_t na, int64_t nb, int32_t dim) { return dim % 64 == 0 && dim <= 256 && na >= 1 && nb >= 1; }
+
 }  // namespace cmhar
 
 using namespace cmhar;
 
 extern "C" {
 
-size_t cmhar_similarity_work_bytes(int64_t na, int64_t nb) {
+size_t cmhar_similarity_work_bytes(int64_t na, int64_t nb, int32_t dim) {
     const int64_t rt = (na + ST - 1) / ST, ct = (nb + ST - 1) / ST;
-    return (size_t)(ct * na + rt * nb) * sizeof(float2) + 256;
+    const size_t fp32_path = (size_t)(ct * na + rt * nb) * sizeof(float2) + 256;
+    const size_t tc_path = tc_eligible(na, nb, dim) ? similarity_tc_work_bytes(na, nb, dim) : 0;
+    return fp32_path > tc_path ? fp32_path : tc_path;
 }
 
 int cmhar_similarity(const float* a, const float* b, int64_t na, int64_t nb, int32_t dim, int64_t diag_offset,
@@ -185,6 +200,10 @@ int cmhar_similarity(const float* a, const float* b, int64_t na, int64_t nb, int
     CMHAR_REQUIRE(!(row_lse_out || col_lse_out) || work, "row/col logsumexp outputs need the work buffer");
     if (na <= 0 || nb <= 0) return CMHAR_OK;
     cudaStream_t st = (cudaStream_t)s;
+    // bf16 tensor-core path (needs the workspace for the bf16 operand images)
+    if (precision == CMHAR_BF16 && work && tc_eligible(na, nb, dim))
+        return launch_similarity_tc(a, b, na, nb, dim, diag_offset, sim_out, sig_scale, sig_bias, sigmoid_sum_out, lse_scale,
+                                    row_lse_out, col_lse_out, diag_out, work, st);
     const long long rt = (na + ST - 1) / ST, ct = (nb + ST - 1) / ST;
     CMHAR_REQUIRE(rt <= 65535, "too many row tiles");
     SimArgs p{};

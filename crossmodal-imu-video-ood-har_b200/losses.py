@@ -37,7 +37,8 @@ def similarity_native(a: torch.Tensor, b: torch.Tensor, *, materialize: bool = F
         row = torch.empty(na, dtype=torch.float32, device=dev)
         col = torch.empty(nb, dtype=torch.float32, device=dev)
         diag = torch.zeros(na, dtype=torch.float32, device=dev)
-        work = torch.empty(lib.cmhar_similarity_work_bytes(na, nb), dtype=torch.uint8, device=dev)
+    if lse_scale is not None or _prec_code(precision) == N.BF16:     # the bf16 tensor-core path stages operand images there
+        work = torch.empty(lib.cmhar_similarity_work_bytes(na, nb, dim), dtype=torch.uint8, device=dev)
     sc, sb = sigmoid if sigmoid is not None else (1.0, 0.0)
     with torch.cuda.device(dev):
         N.check(lib.cmhar_similarity(a.data_ptr(), b.data_ptr(), na, nb, dim, diag_offset, N.ptr(sim),

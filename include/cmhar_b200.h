@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CMHAR_ABI_VERSION 1
+#define CMHAR_ABI_VERSION 2
 
 #define CMHAR_OK               0
 #define CMHAR_ERR_INVALID     -1   /* bad argument / unsupported shape                       */
@@ -201,8 +201,11 @@ int cmhar_video_pool(const void* fmap, int32_t fmap_is_bf16, int64_t n, int32_t 
  * row_lse_out (na) / col_lse_out (nb): logsumexp over the row / column of sim*lse_scale; the
  * column reduction is accumulated as (max, sumexp) pairs in col_work (2*nb floats per row-tile
  * group, see cmhar_similarity_work_bytes) and finished by the same call.
- * diag_out (min(na,nb)) = sim_ii * lse_scale.   Any of the outputs may be NULL. */
-size_t cmhar_similarity_work_bytes(int64_t na, int64_t nb);
+ * diag_out (min(na,nb)) = sim_ii * lse_scale.   Any of the outputs may be NULL.
+ * precision CMHAR_BF16 with a workspace and dim % 64 == 0, dim <= 256: the 128x128 tiles run on the tensor
+ * cores (tcgen05, bf16 operands converted once into the workspace, fp32 accumulation in TMEM; column
+ * statistics come from a second pass over the transposed tiles).  Otherwise fp32 CUDA-core tiles. */
+size_t cmhar_similarity_work_bytes(int64_t na, int64_t nb, int32_t dim);
 int cmhar_similarity(const float* a, const float* b, int64_t na, int64_t nb, int32_t dim,
                      int64_t diag_offset /* column index of row 0's positive (sharded rows) */,
                      float* sim_out, float sig_scale, float sig_bias, double* sigmoid_sum_out,

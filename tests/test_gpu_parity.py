@@ -331,3 +331,57 @@ def test_cuda_graph_capture_of_fused_forward():
     gr.replay()
     torch.cuda.synchronize()
     assert torch.equal(out["logits"], eager["logits"]) and torch.equal(out["pred"], eager["pred"])
+
+
+@pytest.mark.parametrize("na,nb", [(48, 48), (200, 333), (1024, 640)])
+def test_similarity_bf16_tensor_core_path(na, nb):
+    """tcgen05 path (precision='bf16'): against the float64 oracle within the bf16 contract, ragged shapes
+    (zero-padded tiles are masked out of every reduction), sharded rows (diag_offset)."""
+    g = torch.Generator(device=DEV).manual_seed(na * 7 + nb)
+    a = torch.nn.functional.normalize(torch.randn(na, 256, device=DEV, generator=g), dim=1)
+    b = torch.nn.functional.normalize(torch.randn(nb, 256, device=DEV, generator=g), dim=1)
+    r = cm.similarity_native(a, b, materialize=True, sigmoid=(10.0, -10.0), lse_scale=1 / 0.07, precision="bf16")
+    want = a.double() @ b.double().T
+    assert rel_err(r["sim"], want) < TOL["bf16"]
+    # the reductions are functions of the matrix the kernel produced (fp32 accumulators of bf16 products)
+    sim = r["sim"].double()
+    sp = torch.nn.functional.softplus(-(sim * 10 - 10)).sum()
+    assert abs(float(r["sigmoid_sum"]) - float(sp)) < 2e-5 * float(sp)
+    assert torch.allclose(r["row_lse"].double(), torch.logsumexp(sim / 0.07, 1), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(r["col_lse"].double(), torch.logsumexp(sim / 0.07, 0), rtol=1e-4, atol=1e-4)
+    n = min(na, nb)
+    assert torch.allclose(r["diag"][:n].double(), torch.diagonal(sim)[:n] / 0.07, rtol=1e-5, atol=1e-5)
+    # against the oracle's loss values
+    want_sig = torch.nn.functional.softplus(-(want * 10 - 10)).mean()
+    assert abs(float(r["sigmoid_sum"]) / (na * nb) - float(want_sig)) < TOL["bf16"] * float(want_sig)
+    # row shards with a diagonal offset reproduce the full result
+    lo = na // 3
+    part = cm.similarity_native(a[lo:], b, sigmoid=(10.0, -10.0), lse_scale=1 / 0.07, diag_offset=lo, precision="bf16")
+    assert torch.allclose(part["row_lse"], r["row_lse"][lo:], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(part["diag"][:max(0, n - lo)], r["diag"][lo:n], rtol=1e-6, atol=1e-6)
+
+
+def test_similarity_bf16_full_size_properties():
+    """config 3 size (4096 x 4096 x 256) through the tensor-core path: fused reductions == reductions of the
+    materialised matrix, and the timing of both paths (information)."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    e = torch.nn.functional.normalize(torch.randn(4096, 256, device=DEV, generator=g), dim=1)
+    v = torch.nn.functional.normalize(torch.randn(4096, 256, device=DEV, generator=g), dim=1)
+    r = cm.similarity_native(e, v, materialize=True, sigmoid=(10.0, -10.0), lse_scale=1 / 0.07, precision="bf16")
+    sim = r["sim"].double()
+    want = torch.nn.functional.softplus(-(sim * 10 - 10)).sum()
+    assert abs(float(r["sigmoid_sum"]) - float(want)) < 2e-5 * float(want)
+    assert torch.allclose(r["row_lse"].double(), torch.logsumexp(sim / 0.07, 1), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(r["col_lse"].double(), torch.logsumexp(sim / 0.07, 0), rtol=1e-4, atol=1e-4)
+    assert rel_err(r["sim"], e.double() @ v.double().T) < TOL["bf16"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for prec in ("fp32", "bf16"):
+        cm.similarity_native(e, v, sigmoid=(10.0, -10.0), precision=prec)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(10):
+            cm.similarity_native(e, v, sigmoid=(10.0, -10.0), precision=prec)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 10
+        print(f"similarity 4096x4096x256 fused sigmoid loss, {prec}: {ms * 1e3:.1f} us  ({2 * 4096 * 4096 * 256 / ms / 1e9:.1f} TFLOP/s)")
