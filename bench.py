@@ -383,17 +383,18 @@ def main():
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the region
     imu_host = sets[0][0].cpu().pin_memory()
     fmap_host = sets[0][1].cpu().pin_memory()
-    e2e_steps = max(5, min(args.steps, 50))
-    for _ in range(3):
-        pipe.run_host(imu_host, fmap_host)
+    e2e_steps = max(5, min(args.steps, 100))
+    # streaming evaluator loop: batch i+1's H2D overlaps batch i's kernels; every batch pays its own H2D + D2H
+    for _ in pipe.stream_host((imu_host, fmap_host) for _ in range(3)):
+        pass
     barrier()
     t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        pipe.run_host(imu_host, fmap_host)
-    e1.record(stream)
+    checksum = 0
+    for res in pipe.stream_host((imu_host, fmap_host) for _ in range(e2e_steps)):
+        checksum += int(res["pred"][0])                   # results are consumed on the host
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3             # host wall clock: includes staging, launches and syncs
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
     t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -404,12 +405,11 @@ def main():
     for _ in range(3):
         pipe_imu.run_host(imu_host, None)
     torch.cuda.synchronize(dev)
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        pipe_imu.run_host(imu_host, None)
-    e1.record(stream)
+    t0 = time.perf_counter()
+    for res in pipe_imu.stream_host((imu_host, None) for _ in range(e2e_steps)):
+        checksum += int(res["pred"][0])
     torch.cuda.synchronize(dev)
-    e2e_imu = B * e2e_steps / (e0.elapsed_time(e1) * 1e-3)
+    e2e_imu = B * e2e_steps / (time.perf_counter() - t0)
 
     # ---- batch sweep of the fused IMU launch (information only; rank 0)
     sweep = {}
@@ -452,7 +452,8 @@ def main():
                            "step_latency_ms": step_latency_ms},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "imu_only_value": e2e_imu, "note": "pinned host buffers; fmap H2D (262 KB/clip) dominates"},
+                        "imu_only_value": e2e_imu, "api": "CrossModalOODPipeline.stream_host (2-deep ring, host wall clock)",
+                        "note": "pinned host buffers; fmap H2D (262 KB/clip) is the PCIe-bound term"},
                 "gpu_launches": launches_per_step * args.steps,
                 "launches_per_step": launches_per_step,
                 "roofline": roofline, "roofline_video_tail": roofline_video,

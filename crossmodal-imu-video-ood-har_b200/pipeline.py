@@ -16,7 +16,7 @@ throughput benchmark replays.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict, Iterable, List, Optional
 
 import torch
 
@@ -141,6 +141,74 @@ class CrossModalOODPipeline:
         if "loss" in out:
             res["loss"] = h["loss_pin"]
         return res
+
+    @torch.no_grad()
+    def stream_host(self, batches: Iterable, depth: int = 2):
+        """Streaming form of ``run_host`` for a sequence of HOST batches ``(imu_host, fmap_host)``: the
+        host->device copy of batch i+1 (copy engine, its own stream) overlaps the kernels of batch i, the
+        per-window results of every batch are copied back to pinned memory, and the generator yields them in
+        order -- what an evaluator loop over a DataLoader does (reference src/eval/evaluator.py:40-49, with
+        the per-batch ``.cpu()`` sync replaced by a ``depth``-deep ring).  Every batch still pays its own
+        H2D and D2H; only their latency is hidden."""
+        dev = next(self.clf.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(device=dev)
+        slots: List[dict] = []
+        pending: List[dict] = []
+
+        def finish(sl):
+            sl["done"].synchronize()
+            return sl["res"]
+
+        for i, (imu_host, fmap_host) in enumerate(batches):
+            B, L = imu_host.shape[0], imu_host.shape[-1]
+            live = 16 * (self.clf.imu_encoder._check_native_dims(L) - 1)
+            if len(slots) < depth:
+                slots.append({"key": None})
+            sl = slots[i % depth]
+            if len(pending) == depth:                       # the slot about to be reused must have been handed out
+                yield finish(pending.pop(0))
+            key = (B, live, None if fmap_host is None else (tuple(fmap_host.shape), fmap_host.dtype))
+            if sl["key"] != key:
+                sl.update(key=key, imu_pin=torch.empty((B, live), dtype=torch.float32).pin_memory(),
+                          imu_dev=torch.empty((B, live), dtype=torch.float32, device=dev),
+                          res_pin=torch.empty((4, B), dtype=torch.float32).pin_memory(),
+                          pred_pin=torch.empty((B,), dtype=torch.int64).pin_memory(),
+                          loss_pin=torch.empty((), dtype=torch.float64).pin_memory(),
+                          up=torch.cuda.Event(), done=torch.cuda.Event())
+                if fmap_host is not None:
+                    sl["fmap_pin"] = torch.empty_like(fmap_host).pin_memory()
+                    sl["fmap_dev"] = torch.empty(fmap_host.shape, dtype=fmap_host.dtype, device=dev)
+            sl["imu_pin"].copy_(imu_host[:, 0, :live] if imu_host.dim() == 3 else imu_host[:, :live])
+            copy.wait_stream(main)                          # the slot's device buffers were read by batch i - depth
+            with torch.cuda.stream(copy):
+                sl["imu_dev"].copy_(sl["imu_pin"], non_blocking=True)
+                fdev = None
+                if fmap_host is not None:
+                    src = fmap_host
+                    if not fmap_host.is_pinned():
+                        sl["fmap_pin"].copy_(fmap_host)
+                        src = sl["fmap_pin"]
+                    sl["fmap_dev"].copy_(src, non_blocking=True)
+                    fdev = sl["fmap_dev"]
+                sl["up"].record(copy)
+            main.wait_event(sl["up"])
+            out = self.run(sl["imu_dev"], fdev, window_stride=live)
+            sl["pred_pin"].copy_(out["pred"], non_blocking=True)
+            sl["res_pin"][0].copy_(out["msp"], non_blocking=True)
+            sl["res_pin"][1].copy_(out["energy"], non_blocking=True)
+            res = {"pred": sl["pred_pin"], "msp": sl["res_pin"][0], "energy": sl["res_pin"][1]}
+            if "maha" in out:
+                sl["res_pin"][2].copy_(out["maha"], non_blocking=True)
+                res["maha"] = sl["res_pin"][2]
+            if "loss" in out:
+                sl["loss_pin"].copy_(out["loss"], non_blocking=True)
+                res["loss"] = sl["loss_pin"]
+            sl["done"].record(main)
+            sl["res"] = res
+            pending.append(sl)
+        while pending:
+            yield finish(pending.pop(0))
 
     def host_bytes_per_step(self, B: int, L: int, fmap_host: Optional[torch.Tensor]):
         live = 16 * (self.clf.imu_encoder._check_native_dims(L) - 1)

@@ -97,3 +97,20 @@ def test_late_fusion_pipeline_matches_spec():
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(gout["logits"], out["logits"]) and torch.equal(gout["pred"], out["pred"])
+
+
+def test_stream_host_equals_run_host():
+    clf, xm, _, _ = build()
+    B, T = 24, 16
+    pipe = cm.CrossModalOODPipeline(clf, xm, None, frames=T, precision="fp32")
+    batches = [(torch.from_numpy(W.imu_windows(50 + i, B)), torch.from_numpy(W.video_feature_maps(60 + i, B, T)).to(torch.bfloat16))
+               for i in range(5)]
+    want = []
+    for imu, f in batches:
+        r = pipe.run_host(imu, f)
+        want.append({k: v.clone() for k, v in r.items()})
+    got = [{k: v.clone() for k, v in r.items()} for r in pipe.stream_host(iter(batches), depth=2)]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert torch.equal(g["pred"], w["pred"]) and torch.equal(g["energy"], w["energy"])
+        assert abs(float(g["loss"]) - float(w["loss"])) < 1e-12
