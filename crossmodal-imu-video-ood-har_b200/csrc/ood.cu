@@ -9,7 +9,62 @@
 
 namespace cmhar {
 
-// ---- A1/A2 from stored logits: one warp per row -------------------------------------------------
+// ---- A1/A2 from stored logits (HBM-bound: 128 B in, 16 B out per row at C = 32) ---------------------------
+// Fast path (C % 4 == 0, C <= 128): a group of G = C/4 lanes owns a row, every lane loads one float4, so a warp
+// reads 32/G consecutive rows as ONE contiguous 512-byte span; the row reductions are log2(G) xor-shuffles.
+template <int G>
+__global__ void __launch_bounds__(256) logit_scores_vec_kernel(const float* __restrict__ logits, long long n, float invT,
+                                                               float T, long long* __restrict__ pred, float* __restrict__ msp,
+                                                               float* __restrict__ energy) {
+    constexpr int RPW = 32 / G;                                   // rows per warp per load
+    constexpr int U = 4;                                          // independent 512-byte loads in flight per warp
+    const int lane = threadIdx.x & 31, sub = lane % G;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp_global * (RPW * U); base < n; base += n_warps * (RPW * U)) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = base + u * RPW + lane / G;
+            v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (row < n) {
+                const float4* p = reinterpret_cast<const float4*>(logits + row * (4 * G)) + sub;
+                asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(p));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long row = base + u * RPW + lane / G;
+            float m = v[u].x;
+            int idx = 4 * sub;
+            if (v[u].y > m) { m = v[u].y; idx = 4 * sub + 1; }
+            if (v[u].z > m) { m = v[u].z; idx = 4 * sub + 2; }
+            if (v[u].w > m) { m = v[u].w; idx = 4 * sub + 3; }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {                 // first maximal index (torch max(1))
+                const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+                const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+                if (m2 > m || (m2 == m && i2 < idx)) { m = m2; idx = i2; }
+            }
+            float s1 = __expf(v[u].x - m) + __expf(v[u].y - m) + __expf(v[u].z - m) + __expf(v[u].w - m);
+            float sT = (invT == 1.f) ? s1
+                                     : __expf((v[u].x - m) * invT) + __expf((v[u].y - m) * invT) + __expf((v[u].z - m) * invT) + __expf((v[u].w - m) * invT);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                sT += __shfl_xor_sync(0xffffffffu, sT, o);
+            }
+            if (row < n && sub == 0) {
+                if (pred) pred[row] = idx;
+                if (msp) msp[row] = -1.f / s1;
+                if (energy) energy[row] = -(m + T * __logf(sT));
+            }
+        }
+    }
+}
+
+// generic path: one warp per row
 __global__ void __launch_bounds__(256) logit_scores_kernel(const float* __restrict__ logits, long long n, int C,
                                                            float invT, float T, long long* __restrict__ pred,
                                                            float* __restrict__ msp, float* __restrict__ energy) {
@@ -248,8 +303,26 @@ int cmhar_logit_scores(const float* logits, int64_t n, int32_t classes, float te
                        float* msp_out, float* energy_out, cmhar_stream_t s) {
     CMHAR_REQUIRE(logits && classes >= 1 && temperature > 0.f, "cmhar_logit_scores: bad argument");
     if (n <= 0) return CMHAR_OK;
-    logit_scores_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)s>>>(
-        logits, n, classes, 1.f / temperature, temperature, reinterpret_cast<long long*>(pred_out), msp_out, energy_out);
+    const float invT = 1.f / temperature;
+    long long* pred = reinterpret_cast<long long*>(pred_out);
+    cudaStream_t st = (cudaStream_t)s;
+    const int G = classes / 4;
+    const bool vec = (classes % 4 == 0) && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && ((uintptr_t)logits & 15) == 0;
+    if (vec) {
+        const long long rows_per_block = 8LL * (32 / G) * 4;
+        const long long want = (n + rows_per_block - 1) / rows_per_block;
+        const unsigned grid = (unsigned)(want < 16LL * sm_count() ? want : 16LL * sm_count());
+        switch (G) {
+            case 1: logit_scores_vec_kernel<1><<<grid, 256, 0, st>>>(logits, n, invT, temperature, pred, msp_out, energy_out); break;
+            case 2: logit_scores_vec_kernel<2><<<grid, 256, 0, st>>>(logits, n, invT, temperature, pred, msp_out, energy_out); break;
+            case 4: logit_scores_vec_kernel<4><<<grid, 256, 0, st>>>(logits, n, invT, temperature, pred, msp_out, energy_out); break;
+            case 8: logit_scores_vec_kernel<8><<<grid, 256, 0, st>>>(logits, n, invT, temperature, pred, msp_out, energy_out); break;
+            case 16: logit_scores_vec_kernel<16><<<grid, 256, 0, st>>>(logits, n, invT, temperature, pred, msp_out, energy_out); break;
+            default: logit_scores_vec_kernel<32><<<grid, 256, 0, st>>>(logits, n, invT, temperature, pred, msp_out, energy_out); break;
+        }
+    } else {
+        logit_scores_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(logits, n, classes, invT, temperature, pred, msp_out, energy_out);
+    }
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }
