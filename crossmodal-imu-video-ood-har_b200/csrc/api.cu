@@ -4,7 +4,7 @@
 namespace cmhar {
 int launch_imu_forward_fp32(const FwdArgs& a, cudaStream_t stream);
 int launch_imu_forward_bf16(const FwdArgs& a, cudaStream_t stream);
-int launch_head_forward(const FwdArgs& a, cudaStream_t stream);
+int launch_head_forward(const FwdArgs& a, int precision, cudaStream_t stream);
 int launch_imu_forward_bf16_debug(const FwdArgs& a, int stage, float* dump, int* progress, cudaStream_t stream);
 }  // namespace cmhar
 
@@ -51,7 +51,9 @@ int cmhar_debug_imu_bf16(const void* encoder_blob, const float* x, int64_t n_win
 }
 
 int cmhar_head_forward(const void* head_blob, const void* maha_blob, const float* feat, int64_t n, float* logits_out,
-                       int64_t* pred_out, float* msp_out, float* energy_out, float* maha_out, cmhar_stream_t s) {
+                       int64_t* pred_out, float* msp_out, float* energy_out, float* maha_out, int32_t precision,
+                       cmhar_stream_t s) {
+    CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
     CMHAR_REQUIRE(feat && (head_blob || maha_blob), "cmhar_head_forward: null argument");
     CMHAR_REQUIRE(head_blob || !(logits_out || pred_out || msp_out || energy_out),
                   "logits/pred/msp/energy outputs need a head blob");
@@ -63,7 +65,7 @@ int cmhar_head_forward(const void* head_blob, const void* maha_blob, const float
     a.x = feat; a.n = n; a.xstride = D;
     a.logits_out = logits_out; a.pred_out = reinterpret_cast<long long*>(pred_out);
     a.msp_out = msp_out; a.energy_out = energy_out; a.maha_out = maha_out;
-    return launch_head_forward(a, (cudaStream_t)s);
+    return launch_head_forward(a, precision, (cudaStream_t)s);
 }
 
 }  // extern "C"

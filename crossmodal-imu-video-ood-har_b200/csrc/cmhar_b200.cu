@@ -7,6 +7,7 @@ namespace cmhar { struct FwdArgs; }
 #include "imu_encoder_fp32.cu"
 #include "imu_encoder_bf16.cu"
 #include "head.cu"
+#include "head_tc.cu"
 #include "dense.cu"
 #include "similarity.cu"
 #include "similarity_tc.cu"

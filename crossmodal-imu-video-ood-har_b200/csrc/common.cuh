@@ -109,6 +109,14 @@ struct MahaLayout {
     __host__ __device__ size_t total() const { return valid() + C; }
 };
 
+// The tensor-core section of a head / maha blob starts at the next 1 KiB boundary behind the fp32 section.
+__host__ __device__ inline size_t tc_section_offset(size_t fp32_floats) {
+    return (sizeof(BlobHeader) + fp32_floats * sizeof(float) + 1023) / 1024 * 1024;
+}
+struct BlobInfo { uint32_t magic; int a, b, c, has_tc; };
+void register_blob(const void* blob, const BlobInfo& info);
+bool lookup_blob(const void* blob, BlobInfo* info);
+
 // ---- device helpers -----------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -243,10 +243,28 @@ __global__ void __launch_bounds__(NT) head_scores_kernel(const FwdArgs a) {
 
 }  // namespace headk
 
-// x = features (n, xstride >= 128) fp32.  Large batches: 32-row tiles, one persistent CTA per SM;
-// small batches: 8-row tiles so that more SMs take part.
-int launch_head_forward(const FwdArgs& a, cudaStream_t stream) {
+int launch_head_forward_tc(const FwdArgs& a, const uint8_t* head_tc, const float* head_f32, const HeadLayout& hl,
+                           const uint8_t* maha_tc, cudaStream_t stream);                          // head_tc.cu
+
+// x = features (n, xstride >= 128) fp32.
+// CMHAR_BF16 and blobs that carry the tensor-core section: the tcgen05 split-bf16 kernel (head_tc.cu).
+// Otherwise fp32 CUDA cores -- large batches: 32-row tiles, one persistent CTA per SM; small batches: 8-row tiles
+// so that more SMs take part.
+int launch_head_forward(const FwdArgs& a, int precision, cudaStream_t stream) {
     using namespace headk;
+    if (precision == CMHAR_BF16 && (a.xstride & 3) == 0 && ((uintptr_t)a.x & 15) == 0) {
+        BlobInfo hi{}, mi{};
+        const bool want_maha = a.maha_blob && a.maha_out;
+        const bool head_ok = !a.head_blob || (lookup_blob(a.head_blob, &hi) && hi.magic == HEAD_MAGIC && hi.has_tc);
+        const bool maha_ok = !want_maha || (lookup_blob(a.maha_blob, &mi) && mi.magic == MAHA_MAGIC && mi.has_tc);
+        if (head_ok && maha_ok && (a.head_blob || want_maha)) {
+            HeadLayout hl{hi.a, hi.b, hi.c};
+            const uint8_t* htc = a.head_blob ? reinterpret_cast<const uint8_t*>(a.head_blob) + tc_section_offset(hl.total()) : nullptr;
+            const float* hf32 = a.head_blob ? reinterpret_cast<const float*>(a.head_blob + sizeof(BlobHeader)) : nullptr;
+            const uint8_t* mtc = want_maha ? reinterpret_cast<const uint8_t*>(a.maha_blob) + tc_section_offset(MahaLayout{mi.a}.total()) : nullptr;
+            return launch_head_forward_tc(a, htc, hf32, hl, mtc, stream);
+        }
+    }
     static bool configured[64] = {};
     int dev = 0;
     CMHAR_CHECK_CUDA(cudaGetDevice(&dev));

@@ -769,10 +769,10 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
     if (nq == 2) imu_forward_bf16_kernel<2><<<grid, 320, SMEM_BYTES, stream>>>(args);
     else imu_forward_bf16_kernel<4><<<grid, 576, SMEM_BYTES, stream>>>(args);
     CMHAR_LAUNCH_CHECK();
-    return launch_head_after_encoder(args.f, stream);
+    return launch_head_after_encoder(args.f, CMHAR_BF16, stream);
 }
 
-int launch_head_after_encoder(const FwdArgs& a, cudaStream_t stream);     // imu_encoder_fp32.cu
+int launch_head_after_encoder(const FwdArgs& a, int precision, cudaStream_t stream);     // imu_encoder_fp32.cu
 
 int launch_imu_forward_bf16(const FwdArgs& a, cudaStream_t stream) {
     Bf16Args args{a, -1, nullptr, nullptr, nullptr, ablate_mask()};

@@ -274,17 +274,17 @@ __global__ void __launch_bounds__(NT, 1) imu_forward_fp32_kernel(const FwdArgs a
     }
 }
 
-int launch_head_forward(const FwdArgs& a, cudaStream_t stream);     // head.cu
+int launch_head_forward(const FwdArgs& a, int precision, cudaStream_t stream);     // head.cu
 
 // The classifier head and the OOD scores run as a second launch on the CLS features the encoder just
 // wrote (head.cu): on the 8 CLS rows of one tile the head is latency-bound on its 344 KB of weights and
 // used to cost 30 % of the fused kernel; batched over 32-row tiles it is 6 %.
-int launch_head_after_encoder(const FwdArgs& a, cudaStream_t stream) {
+int launch_head_after_encoder(const FwdArgs& a, int precision, cudaStream_t stream) {
     if (!a.head_blob && !(a.maha_blob && a.maha_out)) return CMHAR_OK;
     FwdArgs h = a;
     h.x = a.cls_out; h.xstride = D;
     h.cls_out = nullptr; h.tokens_out = nullptr;
-    return launch_head_forward(h, stream);
+    return launch_head_forward(h, precision, stream);
 }
 
 int launch_imu_forward_fp32(const FwdArgs& a, cudaStream_t stream) {
@@ -301,7 +301,7 @@ int launch_imu_forward_fp32(const FwdArgs& a, cudaStream_t stream) {
     const int grid = (int)((tiles < (long long)sm_count()) ? tiles : (long long)sm_count());
     imu_forward_fp32_kernel<<<grid, NT, smem, stream>>>(a);
     CMHAR_LAUNCH_CHECK();
-    return launch_head_after_encoder(a, stream);
+    return launch_head_after_encoder(a, CMHAR_FP32, stream);
 }
 
 }  // namespace cmhar

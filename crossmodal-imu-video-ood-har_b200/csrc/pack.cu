@@ -3,6 +3,8 @@
 // the state_dict tensors' device pointers (SURVEY.md Appendix B names them).
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -17,6 +19,29 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+// ---- host-side registry of packed blobs: the launchers need a blob's dimensions (and whether it carries the
+// tensor-core section) without a device->host read.  Keyed by the blob pointer; an unknown pointer (a blob the
+// caller copied elsewhere) simply takes the CUDA-core path.
+static std::mutex g_blob_mu;
+static std::unordered_map<const void*, BlobInfo> g_blobs;
+void register_blob(const void* blob, const BlobInfo& info) {
+    std::lock_guard<std::mutex> lk(g_blob_mu);
+    g_blobs[blob] = info;
+}
+bool lookup_blob(const void* blob, BlobInfo* info) {
+    std::lock_guard<std::mutex> lk(g_blob_mu);
+    auto it = g_blobs.find(blob);
+    if (it == g_blobs.end()) return false;
+    *info = it->second;
+    return true;
+}
+
+bool head_tc_eligible(int h1, int h2, int C);                                                   // head_tc.cu
+size_t head_tc_bytes();
+size_t maha_tc_bytes();
+int pack_head_tc(const float* f32, const HeadLayout& hl, uint8_t* dst, cudaStream_t st);
+int pack_maha_tc(const float* f32, const MahaLayout& ml, uint8_t* dst, cudaStream_t st);
 
 // dst[k*ldd + n] = src[n*K + k] * (n < scaled_rows ? scale : 1) * (col_scale ? col_scale(n) : 1)
 // col scale = bn_w[n] / sqrt(bn_var[n] + eps) when bn_w != nullptr (computed in double)
@@ -154,7 +179,7 @@ int cmhar_imu_encoder_pack(const cmhar_imu_encoder_params* p, void* blob, cmhar_
 size_t cmhar_head_blob_bytes(int32_t h1, int32_t h2, int32_t C) {
     if (h1 < 4 || h1 > 256 || (h1 & 3) || h2 < 4 || h2 > 256 || (h2 & 3) || C < 2 || C > CMHAR_MAX_CLASSES) return 0;
     HeadLayout hl{h1, h2, C};
-    return sizeof(BlobHeader) + hl.total() * sizeof(float);
+    return tc_section_offset(hl.total()) + (head_tc_eligible(h1, h2, C) ? head_tc_bytes() : 0);
 }
 
 int cmhar_head_pack(const cmhar_head_params* p, void* blob, cmhar_stream_t s) {
@@ -173,13 +198,18 @@ int cmhar_head_pack(const cmhar_head_params* p, void* blob, cmhar_stream_t s) {
     TRY(bias_fold(p->b2, hl.C, f + hl.b2(), 0, 1.f, nullptr, nullptr, nullptr, nullptr, st));
     BlobHeader h{};
     h.magic = HEAD_MAGIC; h.a = hl.h1; h.b = hl.h2; h.c = hl.C;
+    if (head_tc_eligible(hl.h1, hl.h2, hl.C)) {      // split-bf16 operand images for the tensor-core head (head_tc.cu)
+        h.has_bf16 = 1;
+        TRY(pack_head_tc(f, hl, reinterpret_cast<uint8_t*>(blob) + tc_section_offset(hl.total()), st));
+    }
+    register_blob(blob, BlobInfo{HEAD_MAGIC, hl.h1, hl.h2, hl.C, h.has_bf16});
     return write_header(blob, h, st);
 }
 
 size_t cmhar_maha_blob_bytes(int32_t C) {
     if (C < 1 || C > 1024) return 0;
     MahaLayout ml{C};
-    return sizeof(BlobHeader) + ml.total() * sizeof(float);
+    return tc_section_offset(ml.total()) + (C <= 32 ? maha_tc_bytes() : 0);
 }
 
 int cmhar_maha_pack(const float* whiten, const float* mean_whitened, const float* class_count, int32_t C,
@@ -195,6 +225,11 @@ int cmhar_maha_pack(const float* whiten, const float* mean_whitened, const float
     CMHAR_LAUNCH_CHECK();
     BlobHeader h{};
     h.magic = MAHA_MAGIC; h.a = C;
+    if (C <= 32) {
+        h.has_bf16 = 1;
+        TRY(pack_maha_tc(f, ml, reinterpret_cast<uint8_t*>(blob) + tc_section_offset(ml.total()), st));
+    }
+    register_blob(blob, BlobInfo{MAHA_MAGIC, C, 0, 0, h.has_bf16});
     return write_header(blob, h, st);
 }
 

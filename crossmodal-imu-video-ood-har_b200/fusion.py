@@ -47,7 +47,7 @@ def _head(in_dim: int, config) -> nn.Sequential:
 
 
 def head_scores_native(head_blob: torch.Tensor, maha_blob: Optional[torch.Tensor], feat: torch.Tensor, classes: int,
-                       out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                       out: Optional[Dict[str, torch.Tensor]] = None, precision: Optional[str] = None) -> Dict[str, torch.Tensor]:
     """Classifier head + arg-max / MSP / energy (+ Mahalanobis) on stored (n,128) features: one launch."""
     feat = N.f32c(feat)
     n, dev = feat.shape[0], feat.device
@@ -64,7 +64,8 @@ def head_scores_native(head_blob: torch.Tensor, maha_blob: Optional[torch.Tensor
     maha = buf("maha", (n,)) if maha_blob is not None else None
     with torch.cuda.device(dev):
         N.check(N.lib().cmhar_head_forward(head_blob.data_ptr(), N.ptr(maha_blob), feat.data_ptr(), n, logits.data_ptr(),
-                                           pred.data_ptr(), msp.data_ptr(), energy.data_ptr(), N.ptr(maha), N.stream_ptr(dev)))
+                                           pred.data_ptr(), msp.data_ptr(), energy.data_ptr(), N.ptr(maha), _prec_code(precision),
+                                           N.stream_ptr(dev)))
     return out
 
 
@@ -93,10 +94,11 @@ class _FusionBase(_PackedMixin, nn.Module):
         if self.d_model != 128:
             raise NotImplementedError("native fusion kernels are specialised to a 128-d fused feature")
 
-    def _scores(self, fused: torch.Tensor, out: Optional[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
+    def _scores(self, fused: torch.Tensor, out: Optional[Dict[str, torch.Tensor]], precision: Optional[str] = None
+                ) -> Dict[str, torch.Tensor]:
         dev = fused.device
         maha_blob = self._maha_state.blob(dev) if self._maha_state is not None else None
-        res = head_scores_native(self._head_blob(dev), maha_blob, fused, self.num_classes, out)
+        res = head_scores_native(self._head_blob(dev), maha_blob, fused, self.num_classes, out, precision)
         res["fused"] = fused
         return res
 
@@ -149,7 +151,7 @@ class LateFusionClassifier(_FusionBase):
                                          window_stride=window_stride)["cls"]
         if video_feat is None:
             video_feat = self.video_encoder.forward_features(fmap, frames, precision=precision)
-        return self._scores(self.fuse_native(imu_cls, video_feat, precision), out)
+        return self._scores(self.fuse_native(imu_cls, video_feat, precision), out, precision)
 
     def forward(self, imu, video):
         if _native_mode(self):
@@ -211,7 +213,7 @@ class CrossAttentionFusionClassifier(_FusionBase):
         tokens = imu_forward_native(self.imu_encoder, None, None, imu, want_tokens=True, precision=precision)["tokens"]
         frame_feats = self.video_encoder.forward_frame_features(fmap, precision=precision)
         B = tokens.shape[0]
-        return self._scores(self.fuse_native(tokens, frame_feats.view(B, frames, -1), precision), out)
+        return self._scores(self.fuse_native(tokens, frame_feats.view(B, frames, -1), precision), out, precision)
 
     def _fuse_autograd(self, tokens, frame_feats):
         B, S, d = tokens.shape

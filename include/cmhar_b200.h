@@ -137,10 +137,14 @@ int cmhar_debug_imu_bf16(const void* encoder_blob, const float* x, int64_t n_win
                          float* cls_out, int32_t* progress_host_mapped /* NULL or pinned [grid][16] */,
                          cmhar_stream_t s);
 
-/* Same head + scores from stored features (row-major (n,128) fp32). */
+/* Same head + scores from stored features (row-major (n,128) fp32).
+ * CMHAR_FP32: fp32 FMA arithmetic.  CMHAR_BF16: the tensor-core kernel -- every layer, the whitening and the
+ * class-mean products are tcgen05 MMAs on split-bf16 operands (x = hi + lo, three products per term, fp32
+ * accumulation in TMEM: ~2^-17 relative, fp32-grade logits) -- for the reference head layout (256, 128, <= 32
+ * classes); other layouts, or blobs copied after packing, silently use the fp32 kernel. */
 int cmhar_head_forward(const void* head_blob, const void* maha_blob, const float* feat, int64_t n,
                        float* logits_out, int64_t* pred_out, float* msp_out, float* energy_out,
-                       float* maha_out, cmhar_stream_t s);
+                       float* maha_out, int32_t precision, cmhar_stream_t s);
 
 /* MSP / energy from stored logits (spec rows A1, A2; no reference implementation). */
 int cmhar_logit_scores(const float* logits, int64_t n, int32_t classes, float temperature,

@@ -119,22 +119,44 @@ def test_edge_cases_empty_single_ragged_and_dead_inputs():
         assert torch.equal(sc["logits"], full)
 
 
-def test_stored_feature_head_and_logit_scores():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("n", [1001, 77, 20000])
+def test_stored_feature_head_and_maha_scores(precision, n):
+    """cmhar_head_forward from stored features: the fp32 CUDA-core kernel and the tcgen05 split-bf16 kernel
+    (precision='bf16') both deliver fp32-grade logits, exact labels, and the Mahalanobis score of the spec."""
+    clf, sd = make_classifier(12)
+    rs = np.random.RandomState(n)
+    feats, labels = W.class_features(7, 4000)
+    feat = feats[rs.randint(0, 4000, size=n)] + 0.3 * rs.standard_normal((n, 128)).astype(np.float32)
+    want = oracle.classifier_head(feat, sd, dtype=torch.float64).numpy()
+    maha = cm.MahalanobisOOD(32, DEV, ridge=1e-3).fit(torch.from_numpy(feats).to(DEV), torch.from_numpy(labels).to(DEV))
+    f = torch.from_numpy(feat).to(DEV)
+    logits = torch.empty(n, 32, device=DEV)
+    pred = torch.empty(n, dtype=torch.int64, device=DEV)
+    msp, energy, md = torch.empty(n, device=DEV), torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+    N = cm._native
+    N.check(N.lib().cmhar_head_forward(clf._head_blob(f.device).data_ptr(), maha.blob(f.device).data_ptr(), f.data_ptr(), n,
+                                       logits.data_ptr(), pred.data_ptr(), msp.data_ptr(), energy.data_ptr(), md.data_ptr(),
+                                       N.BF16 if precision == "bf16" else N.FP32, N.stream_ptr(f.device)))
+    torch.cuda.synchronize()
+    assert rel_err(logits, want) < 2e-5
+    got = logits.cpu().numpy()
+    margin = np.sort(want, 1)[:, -1] - np.sort(want, 1)[:, -2]
+    safe = margin > 1e-3 * np.abs(want).max()
+    assert np.array_equal(pred.cpu().numpy()[safe], want.argmax(1)[safe])
+    np.testing.assert_array_equal(pred.cpu().numpy(), got.argmax(1))
+    np.testing.assert_allclose(energy.cpu().numpy(), ood_spec.energy_score(got), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(msp.cpu().numpy(), ood_spec.msp_score(got), rtol=1e-4, atol=1e-5)
+    st = ood_spec.mahalanobis_finalize(*ood_spec.mahalanobis_sufficient_stats(feats, labels, 32), ridge=1e-3)
+    want_m = ood_spec.mahalanobis_score(feat, st)
+    assert float(np.abs(md.cpu().numpy() - want_m).max() / np.abs(want_m).max()) < 2e-4
+
+
+def test_logit_scores_from_stored_logits():
     clf, sd = make_classifier(12)
     rs = np.random.RandomState(0)
     feat = rs.standard_normal((1001, 128)).astype(np.float32)
     want = oracle.classifier_head(feat, sd).numpy()
-    f = torch.from_numpy(feat).to(DEV)
-    n = f.shape[0]
-    logits = torch.empty(n, 32, device=DEV)
-    pred = torch.empty(n, dtype=torch.int64, device=DEV)
-    msp = torch.empty(n, device=DEV)
-    energy = torch.empty(n, device=DEV)
-    N = cm._native
-    N.check(N.lib().cmhar_head_forward(clf._head_blob(f.device).data_ptr(), None, f.data_ptr(), n, logits.data_ptr(),
-                                       pred.data_ptr(), msp.data_ptr(), energy.data_ptr(), None, N.stream_ptr(f.device)))
-    assert rel_err(logits, want) < 2e-5
-    assert np.array_equal(pred.cpu().numpy(), oracle.predict(want))
     s = cm.logit_scores(torch.from_numpy(want).to(DEV), temperature=2.0)
     np.testing.assert_allclose(s["energy"].cpu().numpy(), ood_spec.energy_score(want, T=2.0), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(s["msp"].cpu().numpy(), ood_spec.msp_score(want), rtol=1e-5, atol=1e-7)

@@ -68,14 +68,15 @@ cfg = cm.default_config()
 clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg).to(dev).eval()
 hb = clf._head_blob(dev)
 lg = torch.empty(n, 32, device=dev); pr = torch.empty(n, dtype=torch.int64, device=dev); m1 = torch.empty(n, device=dev); m2 = torch.empty(n, device=dev); m3 = torch.empty(n, device=dev)
-f = lambda: N.check(lib.cmhar_head_forward(hb.data_ptr(), maha.blob(dev).data_ptr(), feat.data_ptr(), n, lg.data_ptr(), pr.data_ptr(), m1.data_ptr(), m2.data_ptr(), m3.data_ptr(), st()))
-ms = timeit(f, 5)
-report(f"head+scores+maha n={n} (fp32 FMA bound)", ms, n * (512 + 128 + 20))
-print(f"   head: {n * (139264 + 2 * 128 * 128 + 3 * 128 * 32) / ms / 1e9:.1f} TFLOP/s fp32")
-f = lambda: N.check(lib.cmhar_head_forward(hb.data_ptr(), None, feat.data_ptr(), n, lg.data_ptr(), pr.data_ptr(), m1.data_ptr(), m2.data_ptr(), None, st()))
-ms = timeit(f, 5)
-report(f"head+scores n={n}", ms, n * (512 + 128 + 16))
-print(f"   head: {n * 139264 / ms / 1e9:.1f} TFLOP/s fp32")
+for PREC, pname in ((0, 'fp32 FMA'), (1, 'tcgen05 split-bf16')):
+    f = lambda: N.check(lib.cmhar_head_forward(hb.data_ptr(), maha.blob(dev).data_ptr(), feat.data_ptr(), n, lg.data_ptr(), pr.data_ptr(), m1.data_ptr(), m2.data_ptr(), m3.data_ptr(), PREC, st()))
+    ms = timeit(f, 5)
+    report(f"head+scores+maha n={n} [" + pname + "]", ms, n * (512 + 128 + 20))
+    print(f"   head: {n * (139264 + 2 * 128 * 128 + 3 * 128 * 32) / ms / 1e9:.1f} TFLOP/s fp32")
+    f = lambda: N.check(lib.cmhar_head_forward(hb.data_ptr(), None, feat.data_ptr(), n, lg.data_ptr(), pr.data_ptr(), m1.data_ptr(), m2.data_ptr(), None, PREC, st()))
+    ms = timeit(f, 5)
+    report(f"head+scores n={n} [" + pname + "]", ms, n * (512 + 128 + 16))
+    print(f"   head: {n * 139264 / ms / 1e9:.1f} TFLOP/s fp32")
 # ROC histograms
 n = 16_000_000
 s = torch.randn(n, device=dev)
