@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(256) score_histogram_kernel(const float* __res
 
 }  // namespace cmhar
 
+namespace cmhar { int launch_head_forward(const FwdArgs& a, int precision, cudaStream_t stream); }
+
 using namespace cmhar;
 
 extern "C" {
@@ -327,9 +329,17 @@ int cmhar_logit_scores(const float* logits, int64_t n, int32_t classes, float te
     return CMHAR_OK;
 }
 
-int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float* score, cmhar_stream_t s) {
+int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float* score, int32_t precision,
+                     cmhar_stream_t s) {
     CMHAR_REQUIRE(maha_blob && feat && score, "cmhar_maha_score: null argument");
+    CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
     if (n <= 0) return CMHAR_OK;
+    if (precision == CMHAR_BF16) {       // tensor-core kernel (whitening + class-mean products as split-bf16 MMAs) when eligible
+        FwdArgs a{};
+        a.maha_blob = reinterpret_cast<const char*>(maha_blob);
+        a.x = feat; a.n = n; a.xstride = D; a.maha_out = score;
+        return launch_head_forward(a, precision, (cudaStream_t)s);
+    }
     const long long tiles = (n + 63) / 64;
     const int grid = (int)((tiles < 3LL * sm_count()) ? tiles : 3LL * sm_count());
     const size_t smem = sizeof(float) * (64 * D + 64 * (D + 4));

@@ -140,14 +140,16 @@ class MahalanobisOOD:
         return self._blobs[key]
 
     @torch.no_grad()
-    def score(self, feats: torch.Tensor) -> torch.Tensor:
-        """min_c Mahalanobis^2 for stored features (n,128)."""
+    def score(self, feats: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+        """min_c Mahalanobis^2 for stored features (n,128).  precision 'bf16' = the tensor-core kernel
+        (split-bf16 operands, fp32-grade result)."""
         N.require_cuda(feats, "MahalanobisOOD.score")
         f = N.f32c(feats)
         out = torch.empty(f.shape[0], dtype=torch.float32, device=f.device)
         with torch.cuda.device(f.device):
+            from .models import _prec_code
             N.check(N.lib().cmhar_maha_score(self.blob(f.device).data_ptr(), f.data_ptr(), f.shape[0],
-                                             out.data_ptr(), N.stream_ptr(f.device)))
+                                             out.data_ptr(), _prec_code(precision), N.stream_ptr(f.device)))
         return out
 
 

@@ -225,8 +225,9 @@ int cmhar_similarity(const float* a, const float* b, int64_t na, int64_t nb, int
  * multi-GPU fit all-reduces over NCCL. */
 int cmhar_maha_accumulate(const float* feat, const int64_t* labels, int64_t n, int32_t classes,
                           double* count, double* sum, double* second, cmhar_stream_t s);
-/* score (n) = min_c || feat@whiten - mean_whitened_c ||^2 */
-int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float* score,
+/* score (n) = min_c || feat@whiten - mean_whitened_c ||^2.  CMHAR_BF16: whitening and class-mean products as
+ * split-bf16 tcgen05 MMAs (fp32-grade, see cmhar_head_forward) when classes <= 32; CMHAR_FP32: fp32 FMA. */
+int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float* score, int32_t precision,
                      cmhar_stream_t s);
 
 /* ------------------------------------------------------------------------------------------

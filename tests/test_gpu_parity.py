@@ -264,6 +264,11 @@ def test_mahalanobis_fit_and_score_vs_spec():
     r = cm.auroc_fpr95(torch.from_numpy(got[ql >= 0]).to(DEV), torch.from_numpy(got[ql < 0]).to(DEV))
     assert round(r["auroc"], 3) == round(ood_spec.auroc(want[ql >= 0], want[ql < 0]), 3)
     assert round(r["fpr"], 3) == round(ood_spec.fpr_at_tpr_fast(want[ql >= 0], want[ql < 0]), 3)
+    # the tensor-core score kernel (split-bf16 MMAs): same contract, same AUROC / FPR95
+    got_tc = m.score(torch.from_numpy(q).to(DEV), precision="bf16").cpu().numpy()
+    assert rel_err(got_tc, want) < 2e-4
+    r2 = cm.auroc_fpr95(torch.from_numpy(got_tc[ql >= 0]).to(DEV), torch.from_numpy(got_tc[ql < 0]).to(DEV))
+    assert round(r2["auroc"], 3) == round(r["auroc"], 3) and round(r2["fpr"], 3) == round(r["fpr"], 3)
 
 
 def test_auroc_fpr95_vs_spec_continuous_tied_and_separated():
