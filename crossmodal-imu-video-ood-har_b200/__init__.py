@@ -14,5 +14,7 @@ from .ood import (logit_scores, MahalanobisOOD, ScoreHistogram, auroc_fpr95, roc
                   finalize_mahalanobis)
 from .evaluator import Evaluator, classification_metrics, shard_bounds
 from .pipeline import CrossModalOODPipeline
+from .shards import WindowShard, write_shard, pack_npy_windows, live_samples
+from .tables import generate_ood_table, ood_rows, save_tables
 
 __version__ = "0.1.0"

@@ -176,3 +176,41 @@ def test_shard_bounds_cover_everything_once():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_window_shard_round_trip(tmp_path):
+    """Packed shard: live bytes are a contiguous slice, full windows rebuild bit for bit,
+    per-window .npy files in the reference layout (T, C) pack to the same shard."""
+    x = W.imu_windows(3, 37)
+    y = np.arange(37) % 5
+    p = str(tmp_path / "a.cmw")
+    cm.write_shard(p, x, y)
+    sh = cm.WindowShard(p)
+    assert len(sh) == 37 and sh.live_len == 240 == cm.live_samples(250) and cm.live_samples(100) == 96
+    np.testing.assert_array_equal(np.asarray(sh.live), x[:, 0, :240])
+    for i in (0, 17, 36):
+        np.testing.assert_array_equal(sh.window_full(i), x[i])
+    got = list(sh.batches(16, lo=5, hi=30))
+    assert [b["imu"].shape[0] for b in got] == [16, 9] and got[0]["imu"].shape[1] == 240
+    np.testing.assert_array_equal(torch.cat([b["label"] for b in got]).numpy(), y[5:30])
+    paths = []
+    for i in range(4):
+        f = tmp_path / f"w{i}.npy"
+        np.save(f, x[i].T)                                   # reference layout on disk: (T, C)
+        paths.append(str(f))
+    assert cm.pack_npy_windows(paths, y[:4], str(tmp_path / "b.cmw")) == 4
+    np.testing.assert_array_equal(np.asarray(cm.WindowShard(str(tmp_path / "b.cmw")).live), x[:4, 0, :240])
+
+
+def test_ood_table_generator(tmp_path):
+    """scorer x split table in the reference's "mean ± std" style, three output formats."""
+    import pandas as pd
+    rows = []
+    for run in range(3):
+        res = {"msp": {"auroc": 0.80 + 0.01 * run, "fpr95": 0.60}, "maha": {"auroc": 0.95, "fpr": 0.20 + 0.02 * run}}
+        rows += cm.ood_rows("pretrained", "holdout_8_of_32", res, run)
+    tables = cm.generate_ood_table(pd.DataFrame(rows))
+    assert tables["ood_auroc"].loc["pretrained", ("holdout_8_of_32", "msp")] == "81.00 ± 1.00"
+    assert tables["ood_fpr95"].loc["pretrained", ("holdout_8_of_32", "maha")] == "22.00 ± 2.00"
+    files = cm.save_tables(tables, tmp_path, prefix="table_ood")
+    assert len(files) == 9 and all(os.path.getsize(f) > 0 for f in files)
