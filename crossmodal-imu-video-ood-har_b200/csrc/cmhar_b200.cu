@@ -9,6 +9,7 @@ namespace cmhar { struct FwdArgs; }
 #include "head.cu"
 #include "head_tc.cu"
 #include "dense.cu"
+#include "linear_tc.cu"
 #include "similarity.cu"
 #include "similarity_tc.cu"
 #include "fusion.cu"

@@ -179,13 +179,25 @@ __global__ void __launch_bounds__(256) video_pool_kernel(const T* __restrict__ f
 
 }  // namespace cmhar
 
+namespace cmhar {
+bool linear_tc_eligible(int in_dim, int out_dim);                                                        // linear_tc.cu
+size_t linear_tc_bytes(int in_dim, int out_dim);
+int pack_linear_tc(const float* wt_f32, int in_dim, int out_dim, uint8_t* dst, cudaStream_t st);
+int launch_linear_tc(const uint8_t* w_img, const float* bias, const float* x1, const float* x2, int K1, long long n, int K, int N,
+                     int relu, float* y, cudaStream_t st);
+static size_t linear_fp32_floats(int in_dim, int out_dim) { return (size_t)in_dim * out_dim + out_dim; }
+}  // namespace cmhar
+
 using namespace cmhar;
 
 extern "C" {
 
+// [header][fp32 W'^T (in,out) | bias] and, when in_dim % 64 == 0, at the next 1 KiB the bf16 chunk images of
+// the tensor-core path.
 size_t cmhar_linear_blob_bytes(int32_t in_dim, int32_t out_dim) {
     if (in_dim < 4 || out_dim < 4 || (in_dim & 3) || (out_dim & 3)) return 0;
-    return sizeof(BlobHeader) + ((size_t)in_dim * out_dim + out_dim) * sizeof(float);
+    if (!linear_tc_eligible(in_dim, out_dim)) return sizeof(BlobHeader) + linear_fp32_floats(in_dim, out_dim) * sizeof(float);
+    return tc_section_offset(linear_fp32_floats(in_dim, out_dim)) + linear_tc_bytes(in_dim, out_dim);
 }
 
 int cmhar_linear_pack(const float* weight, const float* bias, const float* bn_weight, const float* bn_bias,
@@ -203,6 +215,12 @@ int cmhar_linear_pack(const float* weight, const float* bias, const float* bn_we
     CMHAR_LAUNCH_CHECK();
     BlobHeader h{};
     h.magic = LIN_MAGIC; h.a = in_dim; h.b = out_dim;
+    if (linear_tc_eligible(in_dim, out_dim)) {
+        h.has_bf16 = 1;
+        const int rc = pack_linear_tc(f, in_dim, out_dim, reinterpret_cast<uint8_t*>(blob) + tc_section_offset(linear_fp32_floats(in_dim, out_dim)), st);
+        if (rc) return rc;
+    }
+    register_blob(blob, BlobInfo{LIN_MAGIC, in_dim, out_dim, 0, h.has_bf16});
     write_header_kernel<<<1, 1, 0, st>>>(reinterpret_cast<BlobHeader*>(blob), h);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
@@ -220,6 +238,14 @@ static int linear_forward_impl(const void* blob, const float* x, const float* x2
     CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
     if (n <= 0) return CMHAR_OK;
     const float* f = reinterpret_cast<const float*>(reinterpret_cast<const char*>(blob) + sizeof(BlobHeader));
+    if (precision == CMHAR_BF16) {       // tensor-core tiles when the blob carries the bf16 images
+        BlobInfo bi{};
+        const int k1 = x2 ? in_dim1 : in_dim;
+        if (lookup_blob(blob, &bi) && bi.magic == LIN_MAGIC && bi.has_tc && bi.a == in_dim && bi.b == out_dim && (k1 % 32) == 0 &&
+            ((uintptr_t)x & 15) == 0 && (!x2 || ((uintptr_t)x2 & 15) == 0) && ((uintptr_t)y & 15) == 0)
+            return launch_linear_tc(reinterpret_cast<const uint8_t*>(blob) + tc_section_offset(linear_fp32_floats(in_dim, out_dim)),
+                                    f + (size_t)in_dim * out_dim, x, x2, k1, n, in_dim, out_dim, relu, y, (cudaStream_t)s);
+    }
     const unsigned gx = (unsigned)((n + LT_ROWS - 1) / LT_ROWS), gy = (unsigned)((out_dim + LT_COLS - 1) / LT_COLS);
     // k-split only when the plain grid cannot fill the machine and the caller gave a workspace
     int splits = 1;

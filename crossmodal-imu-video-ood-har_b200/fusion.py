@@ -130,7 +130,7 @@ class LateFusionClassifier(_FusionBase):
         y = torch.empty((n, pl.out_dim), dtype=torch.float32, device=a.device)
         lib = N.lib()
         work, wbytes = None, 0
-        if 0 < n <= 2048:
+        if 0 < n <= 2048 and not (_prec_code(precision) == N.BF16 and pl.in_dim % 64 == 0):
             wbytes = lib.cmhar_linear_work_bytes(n, pl.out_dim)
             work = torch.empty(wbytes, dtype=torch.uint8, device=a.device)
         with torch.cuda.device(a.device):

@@ -323,7 +323,8 @@ class _PackedLinear:
         y = out if out is not None else torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)
         lib = N.lib()
         work, wbytes = None, 0
-        if 0 < n <= 2048:        # small batches: workspace for the deterministic k-split
+        tc_path = _prec_code(precision) == N.BF16 and self.in_dim % 64 == 0      # tensor-core tiles: no k-split workspace
+        if 0 < n <= 2048 and not tc_path:        # small batches: workspace for the deterministic k-split
             wbytes = lib.cmhar_linear_work_bytes(n, self.out_dim)
             work = torch.empty(wbytes, dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
@@ -462,11 +463,15 @@ class ProjectionHead(_PackedMixin, nn.Module):
                                  _PackedLinear(self.net[3], None, device))
         return self._packed[key]
 
+    def forward_native(self, x, precision: Optional[str] = None):
+        """Inference route with an explicit precision ('bf16' = tcgen05 tiles, 'fp32' = CUDA-core tiles)."""
+        N.require_cuda(x, "ProjectionHead")
+        l0, l1 = self._packed_layers(x.device)
+        return l1(l0(x, relu=True, precision=precision), relu=False, precision=precision)
+
     def forward(self, x):
         if _native_mode(self):
-            N.require_cuda(x, "ProjectionHead")
-            l0, l1 = self._packed_layers(x.device)
-            return l1(l0(x, relu=True), relu=False)
+            return self.forward_native(x)
         return self.net(x)
 
 
@@ -503,8 +508,8 @@ class CrossModalModel(_PackedMixin, nn.Module):
         (fmap: (B*frames, F, h, w) bf16/fp32).  Returns unit-norm (imu_proj, video_proj)."""
         imu_feat = self.imu_encoder.encode_cls(imu, precision=precision)
         video_feat = self.video_encoder.forward_features(fmap, frames, precision=precision)
-        return (l2_normalize_native(self.imu_proj(imu_feat)),
-                l2_normalize_native(self.video_proj(video_feat)))
+        return (l2_normalize_native(self.imu_proj.forward_native(imu_feat, precision)),
+                l2_normalize_native(self.video_proj.forward_native(video_feat, precision)))
 
 
 # =============================================================================== classifier

@@ -64,13 +64,13 @@ class CrossModalOODPipeline:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             vfeat = self.xm.video_encoder.forward_features(fmap, self.frames, precision=self.precision)
-            vp = l2_normalize_native(self.xm.video_proj(vfeat))
+            vp = l2_normalize_native(self.xm.video_proj.forward_native(vfeat, self.precision))
         if self.fusion is None:
             out = self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
         else:
             out = imu_forward_native(self.clf.imu_encoder, None, None, imu, want_cls=True, precision=self.precision,
                                      window_stride=window_stride)
-        ip = l2_normalize_native(self.xm.imu_proj(out["cls"]))
+        ip = l2_normalize_native(self.xm.imu_proj.forward_native(out["cls"], self.precision))
         main.wait_stream(side)
         if not torch.cuda.is_current_stream_capturing():
             for t in (vfeat, vp):

@@ -162,7 +162,9 @@ int    cmhar_linear_pack(const float* weight /*(out,in)*/, const float* bias /*(
                          cmhar_stream_t s);
 /* y (n,out) = relu?(x (n,in) @ W'^T + b');  in_dim % 4 == 0, out_dim % 4 == 0.
  * `work` (optional, cmhar_linear_work_bytes) lets small batches split the k loop over more CTAs;
- * partial sums are added in a fixed order, so results do not depend on scheduling. */
+ * partial sums are added in a fixed order, so results do not depend on scheduling.
+ * CMHAR_BF16 and in_dim % 64 == 0: 128 x 128 output tiles on the tensor cores (tcgen05, bf16 operands -- the
+ * activations converted on the fly, the weights from the bf16 images in the blob -- fp32 accumulation in TMEM). */
 size_t cmhar_linear_work_bytes(int64_t n, int32_t out_dim);
 int    cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t in_dim,
                             int32_t out_dim, int32_t relu, float* y, void* work, size_t work_bytes,

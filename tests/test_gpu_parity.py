@@ -412,3 +412,34 @@ def test_similarity_bf16_full_size_properties():
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1) / 10
         print(f"similarity 4096x4096x256 fused sigmoid loss, {prec}: {ms * 1e3:.1f} us  ({2 * 4096 * 4096 * 256 / ms / 1e9:.1f} TFLOP/s)")
+
+
+@pytest.mark.parametrize("n,k,m", [(256, 512, 768), (77, 128, 512), (300, 768, 512), (1000, 512, 256)])
+def test_linear_tensor_core_path(n, k, m):
+    """bf16 tcgen05 tiles of the small dense layers against float64, BatchNorm folded, ReLU, ragged rows/cols."""
+    rs = np.random.RandomState(n + k)
+    lin = torch.nn.Linear(k, m)
+    bn = torch.nn.BatchNorm1d(m)
+    with torch.no_grad():
+        bn.running_mean.copy_(torch.from_numpy(rs.standard_normal(m).astype(np.float32)))
+        bn.running_var.copy_(torch.from_numpy(rs.uniform(0.5, 2.0, m).astype(np.float32)))
+        bn.weight.copy_(torch.from_numpy(rs.uniform(0.5, 1.5, m).astype(np.float32)))
+        bn.bias.copy_(torch.from_numpy(rs.standard_normal(m).astype(np.float32)))
+    from crossmodal_imu_video_ood_har_b200.models import _PackedLinear
+    pl = _PackedLinear(lin.to(DEV), bn.to(DEV).eval(), DEV)
+    x = torch.from_numpy(rs.standard_normal((n, k)).astype(np.float32)).to(DEV)
+    want = torch.relu(bn.double()(lin.double()(x.double())))
+    got32 = pl(x, relu=True, precision="fp32")
+    got16 = pl(x, relu=True, precision="bf16")
+    assert rel_err(got32, want) < 1e-5
+    assert 1e-6 < rel_err(got16, want) < TOL["bf16"]          # really the bf16 path, and within its contract
+    # concat variant: [x1 | x2] never materialised
+    if k % 128 == 0:
+        k1 = 128
+        y = torch.empty(n, m, device=DEV)
+        N = cm._native
+        N.check(N.lib().cmhar_concat_linear_forward(pl.blob.data_ptr(), x[:, :k1].contiguous().data_ptr(), k1,
+                                                    x[:, k1:].contiguous().data_ptr(), k - k1, n, m, 1, y.data_ptr(), None, 0,
+                                                    N.BF16, N.stream_ptr(x.device))) if k > k1 else None
+        if k > k1:
+            assert torch.equal(y, got16)
