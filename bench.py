@@ -337,7 +337,9 @@ def main():
         sampler.start()
     barrier()
     e0.record(stream)
+    t_host0 = time.perf_counter()
     run_steps(args.steps, offset=args.warmup)
+    host_issue_ms = (time.perf_counter() - t_host0) * 1e3        # CPU time to enqueue the K steps (no sync inside)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -449,7 +451,7 @@ def main():
                            "batch_per_gpu": B, "global_batch": B * world, "frames": FRAMES, "parallelism": f"dp{world} (windows sharded by rank, no collective)",
                            "l2_policy": f"inputs_larger_than_L2: {n_sets} rotating input sets, {n_sets * bytes_per_set / 1e6:.0f} MB",
                            "cuda_graph": True, "lanes": n_lanes,
-                           "step_latency_ms": step_latency_ms},
+                           "step_latency_ms": step_latency_ms, "host_issue_ms_per_step": host_issue_ms / args.steps},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "imu_only_value": e2e_imu, "api": "CrossModalOODPipeline.stream_host (2-deep ring, host wall clock)",

@@ -43,10 +43,11 @@ constexpr int OFF_K = 32768;                 // K
 constexpr int OFF_VT = 65536;                // V^T
 constexpr int OFF_P = 98304;                 // parameter staging (static block | LN stats | per-layer blocks)
 constexpr int OFF_W = 131072;                // weight ring, NSTAGE chunks
-constexpr int OFF_STAT = OFF_W + NSTAGE * CHUNK;   // LN partial stats [2][128] float2 = 2 KiB
-constexpr int OFF_BAR = OFF_STAT + 2048;     // mbarriers (8 B each) + tmem pointer
+constexpr int OFF_BAR = OFF_W + NSTAGE * CHUNK;    // mbarriers (8 B each) + tmem pointer
 constexpr int SMEM_BYTES = OFF_BAR + 256;
-static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB");
+// 228 KiB per SM, 1 KiB reserved per resident CTA: staying under 226 KiB leaves room for a second, small CTA
+// (the HBM-bound pooling / conversion kernels of other in-flight batches) next to the encoder's.
+static_assert(SMEM_BYTES + 1024 + 2048 <= 233472, "no room left for a co-resident small CTA");
 // fp32 parameters the epilogue needs, staged in shared memory by the producer (with 227 KiB of
 // shared memory the L1 is ~1 KiB, so every __ldg of a bias / LayerNorm vector was an L2 round trip
 // on the critical path).  Static block: once per CTA.  Per-layer block: double buffered.
