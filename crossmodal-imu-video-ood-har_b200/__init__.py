@@ -9,6 +9,7 @@ from .config import default_config
 from .models import (PatchEmbedding, IMUEncoder, VideoEncoder, ProjectionHead, CrossModalModel,
                      IMUClassifier, set_default_precision, get_default_precision)
 from .fusion import LateFusionClassifier, CrossAttentionFusionClassifier, head_scores_native
+from .conv_encoder import ConvIMUEncoder, ConvIMUClassifier
 from .losses import SigmoidContrastiveLoss, InfoNCELoss, similarity_native
 from .ood import (logit_scores, MahalanobisOOD, ScoreHistogram, auroc_fpr95, roc_from_histograms,
                   finalize_mahalanobis)

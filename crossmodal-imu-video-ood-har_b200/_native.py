@@ -51,6 +51,14 @@ class HeadParams(C.Structure):
                    "w2", "b2")]
 
 
+class ConvLayerParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("weight", "bias", "bn_weight", "bn_bias", "bn_mean", "bn_var")]
+
+
+class ConvEncoderParams(C.Structure):
+    _fields_ = [("layer", ConvLayerParams * 3)]
+
+
 _SIGNATURES = {
     "cmhar_abi_version": (C.c_int, []),
     "cmhar_last_error": (C.c_char_p, []),
@@ -81,6 +89,9 @@ _SIGNATURES = {
     "cmhar_cross_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "cmhar_residual_ln_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                          C.c_void_p, C.c_void_p]),
+    "cmhar_conv_encoder_blob_bytes": (C.c_size_t, []),
+    "cmhar_conv_encoder_pack": (C.c_int, [C.POINTER(ConvEncoderParams), C.c_void_p, C.c_void_p]),
+    "cmhar_conv_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "cmhar_video_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]),
     "cmhar_similarity_work_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),

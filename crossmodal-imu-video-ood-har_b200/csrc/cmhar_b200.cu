@@ -13,5 +13,6 @@ namespace cmhar { struct FwdArgs; }
 #include "similarity.cu"
 #include "similarity_tc.cu"
 #include "fusion.cu"
+#include "conv_encoder.cu"
 #include "ood.cu"
 #include "api.cu"

@@ -190,6 +190,23 @@ int cmhar_residual_ln_pool(const float* x, const float* a, const float* gamma, c
                            int64_t n, int32_t s_len, float eps, float* pooled, cmhar_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
+ * 1-D conv / BatchNorm / ReLU IMU encoder (north-star item 1; spec row A6 -- NOT in the reference, whose encoder is
+ * the transformer above; defined in conv_encoder.py, oracle oracle/fusion_spec.py: self-consistency only)
+ *   Conv1d(6->32,k5,s1,p2) BN ReLU, Conv1d(32->64,k5,s2,p2) BN ReLU, Conv1d(64->128,k5,s2,p2) BN ReLU, time mean
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float *weight;            /* (c_out, c_in, 5) */
+    const float *bias;              /* (c_out) or NULL  */
+    const float *bn_weight, *bn_bias, *bn_mean, *bn_var;   /* (c_out) each, or all NULL */
+} cmhar_conv_layer_params;
+typedef struct { cmhar_conv_layer_params layer[3]; } cmhar_conv_encoder_params;
+size_t cmhar_conv_encoder_blob_bytes(void);
+int    cmhar_conv_encoder_pack(const cmhar_conv_encoder_params* p, void* blob, cmhar_stream_t s);
+/* x: window w at x + w*x_window_stride, (6, window) row-major; feat_out (n,128) */
+int    cmhar_conv_encoder_forward(const void* blob, const float* x, int64_t n, int32_t window,
+                                  int64_t x_window_stride, float* feat_out, cmhar_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
  * Video tail (replaces VideoEncoder.forward after the trunk, models.py:210-216:
  *             adaptive_avg_pool2d -> per-frame Linear -> temporal mean == Linear(mean_{t,h,w}))
  * ------------------------------------------------------------------------------------------ */

@@ -83,3 +83,40 @@ def cross_attention_fusion(imu, fmap, sd, frames: int, dims: Dims = Dims(), dtyp
     y = _layer_norm(tokens + o, _t(sd, "norm.weight", dtype), _t(sd, "norm.bias", dtype))
     f = y.mean(1)
     return oracle.classifier_head(f, sd, dims, dtype), f
+
+
+# ------------------------------------------------------------------ conv / BN / ReLU IMU encoder (spec-defined)
+def conv_encoder_state(seed: int, dims: Dims = Dims()) -> Dict[str, np.ndarray]:
+    """Parameters of ``ConvIMUClassifier``: encoder.features.{0,3,6} convs + {1,4,7} BatchNorms + a head."""
+    rs = np.random.RandomState(seed + 600013)
+    sd: Dict[str, np.ndarray] = {}
+    for idx, (cin, cout) in zip((0, 3, 6), ((6, 32), (32, 64), (64, 128))):
+        bound = 1.0 / np.sqrt(cin * 5)
+        sd[f"encoder.features.{idx}.weight"] = (2.0 * rs.uniform(-bound, bound, size=(cout, cin, 5))).astype(np.float32)
+        sd[f"encoder.features.{idx}.bias"] = rs.uniform(-bound, bound, size=cout).astype(np.float32)
+        _batchnorm(rs, cout, f"encoder.features.{idx + 1}", sd)
+    in_dim, idx = dims.d_model, 0
+    for h in dims.head_hidden:
+        _linear(rs, h, in_dim, f"classifier.{idx}", sd)
+        sd[f"classifier.{idx}.weight"] *= 3.0
+        _batchnorm(rs, h, f"classifier.{idx + 1}", sd)
+        in_dim, idx = h, idx + 4
+    _linear(rs, dims.num_classes, in_dim, f"classifier.{idx}", sd)
+    sd[f"classifier.{idx}.weight"] *= 4.0
+    return sd
+
+
+def conv_encoder(x, sd, dtype=torch.float32, prefix: str = "encoder."):
+    """Conv1d(6->32,k5,s1,p2) BN ReLU, Conv1d(32->64,k5,s2,p2) BN ReLU, Conv1d(64->128,k5,s2,p2) BN ReLU, time mean."""
+    h = torch.as_tensor(x).to(dtype)
+    for idx, stride in ((0, 1), (3, 2), (6, 2)):
+        w, b = _t(sd, f"{prefix}features.{idx}.weight", dtype), _t(sd, f"{prefix}features.{idx}.bias", dtype)
+        h = torch.nn.functional.conv1d(h, w, b, stride=stride, padding=2)
+        h = _bn_eval(h.transpose(1, 2), sd, f"{prefix}features.{idx + 1}", dtype).transpose(1, 2)
+        h = torch.relu(h)
+    return h.mean(dim=2)
+
+
+def conv_classifier(x, sd, dims: Dims = Dims(), dtype=torch.float32):
+    f = conv_encoder(x, sd, dtype)
+    return oracle.classifier_head(f, sd, dims, dtype), f

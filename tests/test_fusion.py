@@ -91,3 +91,38 @@ def test_native_fusion_matches_spec(kind, precision, tol):
         finally:
             cm.set_default_precision("fp32")
     assert torch.equal(logits, out["logits"])
+
+
+# ------------------------------------------------------------------ conv / BN / ReLU encoder (spec-defined)
+def build_conv(seed=51):
+    cfg = cm.default_config()
+    sd = fusion_spec.conv_encoder_state(seed)
+    model = cm.ConvIMUClassifier(cfg)
+    model.load_state_dict(tsd(sd), strict=True)
+    return model.eval(), sd
+
+
+def test_conv_encoder_autograd_route_matches_spec():
+    model, sd = build_conv()
+    x = W.imu_windows(4, 5)
+    want, _ = fusion_spec.conv_classifier(x, sd)
+    got = model(torch.from_numpy(x))
+    assert got.requires_grad
+    np.testing.assert_allclose(got.detach().numpy(), want.numpy(), atol=2e-4, rtol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,B", [(250, 77), (100, 33), (256, 300)])
+def test_native_conv_encoder_matches_spec(L, B):
+    model, sd = build_conv()
+    model = model.to("cuda:0")
+    x = W.imu_windows(6, B, W.Dims(imu_window=L))
+    want, want_f = fusion_spec.conv_classifier(x, sd, dtype=torch.float64)
+    out = model.forward_scores(torch.from_numpy(x).cuda(), precision="fp32")
+    torch.cuda.synchronize()
+    rel = lambda g, w: float(np.abs(g.detach().cpu().numpy().astype(np.float64) - w.numpy()).max() / np.abs(w.numpy()).max())
+    assert rel(out["cls"], want_f) < 1e-5
+    assert rel(out["logits"], want) < 1e-4
+    assert np.array_equal(out["pred"].cpu().numpy(), oracle.predict(want))
+    out16 = model.forward_scores(torch.from_numpy(x).cuda(), precision="bf16")      # tensor-core head, same encoder
+    assert rel(out16["logits"], want) < 1e-4

@@ -30,7 +30,8 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "smsp__inst_executed.avg.per_cycle_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warp_latency_issue_stalled_barrier.ratio"]
-for kern, cmdline in (("imu_bf16", "python tools/profile_imu.py 65536 bf16 3"), ("head_tc", "python tools/profile_imu.py 65536 bf16 3")):
+for kern, cmdline in (("imu_bf16", "python tools/profile_imu.py 65536 bf16 3"), ("head_tc", "python tools/profile_imu.py 65536 bf16 3"),
+                      ("linear_tc", "python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-sweep --lanes 1")):
     rep = os.path.join(go, f"prof_{kern}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -38,7 +39,7 @@ for kern, cmdline in (("imu_bf16", "python tools/profile_imu.py 65536 bf16 3"), 
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     with open(os.path.join(out_dir, f"{kern}_kernel_{tag}.md"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on, kernel regex `{kern}` ({tag})\n\ncommand: `{cmdline}` (65 536 windows per launch; 3rd launch captured)\n\n| metric | value | unit |\n|---|---|---|\n")
+        f.write(f"# ncu --set full --clock-control none --import-source on, kernel regex `{kern}` ({tag})\n\ncommand: `{cmdline}` \n\n| metric | value | unit |\n|---|---|---|\n")
         for h, u, v in zip(hdr, units, vals):
             if h in WANT:
                 f.write(f"| {h} | {v} | {u} |\n")
