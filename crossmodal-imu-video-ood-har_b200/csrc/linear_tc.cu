@@ -115,21 +115,29 @@ __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const Args p) {
         const long long r = row0 + row;
         const bool ok = r < p.n;
         uint32_t stage = 0, parity = 1;
-        for (int kc = 0; kc < kc_n; ++kc) {
+        // the global loads of chunk kc+1 are issued before chunk kc is converted and stored: the L2 round trip of the
+        // activation tile is off the per-chunk critical path
+        auto fetch = [&](int kc, float4 (&t)[8]) {
             const int k0 = kc * 64 + half * 32;
-            float4 t[8];
             const float* src = (k0 < p.K1) ? p.x1 + r * p.K1 + k0 : p.x2 + r * (p.K - p.K1) + (k0 - p.K1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) t[i] = ok ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 cur[8], nxt[8];
+        fetch(0, cur);
+        for (int kc = 0; kc < kc_n; ++kc) {
+            if (kc + 1 < kc_n) fetch(kc + 1, nxt);
             float f[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { f[4 * i] = t[i].x; f[4 * i + 1] = t[i].y; f[4 * i + 2] = t[i].z; f[4 * i + 3] = t[i].w; }
+            for (int i = 0; i < 8; ++i) { f[4 * i] = cur[i].x; f[4 * i + 1] = cur[i].y; f[4 * i + 2] = cur[i].z; f[4 * i + 3] = cur[i].w; }
             mbar_wait(BAR(B_AEMPTY + stage), parity, 83);
             store_bf16_32(smem + OFF_A + stage * CHUNK, row, half * 4, f);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_AFULL + stage));
             if (++stage == NS) { stage = 0; parity ^= 1; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
         }
         mbar_wait(BAR(B_ACC), 0, 84);
         tc_fence_after();
