@@ -15,4 +15,5 @@ namespace cmhar { struct FwdArgs; }
 #include "fusion.cu"
 #include "conv_encoder.cu"
 #include "ood.cu"
+#include "maha_fit_tc.cu"
 #include "api.cu"

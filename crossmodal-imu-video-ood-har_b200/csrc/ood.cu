@@ -295,7 +295,11 @@ __global__ void __launch_bounds__(256) score_histogram_kernel(const float* __res
 
 }  // namespace cmhar
 
-namespace cmhar { int launch_head_forward(const FwdArgs& a, int precision, cudaStream_t stream); }
+namespace cmhar {
+int launch_head_forward(const FwdArgs& a, int precision, cudaStream_t stream);                                  // head.cu
+int launch_maha_fit_tc(const float* feat, const long long* labels, long long n, int C, double* count, double* sum, double* second,
+                       cudaStream_t st);                                                                         // maha_fit_tc.cu
+}
 
 using namespace cmhar;
 
@@ -356,10 +360,13 @@ int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float*
 }
 
 int cmhar_maha_accumulate(const float* feat, const int64_t* labels, int64_t n, int32_t classes, double* count,
-                          double* sum, double* second, cmhar_stream_t s) {
+                          double* sum, double* second, int32_t precision, cmhar_stream_t s) {
     CMHAR_REQUIRE(feat && labels && count && sum && second, "cmhar_maha_accumulate: null argument");
     CMHAR_REQUIRE(classes >= 1 && classes <= 64, "classes=%d outside [1,64]", classes);
+    CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
     if (n <= 0) return CMHAR_OK;
+    if (precision == CMHAR_BF16 && ((uintptr_t)feat & 15) == 0)       // both reductions as split-bf16 tcgen05 GEMMs over the rows
+        return launch_maha_fit_tc(feat, reinterpret_cast<const long long*>(labels), n, classes, count, sum, second, (cudaStream_t)s);
     const size_t smem = sizeof(double) * ((size_t)D * D + (size_t)classes * D + ((classes + 1) & ~1)) + sizeof(float) * MA_ROWS * D + sizeof(int) * MA_ROWS;
     static bool configured[64] = {};
     int dev = 0;

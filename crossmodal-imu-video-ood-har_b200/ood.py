@@ -25,6 +25,11 @@ __all__ = ["logit_scores", "MahalanobisOOD", "ScoreHistogram", "auroc_fpr95", "f
 FEAT_DIM = 128
 
 
+def _prec(precision: Optional[str]) -> int:
+    from .models import _prec_code
+    return _prec_code(precision)
+
+
 def _dist_on() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
@@ -93,7 +98,9 @@ class MahalanobisOOD:
                 self._stats[c + c * FEAT_DIM:].view(FEAT_DIM, FEAT_DIM))
 
     @torch.no_grad()
-    def accumulate(self, feats: torch.Tensor, labels: torch.Tensor) -> None:
+    def accumulate(self, feats: torch.Tensor, labels: torch.Tensor, precision: Optional[str] = None) -> None:
+        """Adds the rows' sufficient statistics.  precision 'bf16' = the tensor-core kernel (split-bf16 GEMMs over the
+        row dimension, fp32-grade sums); 'fp32' = CUDA-core FMA tiles."""
         N.require_cuda(feats, "MahalanobisOOD.accumulate")
         f = N.f32c(feats)
         y = labels.to(device=f.device, dtype=torch.int64).contiguous()
@@ -103,7 +110,7 @@ class MahalanobisOOD:
         with torch.cuda.device(f.device):
             N.check(N.lib().cmhar_maha_accumulate(f.data_ptr(), y.data_ptr(), f.shape[0], self.num_classes,
                                                   cnt.data_ptr(), ssum.data_ptr(), second.data_ptr(),
-                                                  N.stream_ptr(f.device)))
+                                                  _prec(precision), N.stream_ptr(f.device)))
 
     def finalize(self) -> "MahalanobisOOD":
         stats = self._stats

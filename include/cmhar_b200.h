@@ -241,9 +241,11 @@ int cmhar_similarity(const float* a, const float* b, int64_t na, int64_t nb, int
 /* Accumulates (+=) sufficient statistics of feat (n,128) fp32 with int64 labels:
  * count (classes) double, sum (classes,128) double, second (128,128) double = sum f f^T.
  * Rows whose label is outside [0,classes) are skipped.  These three buffers are what the
- * multi-GPU fit all-reduces over NCCL. */
+ * multi-GPU fit all-reduces over NCCL.  CMHAR_BF16: both reductions run as split-bf16 tcgen05 GEMMs over the row
+ * dimension (all four hi/lo products for the second moment, fp32 accumulation in TMEM flushed in fp64);
+ * CMHAR_FP32: fp32 FMA register tiles flushed into fp64. */
 int cmhar_maha_accumulate(const float* feat, const int64_t* labels, int64_t n, int32_t classes,
-                          double* count, double* sum, double* second, cmhar_stream_t s);
+                          double* count, double* sum, double* second, int32_t precision, cmhar_stream_t s);
 /* score (n) = min_c || feat@whiten - mean_whitened_c ||^2.  CMHAR_BF16: whitening and class-mean products as
  * split-bf16 tcgen05 MMAs (fp32-grade, see cmhar_head_forward) when classes <= 32; CMHAR_FP32: fp32 FMA. */
 int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float* score, int32_t precision,

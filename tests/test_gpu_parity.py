@@ -264,6 +264,15 @@ def test_mahalanobis_fit_and_score_vs_spec():
     r = cm.auroc_fpr95(torch.from_numpy(got[ql >= 0]).to(DEV), torch.from_numpy(got[ql < 0]).to(DEV))
     assert round(r["auroc"], 3) == round(ood_spec.auroc(want[ql >= 0], want[ql < 0]), 3)
     assert round(r["fpr"], 3) == round(ood_spec.fpr_at_tpr_fast(want[ql >= 0], want[ql < 0]), 3)
+    # the tensor-core FIT kernel (split-bf16 GEMMs over the row dimension): same statistics
+    m2 = cm.MahalanobisOOD(32, DEV)
+    m2.accumulate(f[:7000], y[:7000], precision="bf16")
+    m2.accumulate(f[7000:7001], y[7000:7001], precision="bf16")
+    m2.accumulate(f[7001:], y[7001:], precision="bf16")
+    m2.finalize()
+    np.testing.assert_allclose(m2.fit_["count"], spec["count"])
+    np.testing.assert_allclose(m2.fit_["mean"], spec["mean"], atol=2e-6)
+    np.testing.assert_allclose(m2.fit_["cov"], spec["cov"], atol=2e-5)
     # the tensor-core score kernel (split-bf16 MMAs): same contract, same AUROC / FPR95
     got_tc = m.score(torch.from_numpy(q).to(DEV), precision="bf16").cpu().numpy()
     assert rel_err(got_tc, want) < 2e-4

@@ -63,8 +63,9 @@ for PREC, pname in ((0, "fp32 FMA"), (1, "tcgen05 split-bf16")):
     f = lambda: N.check(lib.cmhar_maha_score(maha.blob(dev).data_ptr(), feat.data_ptr(), n, score.data_ptr(), PREC, st()))
     report(f"maha_score n={n} [{pname}]", timeit(f, 10), n * (512 + 4))
 cnt = torch.zeros(32, dtype=torch.float64, device=dev); ssum = torch.zeros(32, 128, dtype=torch.float64, device=dev); sec = torch.zeros(128, 128, dtype=torch.float64, device=dev)
-f = lambda: N.check(lib.cmhar_maha_accumulate(feat.data_ptr(), lab.data_ptr(), n, 32, cnt.data_ptr(), ssum.data_ptr(), sec.data_ptr(), st()))
-report(f"maha_accumulate n={n}", timeit(f, 10), n * (512 + 8))
+for PREC, pname in ((0, "fp32 FMA"), (1, "tcgen05 split-bf16")):
+    f = lambda: N.check(lib.cmhar_maha_accumulate(feat.data_ptr(), lab.data_ptr(), n, 32, cnt.data_ptr(), ssum.data_ptr(), sec.data_ptr(), PREC, st()))
+    report(f"maha_accumulate n={n} [{pname}]", timeit(f, 10), n * (512 + 8))
 cfg = cm.default_config()
 clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg).to(dev).eval()
 hb = clf._head_blob(dev)
