@@ -281,7 +281,7 @@ def main():
     fit_f = torch.relu(torch.randn(2048 * FRAMES, FEAT_C, FEAT_HW, FEAT_HW, device=dev, generator=gfit)).to(torch.bfloat16)
     fit_y = torch.randint(0, 32, (2048,), device=dev, generator=gfit)
     maha = cm.MahalanobisOOD(32, dev, ridge=1e-3)
-    maha.accumulate(fus.forward_scores(fit_x, fit_f, FRAMES, precision=precision)["fused"], fit_y)
+    maha.accumulate(fus.forward_scores(fit_x, fit_f, FRAMES, precision=precision)["fused"], fit_y, precision=precision)
     maha.finalize()
     del fit_f
     pipe = cm.CrossModalOODPipeline(clf, xm, maha, frames=FRAMES, precision=precision, fusion=fus)

@@ -159,7 +159,7 @@ class Evaluator:
                 x = self._upload(batch["imu"], i & 1)
                 res = self.model.forward_scores(x, precision=self.precision, want_cls=True, want_logits=False,
                                                 window_stride=x.stride(0) if x.dim() == 2 else None)
-                maha.accumulate(res["cls"], torch.as_tensor(batch["label"]))
+                maha.accumulate(res["cls"], torch.as_tensor(batch["label"]), precision=self.precision)
         maha.finalize()
         self.model.set_mahalanobis(maha)
         return maha
