@@ -14,6 +14,7 @@ namespace cmhar { struct FwdArgs; }
 #include "similarity_tc.cu"
 #include "fusion.cu"
 #include "conv_encoder.cu"
+#include "maha_score_tc.cu"
 #include "ood.cu"
 #include "maha_fit_tc.cu"
 #include "api.cu"

@@ -138,8 +138,12 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restri
 // One thread per (b, c); adjacent threads read adjacent hw-blocks, so a warp's request is one
 // contiguous 32*hw*sizeof(T) span per frame (1 KiB for bf16 4x4).  All `frames` loads of a
 // thread are independent and unrolled to keep >= 256 B in flight per thread (HBM-bound stage).
+// 128-thread CTAs (4 warps x 40 registers = 5 K registers, no shared memory): small enough to become resident on
+// an SM whose tensor-core CTA (the encoder: 320 threads x 168 registers, 224 KiB of shared memory) leaves only
+// ~9 K registers and 2.8 KiB free, so the HBM-bound pooling of one batch overlaps the encoder of another.
+constexpr int POOL_NT = 128;
 template <typename T, int VEC /* elements per 16-byte vector, 0 = scalar path */>
-__global__ void __launch_bounds__(256) video_pool_kernel(const T* __restrict__ fmap, long long n, int frames,
+__global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict__ fmap, long long n, int frames,
                                                          int channels, int hw, float* __restrict__ pooled) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= channels) return;
@@ -294,18 +298,18 @@ int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frame
     CMHAR_REQUIRE(fmap && pooled && frames > 0 && channels > 0 && hw > 0, "cmhar_video_pool: bad argument");
     if (n <= 0) return CMHAR_OK;
     cudaStream_t st = (cudaStream_t)s;
-    dim3 grid((channels + 255) / 256, (unsigned)(n < 32768 ? n : 32768));
+    dim3 grid((channels + POOL_NT - 1) / POOL_NT, (unsigned)(n < 32768 ? n : 32768));
     const bool aligned = ((uintptr_t)fmap & 15) == 0;
     if (is_bf16) {
         if (aligned && hw % 8 == 0)
-            video_pool_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled);
+            video_pool_kernel<__nv_bfloat16, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled);
         else
-            video_pool_kernel<__nv_bfloat16, 0><<<grid, 256, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled);
+            video_pool_kernel<__nv_bfloat16, 0><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled);
     } else {
         if (aligned && hw % 4 == 0)
-            video_pool_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled);
+            video_pool_kernel<float, 4><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled);
         else
-            video_pool_kernel<float, 0><<<grid, 256, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled);
+            video_pool_kernel<float, 0><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled);
     }
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;

@@ -6,8 +6,94 @@
 //   A4 score    min_c || f W - mu_c W ||^2    (W = whitening factor of the tied covariance)
 //   A5 AUROC/FPR95 from order-preserving score histograms
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cmhar {
+
+// ---- A1/A2 from stored logits, C = 32 (the reference head): TMA-fed ring, one thread per row -----------------
+// HBM-bound (128 B in, 16 B out per row).  The group-of-lanes kernel below spends ~480 lane-instructions per row
+// on shuffles and redundant bookkeeping and sits at 60 % of the copy bandwidth; here a producer lane streams
+// 16 KiB tiles (128 rows) into a 4-stage shared-memory ring with cp.async.bulk (no registers, no per-thread
+// address arithmetic for the loads) and each consumer thread owns one row of a tile: 8 conflict-free 16-byte
+// shared loads (piece order rotated by row & 7), max / arg-max / sum-exp entirely in registers, three coalesced
+// stores.  ~4x fewer instructions per row, and the bytes in flight no longer depend on warp scheduling.
+namespace lsring {
+using namespace tc;
+constexpr int ROWS = 128, CLS = 32, TILE_BYTES = ROWS * CLS * 4, NSTAGE = 4;
+constexpr int OFF_BAR = NSTAGE * TILE_BYTES, SMEM_BYTES = OFF_BAR + 64;
+constexpr int NT = ROWS + 32;
+
+__global__ void __launch_bounds__(NT) logit_scores_ring_kernel(const float* __restrict__ logits, long long n, float invT, float T,
+                                                               long long* __restrict__ pred, float* __restrict__ msp,
+                                                               float* __restrict__ energy) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = smem_u32(smem), bar0 = sbase + OFF_BAR;
+    auto FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(NSTAGE + s); };
+    const long long tiles = (n + ROWS - 1) / ROWS;
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), ROWS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == ROWS / 32) {
+        if (lane == 0) {                                   // producer
+            uint32_t stage = 0, parity = 1;
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                mbar_wait(EMPTY(stage), parity, 95);
+                const long long r0 = tile * ROWS;
+                const uint32_t bytes = (uint32_t)((n - r0 < ROWS ? n - r0 : ROWS) * (CLS * 4));
+                mbar_expect_tx(FULL(stage), bytes);
+                bulk_g2s(sbase + stage * TILE_BYTES, logits + r0 * CLS, bytes, FULL(stage));
+                if (++stage == NSTAGE) { stage = 0; parity ^= 1; }
+            }
+        }
+        return;
+    }
+    uint32_t stage = 0, parity = 0;
+    const float4* myrow_base = reinterpret_cast<const float4*>(smem) + tid * (CLS / 4);
+    const int rot = tid & 7;
+    const float kInvT2 = invT * LOG2E;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(FULL(stage), parity, 96);
+        const long long r = tile * ROWS + tid;
+        float4 v[8];
+        const float4* src = myrow_base + stage * (TILE_BYTES / 16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = src[j ^ rot];            // v[j] holds classes 4 (j ^ rot) ..
+        __syncwarp();
+        if (lane == 0) mbar_arrive(EMPTY(stage));                   // the row is in registers: the slot may be refilled
+        if (++stage == NSTAGE) { stage = 0; parity ^= 1; }
+        if (r >= n) continue;
+        float m = -INFINITY;
+        int idx = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                               // first maximal index (torch max(1)): ties -> lowest class
+            const int c0 = 4 * (j ^ rot);
+            const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (x[e] > m || (x[e] == m && c0 + e < idx)) { m = x[e]; idx = c0 + e; }
+        }
+        float s1 = 0.f, sT = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                               // (v - m) first: exact at the maximum, no cancellation later
+            v[j].x -= m; v[j].y -= m; v[j].z -= m; v[j].w -= m;
+            s1 += ex2_approx(v[j].x * LOG2E) + ex2_approx(v[j].y * LOG2E) + ex2_approx(v[j].z * LOG2E) + ex2_approx(v[j].w * LOG2E);
+        }
+        if (invT == 1.f) sT = s1;
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                sT += ex2_approx(v[j].x * kInvT2) + ex2_approx(v[j].y * kInvT2) + ex2_approx(v[j].z * kInvT2) + ex2_approx(v[j].w * kInvT2);
+        }
+        if (pred) pred[r] = idx;
+        if (msp) msp[r] = -1.f / s1;
+        if (energy) energy[r] = -(m + T * __logf(sT));
+    }
+}
+}  // namespace lsring
 
 // ---- A1/A2 from stored logits (HBM-bound: 128 B in, 16 B out per row at C = 32) ---------------------------
 // Fast path (C % 4 == 0, C <= 128): a group of G = C/4 lanes owns a row, every lane loads one float4, so a warp
@@ -299,6 +385,7 @@ namespace cmhar {
 int launch_head_forward(const FwdArgs& a, int precision, cudaStream_t stream);                                  // head.cu
 int launch_maha_fit_tc(const float* feat, const long long* labels, long long n, int C, double* count, double* sum, double* second,
                        cudaStream_t st);                                                                         // maha_fit_tc.cu
+int launch_maha_score_tc(const uint8_t* section, const float* feat, long long n, float* score, cudaStream_t st);   // maha_score_tc.cu
 }
 
 using namespace cmhar;
@@ -314,7 +401,18 @@ int cmhar_logit_scores(const float* logits, int64_t n, int32_t classes, float te
     cudaStream_t st = (cudaStream_t)s;
     const int G = classes / 4;
     const bool vec = (classes % 4 == 0) && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && ((uintptr_t)logits & 15) == 0;
-    if (vec) {
+    if (classes == lsring::CLS && ((uintptr_t)logits & 15) == 0) {
+        static bool configured[64] = {};
+        int dev = 0;
+        CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
+        if (!configured[dev & 63]) {
+            CMHAR_CHECK_CUDA(cudaFuncSetAttribute(lsring::logit_scores_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lsring::SMEM_BYTES));
+            configured[dev & 63] = true;
+        }
+        const long long tiles = (n + lsring::ROWS - 1) / lsring::ROWS;
+        const unsigned grid = (unsigned)(tiles < 3LL * sm_count() ? tiles : 3LL * sm_count());      // 3 x 64 KiB rings per SM
+        lsring::logit_scores_ring_kernel<<<grid, lsring::NT, lsring::SMEM_BYTES, st>>>(logits, n, invT, temperature, pred, msp_out, energy_out);
+    } else if (vec) {
         const long long rows_per_block = 8LL * (32 / G) * 4;
         const long long want = (n + rows_per_block - 1) / rows_per_block;
         const unsigned grid = (unsigned)(want < 16LL * sm_count() ? want : 16LL * sm_count());
@@ -338,7 +436,13 @@ int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float*
     CMHAR_REQUIRE(maha_blob && feat && score, "cmhar_maha_score: null argument");
     CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
     if (n <= 0) return CMHAR_OK;
-    if (precision == CMHAR_BF16) {       // tensor-core kernel (whitening + class-mean products as split-bf16 MMAs) when eligible
+    if (precision == CMHAR_BF16) {       // tensor-core kernels (whitening + class-mean products as split-bf16 MMAs) when eligible
+        BlobInfo mi{};
+        if (((uintptr_t)feat & 15) == 0 && lookup_blob(maha_blob, &mi) && mi.magic == MAHA_MAGIC && mi.has_tc) {
+            // streaming kernel: one N=160 GEMM against the resident [W | G] image + per-row reduction
+            const uint8_t* sec = reinterpret_cast<const uint8_t*>(maha_blob) + tc_section_offset(MahaLayout{mi.a}.total()) + maha_score_section_offset();
+            return launch_maha_score_tc(sec, feat, n, score, (cudaStream_t)s);
+        }
         FwdArgs a{};
         a.maha_blob = reinterpret_cast<const char*>(maha_blob);
         a.x = feat; a.n = n; a.xstride = D; a.maha_out = score;

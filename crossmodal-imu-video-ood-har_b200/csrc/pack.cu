@@ -40,6 +40,10 @@ bool lookup_blob(const void* blob, BlobInfo* info) {
 bool head_tc_eligible(int h1, int h2, int C);                                                   // head_tc.cu
 size_t head_tc_bytes();
 size_t maha_tc_bytes();
+size_t maha_score_tc_bytes();
+int pack_maha_score_tc(const float* f32, const MahaLayout& ml, uint8_t* dst, cudaStream_t st);              // maha_score_tc.cu
+// the streaming score kernel's [W | G] image sits behind the head kernel's maha section, 1 KiB aligned
+inline size_t maha_score_section_offset() { return (maha_tc_bytes() + 1023) / 1024 * 1024; }
 int pack_head_tc(const float* f32, const HeadLayout& hl, uint8_t* dst, cudaStream_t st);
 int pack_maha_tc(const float* f32, const MahaLayout& ml, uint8_t* dst, cudaStream_t st);
 
@@ -209,7 +213,7 @@ int cmhar_head_pack(const cmhar_head_params* p, void* blob, cmhar_stream_t s) {
 size_t cmhar_maha_blob_bytes(int32_t C) {
     if (C < 1 || C > 1024) return 0;
     MahaLayout ml{C};
-    return tc_section_offset(ml.total()) + (C <= 32 ? maha_tc_bytes() : 0);
+    return tc_section_offset(ml.total()) + (C <= 32 ? maha_score_section_offset() + maha_score_tc_bytes() : 0);
 }
 
 int cmhar_maha_pack(const float* whiten, const float* mean_whitened, const float* class_count, int32_t C,
@@ -228,6 +232,7 @@ int cmhar_maha_pack(const float* whiten, const float* mean_whitened, const float
     if (C <= 32) {
         h.has_bf16 = 1;
         TRY(pack_maha_tc(f, ml, reinterpret_cast<uint8_t*>(blob) + tc_section_offset(ml.total()), st));
+        TRY(pack_maha_score_tc(f, ml, reinterpret_cast<uint8_t*>(blob) + tc_section_offset(ml.total()) + maha_score_section_offset(), st));
     }
     register_blob(blob, BlobInfo{MAHA_MAGIC, C, 0, 0, h.has_bf16});
     return write_header(blob, h, st);

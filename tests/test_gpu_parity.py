@@ -165,6 +165,19 @@ def test_logit_scores_from_stored_logits():
     z = torch.zeros(4, 40, device=DEV)
     z[1, 7] = z[1, 33] = 2.0
     assert cm.logit_scores(z)["pred"].tolist() == [0, 7, 0, 0]
+    # C = 32: the TMA-ring kernel (one thread per row, rotated piece order) -- ties, ragged tail, many tiles per CTA
+    z = torch.zeros(300, 32, device=DEV)
+    z[1, 7] = z[1, 31] = 2.0
+    z[2, 31] = 1.0
+    z[129, 4] = z[129, 5] = z[129, 30] = 3.0
+    p32 = cm.logit_scores(z)["pred"].tolist()
+    assert p32[:3] == [0, 7, 31] and p32[129] == 4 and p32[299] == 0
+    for n, T in ((250_001, 1.0), (3 * 148 * 128 * 5 + 17, 0.5)):
+        big = (4.0 * np.random.RandomState(n % 1000).standard_normal((n, 32))).astype(np.float32)
+        s = cm.logit_scores(torch.from_numpy(big).to(DEV), temperature=T)
+        np.testing.assert_allclose(s["energy"].cpu().numpy(), ood_spec.energy_score(big, T=T), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(s["msp"].cpu().numpy(), ood_spec.msp_score(big), rtol=1e-5, atol=1e-7)
+        assert np.array_equal(s["pred"].cpu().numpy(), big.argmax(1))
 
 
 def test_cross_modal_and_losses_vs_reference_golden(golden_dir):
@@ -278,6 +291,27 @@ def test_mahalanobis_fit_and_score_vs_spec():
     assert rel_err(got_tc, want) < 2e-4
     r2 = cm.auroc_fpr95(torch.from_numpy(got_tc[ql >= 0]).to(DEV), torch.from_numpy(got_tc[ql < 0]).to(DEV))
     assert round(r2["auroc"], 3) == round(r["auroc"], 3) and round(r2["fpr"], 3) == round(r["fpr"], 3)
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 5003, 148 * 128 * 3 + 5])
+def test_streaming_mahalanobis_score_kernel(n):
+    """maha_score_tc_kernel (one N=160 split-bf16 GEMM against the resident [W | G] image + per-row reduction):
+    ragged tails, single-row input, more than two tiles per persistent CTA (both accumulators / staging buffers
+    wrap), classes without training rows (their distance must never win)."""
+    feats, labels = W.class_features(7, 6000)
+    labels = labels.copy()
+    labels[labels == 3] = 5                                       # class 3 has no rows
+    m = cm.MahalanobisOOD(32, DEV, ridge=1e-3).fit(torch.from_numpy(feats).to(DEV), torch.from_numpy(labels).to(DEV))
+    spec = ood_spec.mahalanobis_finalize(*ood_spec.mahalanobis_sufficient_stats(feats, labels, 32), ridge=1e-3)
+    q, _ = W.class_features(9, n, ood_fraction=0.5)
+    want = ood_spec.mahalanobis_score(q, spec)
+    qd = torch.from_numpy(q).to(DEV)
+    got = m.score(qd, precision="bf16")
+    torch.cuda.synchronize()
+    assert got.shape == (n,)
+    assert rel_err(got, want) < 2e-4
+    ref32 = m.score(qd, precision="fp32")                         # the fp32 CUDA-core kernel: same contract
+    assert rel_err(got, ref32) < 2e-4
 
 
 def test_auroc_fpr95_vs_spec_continuous_tied_and_separated():
