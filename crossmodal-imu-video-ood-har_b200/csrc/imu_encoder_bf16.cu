@@ -62,8 +62,9 @@ enum {
     B_WEMPTY = B_WFULL + NSTAGE, // [NSTAGE]
     B_ACC = B_WEMPTY + NSTAGE,   // [4] accumulator buffer A,B,C,R complete (tcgen05.commit)
     B_HA = B_ACC + 4,            // hA (+R) written by the epilogue        (256)
-    B_QKV = B_HA + 1,            // Q,K,V^T in smem, P zeroed              (256)
-    B_P = B_QKV + 1,             // P (all heads) in smem                  (256)
+    B_QKV = B_HA + 1,            // Q in TMEM, K in smem: the score MMAs may start
+    B_V = B_QKV + 1,             // V^T in smem (drained while the score MMAs run)
+    B_P = B_V + 1,             // P (all heads) in smem                  (256)
     B_O = B_P + 1,               // O in smem                              (256)
     B_HID = B_O + 1,             // [4] hidden chunk c in smem (one barrier per chunk: a waiter may never fall two phases behind)
     B_PBFULL = B_HID + 4,        // [2] per-layer parameter block landed   (tx)
@@ -102,7 +103,7 @@ constexpr int TLOG_CAP = 1024;
 
 // ======================================================================================== kernel
 template <int NQ>
-__global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(const Bf16Args args) {
+__global__ void __maxnreg__(NQ == 2 ? 152 : 104) imu_forward_bf16_kernel(const Bf16Args args) {
     constexpr int NT_EPI = 128 * NQ, CW = 128 / NQ, MMA_WARP = 4 * NQ, LOAD_WARP = 4 * NQ + 1;
     auto epi_bar = [] { epi_bar_n<NT_EPI>(); };
     extern __shared__ __align__(1024) uint8_t smem_tc[];
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
         // epilogue -> MMA barriers: ONE arrival per epilogue warp (lane 0 after __syncwarp), not per thread
         mbar_init(BAR(B_HA), NT_EPI / 32);
         mbar_init(BAR(B_QKV), NT_EPI / 32);
+        mbar_init(BAR(B_V), NT_EPI / 32);
         mbar_init(BAR(B_P), NT_EPI / 32);
         mbar_init(BAR(B_O), NT_EPI / 32);
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_HID + i), NT_EPI / 32);
@@ -246,6 +248,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                     }
                     if (leader) tc_commit(BAR(B_ACC + 1));
                     // O[r][16h + d] = sum_k P[r][16h + k] * V_h[key k of r's window][d]
+                    mbar_wait(BAR(B_V), ph.next(B_V), 7);
                     PROG(6); mbar_wait(BAR(B_P), ph.next(B_P), 6); PROG(1006);
                     tc_fence_after();
 #pragma unroll
@@ -486,9 +489,10 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) imu_forward_bf16_kernel(cons
                         if (m == 0) store_tmem_bf16(lane_base + TM_A + c0 + (cc >> 1), f);
                         else if (!(args.ablate & ABL_NO_STS)) store_bf16_32(dst + chunk_of(c0 + cc), row, piece_of(c0 + cc), f);
                     }
+                    if (m == 1) publish(B_QKV);      // Q and K are in place: the score MMAs overlap the V^T drain
                 }
                 PROG(100 + l);
-                publish(B_QKV);
+                publish(B_V);
                 // ---- softmax: this thread owns the heads whose 16 compact scores fall into its CW columns
                 PROG(13); mbar_wait(BAR(B_ACC + 1), ph.next(B_ACC + 1), 13); PROG(1013);
                 tc_fence_after();

@@ -13,12 +13,13 @@
 // products exact to ~2^-17, so the score is fp32-grade although the tensor cores only take bf16.
 //
 // Persistent CTA per SM, three roles that overlap tile by tile:
-//   * 8 staging warps: coalesced 512-byte row loads (16 rows in flight per warp), split into hi / lo bf16 and
-//     stored as K-major SWIZZLE_128B A tiles (8-byte stores, conflict-free), double buffered; the loads of tile
-//     i+1 are issued while tile i is being converted;
-//   * 1 MMA warp: 24 tcgen05.mma (M=128, N=160, K=16) per tile against the [W | G] image that stays RESIDENT in
-//     shared memory (80 KiB, loaded once per CTA by cp.async.bulk) into one of two TMEM accumulators;
-//   * 4 epilogue warps: thread = row; |y|^2 over 128 columns, min over the 32 class columns, one 4-byte store.
+//   * 2 x 8 staging warps: coalesced 512-byte row loads (16 rows in flight per warp), split into hi / lo bf16 and
+//     stored as K-major SWIZZLE_128B A tiles (8-byte stores, conflict-free); the two groups work on alternate
+//     tiles (= alternate A buffers), one converting while the other's loads are in flight;
+//   * 4 epilogue warps: thread = row; |y|^2 over 128 columns, min over the 32 class columns, one 4-byte store;
+//     the first of them also issues the MMAs, one tile ahead of the accumulator it drains: 24 tcgen05.mma (M=128,
+//     N=160, K=16) per tile against the [W | G] image that stays RESIDENT in shared memory (80 KiB, loaded once
+//     per CTA by cp.async.bulk) into one of two TMEM accumulators.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -35,7 +36,15 @@ constexpr int ABUF = 4 * ACH;                         // hi (2 chunks) | lo (2 c
 constexpr int OFF_W = 0, OFF_A = W_BYTES, OFF_BAR = OFF_A + 2 * ABUF, OFF_MUN = OFF_BAR + 128, SMEM_BYTES = OFF_MUN + 128;
 static_assert(OFF_A % 1024 == 0 && SMEM_BYTES <= 232448, "shared memory map");
 enum { B_W = 0, B_STAGED = 1, B_FREE = 3, B_ACCFULL = 5, B_ACCFREE = 7, B_COUNT = 9 };
-constexpr int N_STAGE_WARPS = 8, EPI_WARP0 = 8, MMA_WARP = 12, NT = 13 * 32;
+// Role layout, templated for the variants compared in tools/bench_hbm_kernels.py (CMHAR_MAHA_VARIANT):
+//   GROUPS  staging groups of 8 warps (group g stages this CTA's tiles g, g + GROUPS, ...)
+//   MERGED  the MMAs are issued by epilogue warp 0 (one tile ahead of the accumulator it drains) instead of a
+//           dedicated warp -- 20 warps = 5 per SM sub-partition leave 96 registers per thread, 21 leave 80
+constexpr int ROWS_PER_WARP = 16;
+template <int GROUPS, bool MERGED> struct Roles {
+    static constexpr int STAGE_WARPS = 8 * GROUPS, EPI_WARP0 = STAGE_WARPS, MMA_WARP = MERGED ? EPI_WARP0 : EPI_WARP0 + 4;
+    static constexpr int NT = (STAGE_WARPS + 4 + (MERGED ? 0 : 1)) * 32;
+};
 constexpr uint32_t ACC_STRIDE = 256;                  // TMEM columns between the two accumulators (160 used)
 constexpr size_t SECTION_BYTES = W_BYTES + 32 * sizeof(float);      // image + |mu_c W|^2 (inf: empty / padding class)
 
@@ -79,8 +88,37 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(NT, 1) maha_score_tc_kernel(const uint8_t* __restrict__ section, const float* __restrict__ feat,
-                                                              long long n, float* __restrict__ score) {
+// convert this warp's rows of one tile (registers t) into the hi / lo A tiles of buffer `abuf`
+template <int ROWS>
+__device__ __forceinline__ void stage_rows(const float4 (&t)[ROWS], uint8_t* abuf, int row0, int piece, int sub) {
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        const float4 x = t[j];
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+        const uint32_t off = sw128_off(row0 + j, piece) + sub;
+        *reinterpret_cast<uint2*>(abuf + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        *reinterpret_cast<uint2*>(abuf + 2 * ACH + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+}
+// this warp's rows of a tile -> registers: src = address of (first row, this lane's 4 elements); rows past
+// `valid` read as zero
+template <int ROWS>
+__device__ __forceinline__ void load_rows(float4 (&t)[ROWS], const float* __restrict__ src, int valid) {
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < valid) t[j] = ld_stream(src + j * D);
+    }
+}
+
+template <int GROUPS, bool MERGED, bool CFENCE>
+__global__ void __launch_bounds__(Roles<GROUPS, MERGED>::NT, 1) maha_score_tc_kernel(const uint8_t* __restrict__ section,
+                                                                                     const float* __restrict__ feat, long long n,
+                                                                                     float* __restrict__ score) {
+    using R = Roles<GROUPS, MERGED>;
+    constexpr int N_STAGE_WARPS = R::STAGE_WARPS, EPI_WARP0 = R::EPI_WARP0, MMA_WARP = R::MMA_WARP;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = smem_u32(smem), bar0 = sbase + OFF_BAR;
@@ -91,7 +129,7 @@ __global__ void __launch_bounds__(NT, 1) maha_score_tc_kernel(const uint8_t* __r
     if (tid == 0) {
         mbar_init(BAR(B_W), 1);
         for (int b = 0; b < 2; ++b) {
-            mbar_init(BAR(B_STAGED + b), N_STAGE_WARPS);
+            mbar_init(BAR(B_STAGED + b), 8);
             mbar_init(BAR(B_FREE + b), 1);
             mbar_init(BAR(B_ACCFULL + b), 1);
             mbar_init(BAR(B_ACCFREE + b), 4);
@@ -107,24 +145,81 @@ __global__ void __launch_bounds__(NT, 1) maha_score_tc_kernel(const uint8_t* __r
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == MMA_WARP) {
-        // ================================================================= MMA issuer
-        const bool leader = elect_one();
-        if (leader) {                                   // the [W | G] image: resident for the life of the CTA
-            mbar_expect_tx(BAR(B_W), W_BYTES);
-            for (int q = 0; q < 4; ++q) bulk_g2s(sbase + OFF_W + q * BCH, section + (size_t)q * BCH, BCH, BAR(B_W));
+    if (warp < N_STAGE_WARPS) {
+        // ================================================================= staging: fp32 rows -> split-bf16 A tiles
+        // Two groups of 8 warps, out of phase: group g stages this CTA's tiles g, g+2, ... into A buffer g; inside a
+        // group warp w owns rows 16 w .. 16 w + 15 and lane l holds elements [4 l, 4 l + 4) of a row.  A step is:
+        // convert + store the rows held in registers, proxy fence, arrive, THEN issue the loads of the group's next
+        // tile -- the fence is a MEMBAR that would otherwise wait for every load still in flight -- so one group
+        // converts while the other group's 64 KiB are on their way from HBM.
+        const int g = warp >> 3, gw = warp & 7;
+        const int kc = lane >> 4, piece = (lane & 15) >> 1, sub = (lane & 1) * 8;
+        const int row0 = gw * ROWS_PER_WARP;
+        float4 t[ROWS_PER_WARP];
+        // 32-bit tile bookkeeping (tiles < 2^31 checked by the launcher) keeps this role inside its register budget
+        const int ntiles = (int)tiles, step = GROUPS * (int)gridDim.x;
+        const float* lane_src = feat + (size_t)row0 * D + 4 * lane;
+        auto fetch = [&](int tile) __attribute__((always_inline)) {
+            const long long left = n - ((long long)tile * 128 + row0);
+            load_rows<ROWS_PER_WARP>(t, lane_src + (size_t)tile * (128 * D), left < ROWS_PER_WARP ? (int)left : ROWS_PER_WARP);
+        };
+        int tile = (int)blockIdx.x + g * (int)gridDim.x;
+        if (tile < ntiles) fetch(tile);
+        for (int it = g; tile < ntiles; tile += step, it += GROUPS) {        // it = index within this CTA's tile sequence
+            const int b = it & 1;                                    // A buffer == accumulator index of this tile
+            mbar_wait(BAR(B_FREE + b), (uint32_t)(((it >> 1) & 1) ^ 1), 83);       // the MMAs that read this buffer are complete
+            if (CFENCE) {
+                // consumer-side proxy fence: this warp never executes the MEMBAR, so the refill loads issued row by row
+                // right after each row is consumed stay in flight across the hand-off (a full tile of prefetch)
+                const bool more = tile + step < ntiles;
+                const long long left = more ? n - ((long long)(tile + step) * 128 + row0) : 0;
+                const int valid = left < ROWS_PER_WARP ? (int)left : ROWS_PER_WARP;
+                const float* nsrc = lane_src + (size_t)(tile + step) * (128 * D);
+                uint8_t* abuf = smem + OFF_A + b * ABUF + kc * ACH;
+#pragma unroll
+                for (int j = 0; j < ROWS_PER_WARP; ++j) {
+                    const float4 x = t[j];
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+                    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                    const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+                    const uint32_t off = sw128_off(row0 + j, piece) + sub;
+                    *reinterpret_cast<uint2*>(abuf + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                    *reinterpret_cast<uint2*>(abuf + 2 * ACH + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+                    t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < valid) t[j] = ld_stream(nsrc + j * D);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B_STAGED + b));       // release: the warp's shared-memory stores are ordered before it
+            } else {
+                stage_rows<ROWS_PER_WARP>(t, smem + OFF_A + b * ABUF + kc * ACH, row0, piece, sub);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B_STAGED + b));
+                if (tile + step < ntiles) fetch(tile + step);
+            }
         }
-        __syncwarp();
-        mbar_wait(BAR(B_W), 0, 80);
+    } else {
+        // ================================================================= epilogue (thread = row) and MMA issue
+        const bool is_epi = warp < EPI_WARP0 + 4;
+        const bool issuer = (warp == MMA_WARP);
+        const int q = warp & 3;                                      // the TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        float* mun = reinterpret_cast<float*>(smem + OFF_MUN);       // |mu_c W|^2, read back as warp-uniform broadcasts
+        if (is_epi) {
+            if (q == 0) mun[lane] = __ldg(reinterpret_cast<const float*>(section + W_BYTES) + lane);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        // ---- MMA issue (one converged warp, one elected lane): 24 MMAs of the CTA's tile `it` into accumulator it & 1
+        const bool leader = issuer && elect_one();
         constexpr uint32_t ID160 = idesc_bf16(128, NB);
-        uint32_t staged_par = 0u, accfree_par = 3u;      // one parity bit per buffer; fresh barrier: waiting on parity 1 passes
-        long long it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            const int b = (int)(it & 1);
+        uint32_t staged_par = 0u, accfree_par = 3u;                  // one parity bit per buffer; fresh barrier: parity 1 passes
+        auto issue_tile = [&](const int b) __attribute__((always_inline)) {
             mbar_wait(BAR(B_ACCFREE + b), (accfree_par >> b) & 1u, 81);
             accfree_par ^= 1u << b;
             mbar_wait(BAR(B_STAGED + b), (staged_par >> b) & 1u, 82);
             staged_par ^= 1u << b;
+            if (CFENCE) fence_async_smem();      // generic-proxy stores (acquired through the barrier) -> async-proxy reads of the MMAs
             tc_fence_after();
             const uint32_t abase = sbase + OFF_A + b * ABUF;
             const uint32_t d = tmem + ACC_STRIDE * (uint32_t)b;
@@ -143,88 +238,56 @@ __global__ void __launch_bounds__(NT, 1) maha_score_tc_kernel(const uint8_t* __r
                 }
             }
             if (leader) { tc_commit(BAR(B_FREE + b)); tc_commit(BAR(B_ACCFULL + b)); }
-        }
-    } else if (warp < N_STAGE_WARPS) {
-        // ================================================================= staging: fp32 rows -> split-bf16 A tiles
-        // warp w owns rows 16 w .. 16 w + 15 of the tile; lane l holds elements [4 l, 4 l + 4) of a row
-        const int kc = lane >> 4, piece = (lane & 15) >> 1, sub = (lane & 1) * 8;
-        float4 t[16];
-        auto load_tile = [&](long long tile) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const long long r = tile * 128 + warp * 16 + j;
-                t[j] = (r < n) ? ld_stream(feat + r * D + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
         };
-        uint32_t free_par = 3u;
-        long long it = 0;
-        if ((long long)blockIdx.x < tiles) load_tile(blockIdx.x);
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            const int b = (int)(it & 1);
-            mbar_wait(BAR(B_FREE + b), (free_par >> b) & 1u, 83);    // the MMAs that read this buffer are complete
-            free_par ^= 1u << b;
-            uint8_t* abuf = smem + OFF_A + b * ABUF + kc * ACH;
-            const long long next = tile + gridDim.x;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int row = warp * 16 + j;
-                const float4 x = t[j];
-                const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
-                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-                const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
-                const uint32_t off = sw128_off(row, piece) + sub;
-                *reinterpret_cast<uint2*>(abuf + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-                *reinterpret_cast<uint2*>(abuf + 2 * ACH + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-                if (next < tiles) {                                  // refill this register with the next tile's row right away
-                    const long long r = next * 128 + row;
-                    t[j] = (r < n) ? ld_stream(feat + r * D + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+        if (issuer) {
+            if (leader) {                                            // the [W | G] image: resident for the life of the CTA
+                mbar_expect_tx(BAR(B_W), W_BYTES);
+                for (int c = 0; c < 4; ++c) bulk_g2s(sbase + OFF_W + c * BCH, section + (size_t)c * BCH, BCH, BAR(B_W));
             }
-            fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(B_STAGED + b));
+            mbar_wait(BAR(B_W), 0, 80);
+            if (!MERGED) {                                           // dedicated warp: just run ahead of the epilogue
+                long long it = 0;
+                for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) issue_tile((int)(it & 1));
+            } else if ((long long)blockIdx.x < tiles) {
+                issue_tile(0);
+            }
         }
-    } else {
-        // ================================================================= epilogue: thread = row
-        const int q = warp - EPI_WARP0;                              // == warp & 3: the TMEM lane quarter this warp may read
-        const int row = q * 32 + lane;
-        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-        float* mun = reinterpret_cast<float*>(smem + OFF_MUN);       // |mu_c W|^2, read back as warp-uniform broadcasts
-        if (q == 0) mun[lane] = __ldg(reinterpret_cast<const float*>(section + W_BYTES) + lane);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        uint32_t full_par = 0u;
-        long long it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            const int b = (int)(it & 1);
-            mbar_wait(BAR(B_ACCFULL + b), (full_par >> b) & 1u, 84);
-            full_par ^= 1u << b;
-            tc_fence_after();
-            const uint32_t acc = lane_base + ACC_STRIDE * (uint32_t)b;
-            uint32_t v[64];
-            float yy0 = 0.f, yy1 = 0.f, yy2 = 0.f, yy3 = 0.f;
+        if (is_epi) {
+            uint32_t full_par = 0u;
+            long long it = 0;
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+                const int b = (int)(it & 1);
+                if (MERGED && issuer && tile + gridDim.x < tiles) issue_tile(b ^ 1);      // keep the tensor pipe one tile ahead of the drain
+                mbar_wait(BAR(B_ACCFULL + b), (full_par >> b) & 1u, 84);
+                full_par ^= 1u << b;
+                tc_fence_after();
+                const uint32_t acc = lane_base + ACC_STRIDE * (uint32_t)b;
+                uint32_t v[32];
+                float yy0 = 0.f, yy1 = 0.f, yy2 = 0.f, yy3 = 0.f;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                TMEM_LD32(acc + 64 * h, v);
-                TMEM_LD32(acc + 64 * h + 32, (v + 32));
-                tc_wait_ld();
+                for (int h = 0; h < 4; ++h) {
+                    TMEM_LD32(acc + 32 * h, v);
+                    tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 64; i += 4) {
-                    yy0 = fmaf(__uint_as_float(v[i]), __uint_as_float(v[i]), yy0);
-                    yy1 = fmaf(__uint_as_float(v[i + 1]), __uint_as_float(v[i + 1]), yy1);
-                    yy2 = fmaf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 2]), yy2);
-                    yy3 = fmaf(__uint_as_float(v[i + 3]), __uint_as_float(v[i + 3]), yy3);
+                    for (int i = 0; i < 32; i += 4) {
+                        yy0 = fmaf(__uint_as_float(v[i]), __uint_as_float(v[i]), yy0);
+                        yy1 = fmaf(__uint_as_float(v[i + 1]), __uint_as_float(v[i + 1]), yy1);
+                        yy2 = fmaf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 2]), yy2);
+                        yy3 = fmaf(__uint_as_float(v[i + 3]), __uint_as_float(v[i + 3]), yy3);
+                    }
                 }
-            }
-            TMEM_LD32(acc + 128, v);
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(B_ACCFREE + b));          // accumulator b may be overwritten
-            float best = INFINITY;
+                TMEM_LD32(acc + 128, v);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B_ACCFREE + b));      // accumulator b may be overwritten
+                float best = INFINITY;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) best = fminf(best, fmaf(-2.f, __uint_as_float(v[c]), mun[c]));
-            const long long r = tile * 128 + row;
-            if (r < n) score[r] = fmaxf((yy0 + yy1) + (yy2 + yy3) + best, 0.f);
+                for (int c = 0; c < 32; ++c) best = fminf(best, fmaf(-2.f, __uint_as_float(v[c]), mun[c]));
+                const long long r = tile * 128 + row;
+                if (r < n) score[r] = fmaxf((yy0 + yy1) + (yy2 + yy3) + best, 0.f);
+            }
         }
     }
     tc_fence_before();
@@ -248,19 +311,35 @@ int pack_maha_score_tc(const float* f32, const MahaLayout& ml, uint8_t* dst, cud
 }
 
 // section: device pointer to the [W | G] image + class norms inside the maha blob; feat (n,128) fp32, 16-byte aligned
-int launch_maha_score_tc(const uint8_t* section, const float* feat, long long n, float* score, cudaStream_t st) {
+template <int GROUPS, bool MERGED, bool CFENCE>
+static int launch_variant(const uint8_t* section, const float* feat, long long n, float* score, cudaStream_t st) {
     static bool configured[64] = {};
     int dev = 0;
     CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
+    auto kern = mstc::maha_score_tc_kernel<GROUPS, MERGED, CFENCE>;
     if (!configured[dev & 63]) {
-        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(mstc::maha_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mstc::SMEM_BYTES));
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mstc::SMEM_BYTES));
         configured[dev & 63] = true;
     }
     const long long tiles = (n + 127) / 128;
+    CMHAR_REQUIRE(tiles < 0x7fffffffLL, "too many rows");
     const int grid = (int)(tiles < (long long)sm_count() ? tiles : (long long)sm_count());
-    mstc::maha_score_tc_kernel<<<grid, mstc::NT, mstc::SMEM_BYTES, st>>>(section, feat, n, score);
+    kern<<<grid, mstc::Roles<GROUPS, MERGED>::NT, mstc::SMEM_BYTES, st>>>(section, feat, n, score);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
+}
+
+int launch_maha_score_tc(const uint8_t* section, const float* feat, long long n, float* score, cudaStream_t st) {
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("CMHAR_MAHA_VARIANT"); variant = e ? atoi(e) : 0; }      // development switch
+    // Measured on B200, 2 M rows (tools/bench_maha_variants.py): one staging group + dedicated MMA warp 213 us (74 % of the
+    // copy bandwidth) with the canonical writer-side proxy fence, 210 us with the consumer-side fence that keeps a full
+    // tile of loads in flight -- i.e. not latency-bound any more: a tile moves 64 KiB of staging stores + 24 x 9 KiB of
+    // operand reads through the SM's 128 B/clk shared-memory port (2 240 cycles of the ~3 800 per tile).  Two staging
+    // groups (21 warps -> 80 registers, spills) 292 us; MMAs issued from an epilogue warp (descriptors leave the uniform
+    // datapath) 583 us -- both dropped.
+    if (variant == 3) return launch_variant<1, false, true>(section, feat, n, score, st);
+    return launch_variant<1, false, false>(section, feat, n, score, st);
 }
 
 }  // namespace cmhar
