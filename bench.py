@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--lanes", type=int, default=8, help="CUDA streams independent steps are pipelined over (1 = serial)")
+    ap.add_argument("--lanes", type=int, default=16, help="CUDA streams independent steps are pipelined over (1 = serial)")
     return ap.parse_args()
 
 

@@ -39,6 +39,17 @@ int cmhar_imu_forward(const void* encoder_blob, const void* head_blob, const voi
     return launch_imu_forward_fp32(a, (cudaStream_t)s);
 }
 
+int cmhar_debug_cta_trace(uint64_t* device_buffer, int64_t capacity_records) {
+    unsigned long long* ptr = reinterpret_cast<unsigned long long*>(device_buffer);
+    if (ptr) {
+        CMHAR_REQUIRE(capacity_records > 0, "cmhar_debug_cta_trace: capacity must be positive");
+        const unsigned long long head[2] = {0ull, (unsigned long long)capacity_records};
+        CMHAR_CHECK_CUDA(cudaMemcpy(ptr, head, sizeof(head), cudaMemcpyHostToDevice));
+    }
+    CMHAR_CHECK_CUDA(cudaMemcpyToSymbol(cmhar::g_cta_trace, &ptr, sizeof(ptr)));
+    return CMHAR_OK;
+}
+
 int cmhar_debug_imu_bf16(const void* encoder_blob, const float* x, int64_t n_windows, int64_t x_window_stride,
                          int32_t stage, float* residual_dump, float* cls_out, int32_t* progress_host_mapped,
                          cmhar_stream_t s) {

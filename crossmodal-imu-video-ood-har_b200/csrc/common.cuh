@@ -134,6 +134,29 @@ __device__ __forceinline__ float warp_min(float v) {
     return v;
 }
 
+// ---- CTA trace (development aid, cmhar_debug_cta_trace): when a buffer is installed, thread 0 of every CTA of the
+// instrumented kernels appends {kernel id, SM id, start, end} (globaltimer ns) -- the only way to see how the CTAs
+// of concurrently running kernels share the SMs without nsys.  One global load per CTA when disabled.
+// (defined here: the library is a single translation unit, see cmhar_b200.cu)
+__device__ unsigned long long* g_cta_trace = nullptr;        // [0] = record counter, [1] = capacity, then 4 words per record
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long trace_begin() { return g_cta_trace ? trace_now() : 0ull; }
+__device__ __forceinline__ void trace_end(int kernel_id, unsigned long long t0) {
+    unsigned long long* buf = g_cta_trace;
+    if (!buf || t0 == 0ull) return;
+    const unsigned long long slot = atomicAdd(buf, 1ull);
+    if (slot >= buf[1]) return;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* r = buf + 2 + 4 * slot;
+    r[0] = (unsigned long long)kernel_id; r[1] = smid; r[2] = t0; r[3] = trace_now();
+}
+enum { TRACE_ENCODER = 1, TRACE_POOL = 2, TRACE_HEAD = 3, TRACE_LINEAR = 4, TRACE_SIM = 5 };
+
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {

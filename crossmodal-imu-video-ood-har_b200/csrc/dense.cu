@@ -5,6 +5,7 @@
 // (ProjectionHead: Linear-BN-ReLU-Linear), :288-289 (F.normalize) and :210-215 (spatial average
 // pool + temporal mean; both are linear so pool-then-project == project-then-pool).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cmhar {
 
@@ -147,6 +148,10 @@ __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict
                                                          int channels, int hw, float* __restrict__ pooled) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= channels) return;
+    const unsigned long long trace_t0 = (threadIdx.x == 0) ? trace_begin() : 0ull;
+    // read-once stream: evict_first in L2, so the feature maps do not displace the weight images other kernels re-read
+    uint64_t stream_policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
     const size_t fstride = (size_t)channels * hw;
     for (long long b = blockIdx.y; b < n; b += gridDim.y) {
     const T* base = fmap + ((size_t)b * frames * channels + c) * hw;
@@ -158,8 +163,8 @@ __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict
             const uint4* p = reinterpret_cast<const uint4*>(base + t * fstride);
             for (int v = 0; v < nv; ++v) {
                 uint4 u;
-                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p + v));
+                asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                             : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p + v), "l"(stream_policy));
                 if (sizeof(T) == 2) {
                     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -179,7 +184,119 @@ __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict
     }
     pooled[b * channels + c] = acc / (float)(frames * hw);
     }
+    if (threadIdx.x == 0) trace_end(TRACE_POOL, trace_t0);
 }
+
+
+// ---- video tail, co-resident variant ----------------------------------------------------------------------
+// The kernel above needs ~16 resident CTAs per SM to saturate HBM, and a CTA trace of the pipelined step
+// (tools/cta_trace.py) shows what that costs: ~1 000 pooling CTAs of several in-flight batches sit on ~70 of
+// the 148 SMs waiting for HBM, and the encoder's whole-SM CTAs cannot start there -- the two stages time-share
+// the chip and their times ADD.  This variant takes its bytes in flight from 32 KiB of shared memory instead of
+// thousands of registers: ONE 128-thread CTA per SM (<= 40 registers per thread, 33 KiB of shared memory) streams
+// [128 channels x hw] slabs (4 KiB for bf16 4x4 maps) through an 8-stage cp.async.bulk ring and fits NEXT to an
+// encoder CTA (whose weight ring was cut from 6 to 4 stages to make the room: no loss, tools/enc_sweep.py), so
+// the HBM-bound stage of one batch overlaps the tensor-bound stage of the others on the same SMs.
+namespace poolring {
+using namespace tc;
+constexpr int CB = 128;                       // channels per slab == threads per CTA
+constexpr int RING_BYTES = 32768;
+constexpr int MAX_STAGES = 16;
+constexpr int STAGE_TARGET = 16384;          // bytes per ring stage (whole frames)
+constexpr int OFF_BAR = RING_BYTES, SMEM_BYTES = RING_BYTES + 2 * MAX_STAGES * 8;
+
+template <typename T>
+__global__ void __launch_bounds__(CB, 12) video_pool_ring_kernel(const T* __restrict__ fmap, long long n, int frames, int channels,
+                                                                 int hw, float* __restrict__ pooled, int stage_target, int cpt) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned long long trace_t0 = (tid == 0) ? trace_begin() : 0ull;
+    const uint32_t sbase = smem_u32(smem), bar0 = sbase + OFF_BAR;
+    const int chan_bytes = hw * (int)sizeof(T);               // multiple of 16, <= 64
+    const int CBC = CB * cpt;                                 // channels per CTA: thread tid owns channels tid + 128 j, j < cpt <= 4
+    const int slab_bytes = CBC * chan_bytes;                  // one frame of this CTA's channels (contiguous in HBM: larger bulk
+                                                              // copies stream better, 16 KiB when the CTA takes all 512 channels)
+    // a ring stage holds G frames (16 KiB for bf16 4x4 maps): every stage costs one barrier round trip between the
+    // consumers and the issuing thread (~0.7 us), so single-frame 4 KiB stages capped a CTA at 6 GB/s
+    int G = stage_target / slab_bytes; G = G < 1 ? 1 : (G > frames ? frames : G);
+    const int stage_bytes = G * slab_bytes;
+    const int nst = RING_BYTES / stage_bytes < MAX_STAGES ? RING_BYTES / stage_bytes : MAX_STAGES;
+    const int spu = (frames + G - 1) / G;                     // stages per unit
+    auto FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(MAX_STAGES + s); };
+    if (tid == 0) {
+        for (int s = 0; s < nst; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), CB / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int cblocks = channels / CBC;
+    const int units = (int)n * cblocks;                        // unit = (clip, channel block) (launcher: fits int)
+    const int my_units = ((int)blockIdx.x < units) ? (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total = my_units * spu;
+    const uint64_t stream_policy = l2_policy_evict_first();   // read-once: do not displace the weight images in L2
+    // producer state (thread 0 only): stage-step p of this CTA's sequence goes to ring stage p % nst
+    int p_unit = blockIdx.x, p_f = 0, p_s = 0, p_n = 0;
+    uint32_t p_par = 1u;                                      // parity to wait for on EMPTY (fresh barrier: 1 passes)
+    auto issue = [&]() {
+        mbar_wait(EMPTY(p_s), p_par, 97);
+        const int g = (frames - p_f < G) ? frames - p_f : G;
+        mbar_expect_tx(FULL(p_s), (uint32_t)(g * slab_bytes));
+        const int b = p_unit / cblocks, cb = p_unit - b * cblocks;
+        const T* src = fmap + (((size_t)b * frames + p_f) * channels + (size_t)cb * CBC) * hw;
+        for (int f = 0; f < g; ++f)
+            bulk_g2s_hint(sbase + p_s * stage_bytes + f * slab_bytes, src + (size_t)f * channels * hw, (uint32_t)slab_bytes, FULL(p_s), stream_policy);
+        p_f += g;
+        if (p_f == frames) { p_f = 0; p_unit += gridDim.x; }
+        if (++p_s == nst) { p_s = 0; p_par ^= 1u; }
+        ++p_n;
+    };
+    if (tid == 0)
+        while (p_n < nst && p_n < total) issue();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int f0 = 0, s = 0, unit = blockIdx.x;
+    uint32_t par = 0u;
+    const float inv = 1.f / (float)(frames * hw);
+    for (int it = 0; it < total; ++it) {
+        mbar_wait(FULL(s), par, 98);
+        const int g = (frames - f0 < G) ? frames - f0 : G;
+        const uint8_t* base = smem + s * stage_bytes + tid * chan_bytes;
+        for (int f = 0; f < g; ++f) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < cpt) {
+                    const uint4* src = reinterpret_cast<const uint4*>(base + f * slab_bytes + j * (CB * chan_bytes));
+                    for (int v = 0; v < chan_bytes / 16; ++v) {
+                        const uint4 u = src[v];
+                        if (sizeof(T) == 2) {
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) { const float2 x = __bfloat1622float2(h2[q]); acc[j] += x.x + x.y; }
+                        } else {
+                            const float* x = reinterpret_cast<const float*>(&u);
+                            acc[j] += (x[0] + x[1]) + (x[2] + x[3]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(EMPTY(s));                 // this warp's channels of the stage are in registers
+        if (++s == nst) { s = 0; par ^= 1u; }
+        if (tid == 0 && p_n < total) issue();
+        f0 += g;
+        if (f0 == frames) {
+            const int b = unit / cblocks, cb = unit - b * cblocks;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < cpt) pooled[(size_t)b * channels + cb * CBC + j * CB + tid] = acc[j] * inv;
+                acc[j] = 0.f;
+            }
+            f0 = 0; unit += gridDim.x;
+        }
+    }
+    if (tid == 0) trace_end(TRACE_POOL, trace_t0);
+}
+}  // namespace poolring
 
 }  // namespace cmhar
 
@@ -298,7 +415,45 @@ int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frame
     CMHAR_REQUIRE(fmap && pooled && frames > 0 && channels > 0 && hw > 0, "cmhar_video_pool: bad argument");
     if (n <= 0) return CMHAR_OK;
     cudaStream_t st = (cudaStream_t)s;
-    dim3 grid((channels + POOL_NT - 1) / POOL_NT, (unsigned)(n < 32768 ? n : 32768));
+    // pipeline-sized batches: the co-resident ring kernel (one small CTA per SM next to the encoder's); large batches
+    // that own the GPU anyway: the flooding kernel below (101 % of the measured copy bandwidth at 2 048 clips)
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("CMHAR_POOL_MODE"); mode = e ? atoi(e) : 0; }        // development switch: 1 = flood, 2 = ring
+    const int esize = is_bf16 ? 2 : 4;
+    const bool ring_ok = ((uintptr_t)fmap & 15) == 0 && channels % poolring::CB == 0 && (hw * esize) % 16 == 0 && hw * esize <= 64;
+    if (ring_ok && mode != 1 && (mode == 2 || n <= 1024) && n * (channels / poolring::CB) * frames < 0x7fffffffLL) {
+        static bool configured[64] = {};
+        int dev = 0;
+        CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
+        if (!configured[dev & 63]) {
+            CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, poolring::SMEM_BYTES));
+            CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, poolring::SMEM_BYTES));
+            // an SM configured by this kernel alone must still be able to take an encoder CTA: ask for the largest carveout
+            CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            configured[dev & 63] = true;
+        }
+        static int cpt_cap = -1;
+        if (cpt_cap < 0) { const char* e = getenv("CMHAR_POOL_CPT"); cpt_cap = e ? atoi(e) : 1; }     // 4 channels per thread (16 KiB slabs, one unit per clip): +12 % alone, but 256 units on 148 CTAs is 2 uneven rounds
+        int cpt = 1;
+        for (int c = 4; c >= 1; --c) if (c <= cpt_cap && channels % (poolring::CB * c) == 0 && poolring::CB * c * hw * esize <= 16384) { cpt = c; break; }
+        const long long units = n * (channels / (poolring::CB * cpt));
+        static int per_sm = -1;
+        if (per_sm < 0) { const char* e = getenv("CMHAR_POOL_CTAS_PER_SM"); per_sm = e ? atoi(e) : 1; }
+        const long long cap = (long long)per_sm * sm_count();
+        const unsigned grid = (unsigned)(units < cap ? units : cap);
+        static int stage_target = -1;
+        if (stage_target < 0) { const char* e = getenv("CMHAR_POOL_STAGE"); stage_target = e ? atoi(e) : poolring::STAGE_TARGET; }
+        if (is_bf16) poolring::video_pool_ring_kernel<__nv_bfloat16><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
+        else poolring::video_pool_ring_kernel<float><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const float*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
+        CMHAR_LAUNCH_CHECK();
+        return CMHAR_OK;
+    }
+    static int cap_y = -1;
+    if (cap_y < 0) { const char* e = getenv("CMHAR_POOL_GRIDY"); cap_y = e ? atoi(e) : 0; }      // development switch
+    long long gy = n < 32768 ? n : 32768;
+    if (cap_y > 0 && gy > cap_y) gy = cap_y;
+    dim3 grid((channels + POOL_NT - 1) / POOL_NT, (unsigned)gy);
     const bool aligned = ((uintptr_t)fmap & 15) == 0;
     if (is_bf16) {
         if (aligned && hw % 8 == 0)

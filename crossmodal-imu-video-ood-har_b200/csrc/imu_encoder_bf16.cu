@@ -29,7 +29,7 @@ namespace cmhar {
 namespace tc {
 
 constexpr int CHUNK = 16384;                 // bytes of one [128 x 64] bf16 SW128 chunk
-constexpr int NSTAGE = 6;
+constexpr int NSTAGE = 4;
 constexpr int CHUNKS_PER_LAYER = 24;
 // roles: 4*NQ epilogue warps (NQ = column splits per row), then the MMA warp, then the weight producer
 
@@ -45,9 +45,10 @@ constexpr int OFF_P = 98304;                 // parameter staging (static block 
 constexpr int OFF_W = 131072;                // weight ring, NSTAGE chunks
 constexpr int OFF_BAR = OFF_W + NSTAGE * CHUNK;    // mbarriers (8 B each) + tmem pointer
 constexpr int SMEM_BYTES = OFF_BAR + 256;
-// 228 KiB per SM, 1 KiB reserved per resident CTA: staying under 226 KiB leaves room for a second, small CTA
-// (the HBM-bound pooling / conversion kernels of other in-flight batches) next to the encoder's.
-static_assert(SMEM_BYTES + 1024 + 2048 <= 233472, "no room left for a co-resident small CTA");
+// 228 KiB per SM, 1 KiB reserved per resident CTA.  A 4-stage weight ring is as fast as the former 6-stage one
+// (tools/enc_sweep.py) and leaves 34 KiB: room for the co-resident HBM-bound pooling CTA of another in-flight
+// batch (dense.cu, video_pool_ring_kernel: 32 KiB cp.async.bulk ring + barriers).
+static_assert(SMEM_BYTES + 1024 + 32768 + 256 + 1024 <= 233472, "no room left for the co-resident pooling CTA");
 // fp32 parameters the epilogue needs, staged in shared memory by the producer (with 227 KiB of
 // shared memory the L1 is ~1 KiB, so every __ldg of a bias / LayerNorm vector was an L2 round trip
 // on the critical path).  Static block: once per CTA.  Per-layer block: double buffered.
@@ -110,6 +111,7 @@ __global__ void __maxnreg__(NQ == 2 ? 152 : 104) imu_forward_bf16_kernel(const B
     uint8_t* const smem = smem_tc;
     const FwdArgs& a = args.f;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned long long trace_t0 = (tid == 0) ? trace_begin() : 0ull;
     const BlobHeader* eh = reinterpret_cast<const BlobHeader*>(a.enc_blob);
     const int S = eh->a, n_layers = eh->b;
     const float* encf = reinterpret_cast<const float*>(a.enc_blob + 1024);
@@ -159,6 +161,7 @@ __global__ void __maxnreg__(NQ == 2 ? 152 : 104) imu_forward_bf16_kernel(const B
         if (lane == 0) {
             uint32_t stage = 0, parity = 1;           // fresh barriers: waiting on parity 1 passes
             uint32_t pb_parity[2] = {1, 1};
+            const uint64_t keep = l2_policy_evict_last();      // the weight images are re-read by every tile of every CTA
             mbar_expect_tx(BAR(B_STATIC), SB_FLOATS * 4);
             bulk_g2s(sbase + OFF_SB, gparams, SB_FLOATS * 4, BAR(B_STATIC));
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -175,7 +178,7 @@ __global__ void __maxnreg__(NQ == 2 ? 152 : 104) imu_forward_bf16_kernel(const B
                     if ((args.ablate & ABL_NO_TMA) && tile != blockIdx.x) { mbar_arrive(BAR(B_WFULL + stage)); }
                     else {
                     mbar_expect_tx(BAR(B_WFULL + stage), CHUNK);
-                    bulk_g2s(sbase + OFF_W + stage * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(B_WFULL + stage));
+                    bulk_g2s_hint(sbase + OFF_W + stage * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(B_WFULL + stage), keep);
                     }
                     if (++stage == NSTAGE) { stage = 0; parity ^= 1; }
                 }
@@ -624,6 +627,7 @@ __global__ void __maxnreg__(NQ == 2 ? 152 : 104) imu_forward_bf16_kernel(const B
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
+    if (tid == 0) trace_end(TRACE_ENCODER, trace_t0);
 }
 
 // ================================================================================ weight packing
@@ -767,6 +771,9 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
     if (!configured[dev & 63]) {
         CMHAR_CHECK_CUDA(cudaFuncSetAttribute(imu_forward_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CMHAR_CHECK_CUDA(cudaFuncSetAttribute(imu_forward_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        // 193 KiB would select the 196 KiB carveout and leave nothing for a co-resident CTA: configure the SM for 228 KiB
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(imu_forward_bf16_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(imu_forward_bf16_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured[dev & 63] = true;
     }
     const long long tiles = (args.f.n + 7) / 8;

@@ -57,6 +57,7 @@ __global__ void pack_linear_chunks_kernel(const float* __restrict__ wt, int K, i
 __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const Args p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned long long trace_t0 = (tid == 0) ? trace_begin() : 0ull;
     const uint32_t sbase = smem_u32(smem), bar0 = sbase + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * B_COUNT);
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const Args p) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
     }
+    if (tid == 0) trace_end(TRACE_LINEAR, trace_t0);
 }
 
 }  // namespace lintc

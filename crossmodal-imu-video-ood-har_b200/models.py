@@ -389,8 +389,9 @@ class VideoEncoder(_PackedMixin, nn.Module):
             self._packed[key] = _PackedLinear(self.projection, None, device)
         return self._packed[key]
 
-    def forward_features(self, fmap: torch.Tensor, frames: int, precision: Optional[str] = None) -> torch.Tensor:
-        """Native tail: fmap (B*T, F, h, w) bf16/fp32 -> (B, video_d_model) fp32."""
+    def pool_features(self, fmap: torch.Tensor, frames: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """HBM-bound half of the native tail: fmap (B*T, F, h, w) bf16/fp32 -> spatio-temporal mean (B, F) fp32
+        (reference models.py:210-211,215 commuted in front of the linear projection)."""
         N.require_cuda(fmap, "VideoEncoder")
         if fmap.dtype not in (torch.float32, torch.bfloat16):
             fmap = fmap.float()
@@ -400,11 +401,19 @@ class VideoEncoder(_PackedMixin, nn.Module):
         if BT % frames:
             raise ValueError(f"{BT} frames do not split into clips of {frames}")
         B = BT // frames
-        pooled = torch.empty((B, Fd), dtype=torch.float32, device=fmap.device)
+        pooled = out if out is not None else torch.empty((B, Fd), dtype=torch.float32, device=fmap.device)
         with torch.cuda.device(fmap.device):
             N.check(N.lib().cmhar_video_pool(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw,
                                              pooled.data_ptr(), N.stream_ptr(fmap.device)))
-        return self._packed_projection(fmap.device)(pooled, relu=False, precision=precision)
+        return pooled
+
+    def project_pooled(self, pooled: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+        """(B, F) pooled features -> (B, video_d_model): the reference's ``projection`` (models.py:213)."""
+        return self._packed_projection(pooled.device)(pooled, relu=False, precision=precision)
+
+    def forward_features(self, fmap: torch.Tensor, frames: int, precision: Optional[str] = None) -> torch.Tensor:
+        """Native tail: fmap (B*T, F, h, w) bf16/fp32 -> (B, video_d_model) fp32."""
+        return self.project_pooled(self.pool_features(fmap, frames), precision)
 
     def forward_frame_features(self, fmap: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
         """Per-frame tail (cross-attention fusion needs frame tokens): fmap (B*T, F, h, w) -> (B*T, video_d_model),

@@ -137,6 +137,11 @@ int cmhar_debug_imu_bf16(const void* encoder_blob, const float* x, int64_t n_win
                          float* cls_out, int32_t* progress_host_mapped /* NULL or pinned [grid][16] */,
                          cmhar_stream_t s);
 
+/* Diagnostic hook (tools only): installs (or, with NULL, removes) a device buffer of 2 + 4 * capacity_records
+ * uint64 words; while installed, thread 0 of every CTA of the encoder / pooling / head / dense / similarity kernels
+ * appends {kernel id, SM id, start ns, end ns} (globaltimer).  Word 0 counts the records.  Synchronous. */
+int cmhar_debug_cta_trace(uint64_t* device_buffer, int64_t capacity_records);
+
 /* Same head + scores from stored features (row-major (n,128) fp32).
  * CMHAR_FP32: fp32 FMA arithmetic.  CMHAR_BF16: the tensor-core kernel -- every layer, the whitening and the
  * class-mean products are tcgen05 MMAs on split-bf16 operands (x = hi + lo, three products per term, fp32

@@ -233,6 +233,21 @@ def test_video_pool_shapes(hw, dtype):
     assert rel_err(pooled, want) < 1e-5
 
 
+@pytest.mark.parametrize("n,T,Fd,hw,dtype", [(1, 16, 512, 16, torch.bfloat16), (37, 16, 512, 16, torch.bfloat16),
+                                             (300, 16, 512, 16, torch.bfloat16), (41, 3, 256, 16, torch.float32),
+                                             (64, 5, 128, 8, torch.bfloat16), (19, 7, 384, 32, torch.bfloat16)])
+def test_video_pool_ring_kernel(n, T, Fd, hw, dtype):
+    """The co-resident TMA-ring pooling kernel (channels % 128 == 0, 16..64 bytes per channel, n <= 1024): one clip,
+    fewer units than CTAs, many units per persistent CTA (ring stages and parities wrap), 1-, 2- and 4-vector slabs."""
+    rs = np.random.RandomState(n + hw)
+    fm = torch.from_numpy(np.maximum(rs.standard_normal((n * T, Fd, hw)), 0).astype(np.float32)).to(DEV).to(dtype)
+    pooled = torch.full((n, Fd), float("nan"), device=DEV)
+    N = cm._native
+    N.check(N.lib().cmhar_video_pool(fm.data_ptr(), int(dtype == torch.bfloat16), n, T, Fd, hw, pooled.data_ptr(), N.stream_ptr(fm.device)))
+    want = fm.float().view(n, T, Fd, hw).mean(dim=(1, 3))
+    assert rel_err(pooled, want) < 1e-5
+
+
 def test_similarity_losses_ragged_and_sharded():
     rs = np.random.RandomState(5)
     a = rs.standard_normal((300, 256)).astype(np.float32)

@@ -10,27 +10,27 @@ torch.manual_seed(0)
 cfg = cm.default_config()
 clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg).to(dev).eval()
 xm = cm.CrossModalModel(cfg).to(dev).eval()
-B, L = 256, 8
+B, L = 256, int(os.environ.get("LANES", "8"))
 xs = [torch.randn(B, 6, 250, device=dev) for _ in range(L)]
 fs = [torch.relu(torch.randn(B * 16, 512, 4, 4, device=dev)).to(torch.bfloat16) for _ in range(L)]
 
-def capture(fn):
+def capture(fn, hi_prio=False):
     graphs = []
     for i in range(L):
-        s = torch.cuda.Stream()
+        s = torch.cuda.Stream(priority=-1) if hi_prio else torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             fn(i)
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=s if hi_prio else None):
             out = fn(i)
         graphs.append((g, out))
     return graphs
 
-def bench(name, fn, steps=2000):
-    graphs = capture(fn)
-    lanes = [torch.cuda.Stream() for _ in range(L)]
+def bench(name, fn, steps=2000, hi_prio=False):
+    graphs = capture(fn, hi_prio)
+    lanes = [torch.cuda.Stream(priority=-1) if hi_prio else torch.cuda.Stream() for _ in range(L)]
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for rep in range(2):
@@ -63,6 +63,26 @@ with torch.no_grad():
         main.wait_stream(side)
         return o
     bench("encoder || pool (2 branches)", enc_and_pool)
+    lo_prio = torch.cuda.Stream(priority=0)
+    hi_lanes = None
+    def enc_and_pool_prio(i):      # pooling on a low-priority side stream: pending encoder CTAs are dispatched first
+        main = torch.cuda.current_stream()
+        lo_prio.wait_stream(main)
+        with torch.cuda.stream(lo_prio):
+            N.check(N.lib().cmhar_video_pool(fs[i].data_ptr(), 1, B, 16, 512, 16, pooled[i].data_ptr(), N.stream_ptr(dev)))
+        o = imu_forward_native(clf.imu_encoder, None, None, xs[i], want_cls=True, precision="bf16")
+        main.wait_stream(lo_prio)
+        return o
+    bench("encoder (hi prio lanes) || pool (lo prio)", enc_and_pool_prio, hi_prio=True)
+    def pool_then_enc(i):
+        N.check(N.lib().cmhar_video_pool(fs[i].data_ptr(), 1, B, 16, 512, 16, pooled[i].data_ptr(), N.stream_ptr(dev)))
+        return imu_forward_native(clf.imu_encoder, None, None, xs[i], want_cls=True, precision="bf16")
+    bench("pool -> encoder (one branch)", pool_then_enc)
+    if os.environ.get("LANE_PROBE_SHORT"):
+        fus = cm.LateFusionClassifier(clf.imu_encoder, xm.video_encoder, cfg).to(dev).eval()
+        pipe = cm.CrossModalOODPipeline(clf, xm, None, frames=16, precision="bf16", fusion=fus)
+        bench("full pipeline (14 launches)", lambda i: pipe.run(xs[i], fs[i]))
+        sys.exit(0)
     fus = cm.LateFusionClassifier(clf.imu_encoder, xm.video_encoder, cfg).to(dev).eval()
     pipe = cm.CrossModalOODPipeline(clf, xm, None, frames=16, precision="bf16", fusion=fus)
     bench("full pipeline (14 launches)", lambda i: pipe.run(xs[i], fs[i]))
