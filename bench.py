@@ -436,6 +436,42 @@ def main():
             sweep[str(nb)] = entry
             del xs, so
 
+    # ---- the standalone HBM-bound scoring kernels (information only; rank 0): MSP / energy from stored logits and the
+    # Mahalanobis score from stored features, algorithmic bytes per row from SURVEY.md section 8d
+    scoring = {}
+    if rank == 0 and not args.no_sweep:
+        g = torch.Generator(device=dev); g.manual_seed(7)
+        n_rows = 4_000_000
+        logits = torch.randn(n_rows, 32, device=dev, generator=g)
+        pr = torch.empty(n_rows, dtype=torch.int64, device=dev); s1 = torch.empty(n_rows, device=dev); s2 = torch.empty(n_rows, device=dev)
+        mu = 2.0 * torch.randn(32, 128, device=dev, generator=g)
+        yfit = torch.randint(0, 32, (20000,), device=dev, generator=g)
+        ffit = mu[yfit] + torch.randn(20000, 128, device=dev, generator=g)
+        maha_alone = cm.MahalanobisOOD(32, dev, ridge=1e-3).fit(ffit, yfit)
+        n_feat = 2_000_000
+        feat = mu[torch.randint(0, 32, (n_feat,), device=dev, generator=g)] + torch.randn(n_feat, 128, device=dev, generator=g)
+        sc = torch.empty(n_feat, device=dev)
+        mblob = maha_alone.blob(dev)
+        for name, fn, nbytes in (
+                ("logit_scores_ring_kernel", lambda: N.check(N.lib().cmhar_logit_scores(logits.data_ptr(), n_rows, 32, 1.0, pr.data_ptr(), s1.data_ptr(), s2.data_ptr(), N.stream_ptr(dev))), n_rows * (128 + 16)),
+                ("maha_score_tc_kernel", lambda: N.check(N.lib().cmhar_maha_score(mblob.data_ptr(), feat.data_ptr(), n_feat, sc.data_ptr(), N.BF16, N.stream_ptr(dev))), n_feat * (512 + 4))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0.record(stream)
+            for _ in range(10):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / 10
+            gb = nbytes / (ms * 1e-3) / 1e9
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full captures of the same launches
+            # (profiles/logit_ring_kernel_r1m.md, profiles/maha_score_kernel_r1m.md): within 1 % of the algorithmic bytes
+            traffic = {"logit_scores_ring_kernel": 569_077_760, "maha_score_tc_kernel": 1_031_729_816}[name]
+            scoring[name] = {"bound": "hbm", "achieved": gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb / peaks["hbm_gbs"],
+                             "launch_ms": ms, "bytes_per_launch": nbytes, "traffic": traffic}
+        del logits, feat
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         wps, cores, iters = cpu_workload(clf, xm, fus, B, budget_s=12.0)
@@ -451,7 +487,7 @@ def main():
         if sat:
             roofline_sat = {"kernel": f"imu_forward_{precision}_kernel", "bound": "tensor", "achieved": sat["tflops"],
                             "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": sat["tflops"] / peaks["bf16_tflops_sustained"],
-                            "traffic": 81_630_720, "peak_source": peaks["source"] + " sustained (back-to-back launches)",
+                            "traffic": 82_703_616, "peak_source": peaks["source"] + " sustained (back-to-back launches)",
                             "windows_per_launch": 65536, "flop_per_window": FLOP_ENC}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -463,11 +499,12 @@ def main():
                            "step_latency_ms": step_latency_ms, "host_issue_ms_per_step": host_issue_ms / args.steps},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "imu_only_value": e2e_imu, "api": "CrossModalOODPipeline.stream_host (2-deep ring, host wall clock)",
+                        "imu_only_value": e2e_imu, "api": "CrossModalOODPipeline.stream_host (2-deep ring, copies wait on the slot event only, host wall clock)",
                         "note": "pinned host buffers; fmap H2D (262 KB/clip) is the PCIe-bound term"},
                 "gpu_launches": launches_per_step * args.steps,
                 "launches_per_step": launches_per_step,
                 "roofline": roofline, "roofline_saturated_batch": roofline_sat, "roofline_video_tail": roofline_video,
+                "roofline_scoring": scoring,
                 "cpu_baseline": cpu_baseline, "imu_batch_sweep": sweep}
         emit(line)
     if world > 1:

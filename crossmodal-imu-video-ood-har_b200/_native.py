@@ -95,6 +95,8 @@ _SIGNATURES = {
     "cmhar_conv_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "cmhar_video_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]),
+    "cmhar_video_pool_coresident": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p]),
     "cmhar_similarity_work_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "cmhar_similarity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
                                    C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p,

@@ -410,45 +410,66 @@ int cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmhar_s
     return CMHAR_OK;
 }
 
+static bool pool_ring_eligible(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw) {
+    const int esize = is_bf16 ? 2 : 4;
+    return ((uintptr_t)fmap & 15) == 0 && channels % poolring::CB == 0 && (hw * esize) % 16 == 0 && hw * esize <= 64 &&
+           n * (channels / poolring::CB) * frames < 0x7fffffffLL;
+}
+
+static int launch_pool_ring(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
+                            float* pooled, cudaStream_t st) {
+    const int esize = is_bf16 ? 2 : 4;
+    static bool configured[64] = {};
+    int dev = 0;
+    CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, poolring::SMEM_BYTES));
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, poolring::SMEM_BYTES));
+        // an SM configured by this kernel alone must still be able to take an encoder CTA: ask for the largest carveout
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured[dev & 63] = true;
+    }
+    static int cpt_cap = -1;
+    if (cpt_cap < 0) { const char* e = getenv("CMHAR_POOL_CPT"); cpt_cap = e ? atoi(e) : 1; }     // 4 channels per thread (16 KiB slabs, one unit per clip): +12 % alone, but 256 units on 148 CTAs is 2 uneven rounds
+    int cpt = 1;
+    for (int c = 4; c >= 1; --c) if (c <= cpt_cap && channels % (poolring::CB * c) == 0 && poolring::CB * c * hw * esize <= 16384) { cpt = c; break; }
+    const long long units = n * (channels / (poolring::CB * cpt));
+    static int per_sm = -1;
+    if (per_sm < 0) { const char* e = getenv("CMHAR_POOL_CTAS_PER_SM"); per_sm = e ? atoi(e) : 1; }
+    const long long cap = (long long)per_sm * sm_count();
+    const unsigned grid = (unsigned)(units < cap ? units : cap);
+    static int stage_target = -1;
+    if (stage_target < 0) { const char* e = getenv("CMHAR_POOL_STAGE"); stage_target = e ? atoi(e) : poolring::STAGE_TARGET; }
+    if (is_bf16) poolring::video_pool_ring_kernel<__nv_bfloat16><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
+    else poolring::video_pool_ring_kernel<float><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const float*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+int cmhar_video_pool_coresident(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
+                                float* pooled, cmhar_stream_t s) {
+    CMHAR_REQUIRE(fmap && pooled && frames > 0 && channels > 0 && hw > 0, "cmhar_video_pool_coresident: bad argument");
+    if (n <= 0) return CMHAR_OK;
+    CMHAR_REQUIRE(pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw),
+                  "cmhar_video_pool_coresident: needs a 16-byte aligned map, channels %% 128 == 0 and 16..64 bytes per channel (got channels=%d hw=%d)", channels, hw);
+    return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, (cudaStream_t)s);
+}
+
 int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
                      float* pooled, cmhar_stream_t s) {
     CMHAR_REQUIRE(fmap && pooled && frames > 0 && channels > 0 && hw > 0, "cmhar_video_pool: bad argument");
     if (n <= 0) return CMHAR_OK;
     cudaStream_t st = (cudaStream_t)s;
-    // pipeline-sized batches: the co-resident ring kernel (one small CTA per SM next to the encoder's); large batches
-    // that own the GPU anyway: the flooding kernel below (101 % of the measured copy bandwidth at 2 048 clips)
+    // Default: the flooding kernel below (101 % of the measured copy bandwidth at 2 048 clips; 60 % at 256).  The
+    // co-resident ring kernel (cmhar_video_pool_coresident, or CMHAR_POOL_MODE=2 here) does overlap the encoder --
+    // encoder || pooling 28.5 -> 22.5-27 us per 256-window step -- but one 32 KiB ring per SM sustains only ~1.4 TB/s
+    // (HBM latency under load is ~3 us), which stretches every lane's dependency chain: the full 16-lane step measured
+    // 29.9 us on one B200 box and 34.3 us on another, against a steady 32.5 us for the flooding kernel.
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("CMHAR_POOL_MODE"); mode = e ? atoi(e) : 0; }        // development switch: 1 = flood, 2 = ring
-    const int esize = is_bf16 ? 2 : 4;
-    const bool ring_ok = ((uintptr_t)fmap & 15) == 0 && channels % poolring::CB == 0 && (hw * esize) % 16 == 0 && hw * esize <= 64;
-    if (ring_ok && mode != 1 && (mode == 2 || n <= 1024) && n * (channels / poolring::CB) * frames < 0x7fffffffLL) {
-        static bool configured[64] = {};
-        int dev = 0;
-        CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
-        if (!configured[dev & 63]) {
-            CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, poolring::SMEM_BYTES));
-            CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, poolring::SMEM_BYTES));
-            // an SM configured by this kernel alone must still be able to take an encoder CTA: ask for the largest carveout
-            CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            CMHAR_CHECK_CUDA(cudaFuncSetAttribute(poolring::video_pool_ring_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            configured[dev & 63] = true;
-        }
-        static int cpt_cap = -1;
-        if (cpt_cap < 0) { const char* e = getenv("CMHAR_POOL_CPT"); cpt_cap = e ? atoi(e) : 1; }     // 4 channels per thread (16 KiB slabs, one unit per clip): +12 % alone, but 256 units on 148 CTAs is 2 uneven rounds
-        int cpt = 1;
-        for (int c = 4; c >= 1; --c) if (c <= cpt_cap && channels % (poolring::CB * c) == 0 && poolring::CB * c * hw * esize <= 16384) { cpt = c; break; }
-        const long long units = n * (channels / (poolring::CB * cpt));
-        static int per_sm = -1;
-        if (per_sm < 0) { const char* e = getenv("CMHAR_POOL_CTAS_PER_SM"); per_sm = e ? atoi(e) : 1; }
-        const long long cap = (long long)per_sm * sm_count();
-        const unsigned grid = (unsigned)(units < cap ? units : cap);
-        static int stage_target = -1;
-        if (stage_target < 0) { const char* e = getenv("CMHAR_POOL_STAGE"); stage_target = e ? atoi(e) : poolring::STAGE_TARGET; }
-        if (is_bf16) poolring::video_pool_ring_kernel<__nv_bfloat16><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
-        else poolring::video_pool_ring_kernel<float><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const float*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
-        CMHAR_LAUNCH_CHECK();
-        return CMHAR_OK;
-    }
+    if (mode < 0) { const char* e = getenv("CMHAR_POOL_MODE"); mode = e ? atoi(e) : 1; }        // 1 = flood (default), 2 = ring
+    if (mode == 2 && pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw))
+        return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, st);
     static int cap_y = -1;
     if (cap_y < 0) { const char* e = getenv("CMHAR_POOL_GRIDY"); cap_y = e ? atoi(e) : 0; }      // development switch
     long long gy = n < 32768 ? n : 32768;

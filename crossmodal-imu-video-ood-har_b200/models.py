@@ -389,9 +389,11 @@ class VideoEncoder(_PackedMixin, nn.Module):
             self._packed[key] = _PackedLinear(self.projection, None, device)
         return self._packed[key]
 
-    def pool_features(self, fmap: torch.Tensor, frames: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def pool_features(self, fmap: torch.Tensor, frames: int, out: Optional[torch.Tensor] = None,
+                      coresident: bool = False) -> torch.Tensor:
         """HBM-bound half of the native tail: fmap (B*T, F, h, w) bf16/fp32 -> spatio-temporal mean (B, F) fp32
-        (reference models.py:210-211,215 commuted in front of the linear projection)."""
+        (reference models.py:210-211,215 commuted in front of the linear projection).  ``coresident`` selects the
+        one-small-CTA-per-SM ring kernel that can run next to the encoder's CTAs (see include/cmhar_b200.h)."""
         N.require_cuda(fmap, "VideoEncoder")
         if fmap.dtype not in (torch.float32, torch.bfloat16):
             fmap = fmap.float()
@@ -403,8 +405,9 @@ class VideoEncoder(_PackedMixin, nn.Module):
         B = BT // frames
         pooled = out if out is not None else torch.empty((B, Fd), dtype=torch.float32, device=fmap.device)
         with torch.cuda.device(fmap.device):
-            N.check(N.lib().cmhar_video_pool(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw,
-                                             pooled.data_ptr(), N.stream_ptr(fmap.device)))
+            fn = N.lib().cmhar_video_pool_coresident if coresident else N.lib().cmhar_video_pool
+            N.check(fn(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw,
+                       pooled.data_ptr(), N.stream_ptr(fmap.device)))
         return pooled
 
     def project_pooled(self, pooled: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:

@@ -220,6 +220,14 @@ int    cmhar_conv_encoder_forward(const void* blob, const float* x, int64_t n, i
 int cmhar_video_pool(const void* fmap, int32_t fmap_is_bf16, int64_t n, int32_t frames,
                      int32_t channels, int32_t hw, float* pooled, cmhar_stream_t s);
 
+/* Same reduction by the co-resident kernel: ONE 128-thread CTA per SM streams [128 channels x hw] slabs through a
+ * 32 KiB cp.async.bulk ring (<= 40 registers per thread), small enough to be resident next to an encoder CTA, so
+ * the HBM-bound pooling of one batch overlaps the tensor-bound encoder of others on the same SMs.  Sustains about a
+ * quarter of the HBM bandwidth on its own -- use cmhar_video_pool when the stage has the GPU to itself.
+ * Requires a 16-byte aligned map, channels % 128 == 0 and 16..64 bytes per channel (CMHAR_ERR_INVALID otherwise). */
+int cmhar_video_pool_coresident(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels,
+                                int32_t hw, float* pooled, cmhar_stream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * Contrastive similarity (replaces SigmoidContrastiveLoss.forward / InfoNCELoss.forward,
  *                         reference src/models/losses.py:25-54,67-87)

@@ -243,7 +243,7 @@ def test_video_pool_ring_kernel(n, T, Fd, hw, dtype):
     fm = torch.from_numpy(np.maximum(rs.standard_normal((n * T, Fd, hw)), 0).astype(np.float32)).to(DEV).to(dtype)
     pooled = torch.full((n, Fd), float("nan"), device=DEV)
     N = cm._native
-    N.check(N.lib().cmhar_video_pool(fm.data_ptr(), int(dtype == torch.bfloat16), n, T, Fd, hw, pooled.data_ptr(), N.stream_ptr(fm.device)))
+    N.check(N.lib().cmhar_video_pool_coresident(fm.data_ptr(), int(dtype == torch.bfloat16), n, T, Fd, hw, pooled.data_ptr(), N.stream_ptr(fm.device)))
     want = fm.float().view(n, T, Fd, hw).mean(dim=(1, 3))
     assert rel_err(pooled, want) < 1e-5
 
