@@ -447,7 +447,7 @@ def main():
         mu = 2.0 * torch.randn(32, 128, device=dev, generator=g)
         yfit = torch.randint(0, 32, (20000,), device=dev, generator=g)
         ffit = mu[yfit] + torch.randn(20000, 128, device=dev, generator=g)
-        maha_alone = cm.MahalanobisOOD(32, dev, ridge=1e-3).fit(ffit, yfit)
+        maha_alone = cm.MahalanobisOOD(32, dev, ridge=1e-3).fit(ffit, yfit, all_reduce=False)       # rank-0-only block: no collectives
         n_feat = 2_000_000
         feat = mu[torch.randint(0, 32, (n_feat,), device=dev, generator=g)] + torch.randn(n_feat, 128, device=dev, generator=g)
         sc = torch.empty(n_feat, device=dev)

@@ -20,9 +20,9 @@ namespace lintc {
 using namespace tc;
 
 constexpr int CHUNK = 16384;
-constexpr int NS = 4;
-constexpr int OFF_A = 0, OFF_B = NS * CHUNK, OFF_BAR = 2 * NS * CHUNK;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int NS = 4;                                  // barrier slots (maximum ring depth); the depth in use is a launch parameter
+constexpr int SMEM_BYTES = 2 * NS * CHUNK + 256;
+constexpr int smem_bytes(int ns) { return 2 * ns * CHUNK + 256; }
 enum { B_AFULL = 0, B_AEMPTY = B_AFULL + NS, B_BFULL = B_AEMPTY + NS, B_BEMPTY = B_BFULL + NS, B_ACC = B_BEMPTY + NS, B_COUNT };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier area too small");
 constexpr int NT = 8 * 32 + 64;
@@ -36,6 +36,7 @@ struct Args {
     long long n;
     int relu;
     float* y;                  // (n, N)
+    int ns;                    // ring depth (2..NS): 2 stages = 64 KiB of shared memory, three CTAs of different layers / batches per SM
 };
 
 // folded fp32 W^T (K, N) row-major -> bf16 chunk images [ceil(N/128)][K/64][128 x 64 SW128], zero padded rows
@@ -54,10 +55,12 @@ __global__ void pack_linear_chunks_kernel(const float* __restrict__ wt, int K, i
     *reinterpret_cast<uint4*>(chunk + sw128_off(n & 127, j)) = u;
 }
 
-__global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const Args p) {
+__global__ void __launch_bounds__(NT, 2) linear_tc_kernel(const Args p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned long long trace_t0 = (tid == 0) ? trace_begin() : 0ull;
+    const int ns = p.ns;
+    const int OFF_A = 0, OFF_B = ns * CHUNK, OFF_BAR = 2 * ns * CHUNK;
     const uint32_t sbase = smem_u32(smem), bar0 = sbase + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * B_COUNT);
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const Args p) {
     constexpr int MMA_WARP = 8, LOAD_WARP = 9;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) {
+        for (int s = 0; s < ns; ++s) {
             mbar_init(BAR(B_AFULL + s), 8); mbar_init(BAR(B_AEMPTY + s), 1);
             mbar_init(BAR(B_BFULL + s), 1); mbar_init(BAR(B_BEMPTY + s), 1);
         }
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const Args p) {
                 mbar_wait(BAR(B_BEMPTY + stage), parity, 80);
                 mbar_expect_tx(BAR(B_BFULL + stage), CHUNK);
                 bulk_g2s(sbase + OFF_B + stage * CHUNK, p.w_img + ((size_t)nt * kc_n + kc) * CHUNK, CHUNK, BAR(B_BFULL + stage));
-                if (++stage == NS) { stage = 0; parity ^= 1; }
+                if (++stage == ns) { stage = 0; parity ^= 1; }
             }
         }
     } else if (warp == MMA_WARP) {
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const Args p) {
             for (int k = 0; k < 4; ++k)
                 if (leader) umma(tmem, dA + (uint64_t)(2 * k), dB + (uint64_t)(2 * k), ID128, (kc > 0 || k > 0) ? 1u : 0u);
             if (leader) { tc_commit(BAR(B_AEMPTY + stage)); tc_commit(BAR(B_BEMPTY + stage)); }
-            if (++stage == NS) { stage = 0; parity ^= 1; }
+            if (++stage == ns) { stage = 0; parity ^= 1; }
         }
         if (leader) tc_commit(BAR(B_ACC));
     } else {
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const Args p) {
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_AFULL + stage));
-            if (++stage == NS) { stage = 0; parity ^= 1; }
+            if (++stage == ns) { stage = 0; parity ^= 1; }
 #pragma unroll
             for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
         }
@@ -192,10 +195,12 @@ int launch_linear_tc(const uint8_t* w_img, const float* bias, const float* x1, c
         CMHAR_CHECK_CUDA(cudaFuncSetAttribute(lintc::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lintc::SMEM_BYTES));
         configured[dev & 63] = true;
     }
-    lintc::Args p{w_img, bias, x1, x2, x2 ? K1 : K, K, N, n, relu, y};
+    static int ns = 0;
+    if (ns == 0) { const char* e = getenv("CMHAR_LINEAR_NS"); ns = e ? atoi(e) : 2; if (ns < 2 || ns > lintc::NS) ns = 2; }      // development switch
+    lintc::Args p{w_img, bias, x1, x2, x2 ? K1 : K, K, N, n, relu, y, ns};
     const long long mt = (n + 127) / 128;
     CMHAR_REQUIRE(mt <= 0x7fffffffLL, "too many rows");
-    lintc::linear_tc_kernel<<<dim3((unsigned)mt, (unsigned)((N + 127) / 128)), lintc::NT, lintc::SMEM_BYTES, st>>>(p);
+    lintc::linear_tc_kernel<<<dim3((unsigned)mt, (unsigned)((N + 127) / 128)), lintc::NT, lintc::smem_bytes(ns), st>>>(p);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }

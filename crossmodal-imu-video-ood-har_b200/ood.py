@@ -112,9 +112,11 @@ class MahalanobisOOD:
                                                   cnt.data_ptr(), ssum.data_ptr(), second.data_ptr(),
                                                   _prec(precision), N.stream_ptr(f.device)))
 
-    def finalize(self) -> "MahalanobisOOD":
+    def finalize(self, all_reduce: bool = True) -> "MahalanobisOOD":
+        """``all_reduce=False`` keeps the fit local to this rank (a scorer fitted on replicated data, or code that only
+        one rank executes -- a collective entered by a single rank would hang the others)."""
         stats = self._stats
-        if _dist_on():
+        if all_reduce and _dist_on():
             stats = stats.clone()
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)       # 20 512 doubles over NCCL/NVLink
         host = stats.cpu().numpy()
@@ -124,10 +126,10 @@ class MahalanobisOOD:
         self._blobs.clear()
         return self
 
-    def fit(self, feats: torch.Tensor, labels: torch.Tensor) -> "MahalanobisOOD":
+    def fit(self, feats: torch.Tensor, labels: torch.Tensor, all_reduce: bool = True) -> "MahalanobisOOD":
         self.reset()
         self.accumulate(feats, labels)
-        return self.finalize()
+        return self.finalize(all_reduce=all_reduce)
 
     def blob(self, device) -> torch.Tensor:
         if self.fit_ is None:
