@@ -564,10 +564,15 @@ __global__ void __maxnreg__(NQ == 2 ? 152 : 104) imu_forward_bf16_kernel(const B
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 b = ld4(PB + PB_B1 + c * 128 + c0 + cc + i);
-                            f[i] = fmaxf(__uint_as_float(vv[cc + i]) + b.x, 0.f); f[i + 1] = fmaxf(__uint_as_float(vv[cc + i + 1]) + b.y, 0.f);
-                            f[i + 2] = fmaxf(__uint_as_float(vv[cc + i + 2]) + b.z, 0.f); f[i + 3] = fmaxf(__uint_as_float(vv[cc + i + 3]) + b.w, 0.f);
+                            f[i] = __uint_as_float(vv[cc + i]) + b.x; f[i + 1] = __uint_as_float(vv[cc + i + 1]) + b.y;
+                            f[i + 2] = __uint_as_float(vv[cc + i + 2]) + b.z; f[i + 3] = __uint_as_float(vv[cc + i + 3]) + b.w;
                         }
-                        store_tmem_bf16(lane_base + 128 * buf + c0 + (cc >> 1), f);      // hidden chunk over its own accumulator
+                        {   // ReLU rides on the bf16 conversion (cvt.rn.relu.bf16x2.f32): hidden chunk over its own accumulator
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16_relu(f[2 * i], f[2 * i + 1]);
+                            TMEM_ST16(lane_base + 128 * buf + c0 + (cc >> 1), pk);
+                        }
                     }
                     PROG(180 + c);
                     publish_tmem(B_HID + c);

@@ -180,6 +180,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// max(x, 0) fused into the conversion: one F2FP per pair instead of two FMNMX + one F2FP
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 // byte offset of the 16-byte piece holding columns [8j, 8j+8) of row r inside a [128 x 64] SW128 chunk
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
