@@ -114,3 +114,40 @@ def test_stream_host_equals_run_host():
     for g, w in zip(got, want):
         assert torch.equal(g["pred"], w["pred"]) and torch.equal(g["energy"], w["energy"])
         assert abs(float(g["loss"]) - float(w["loss"])) < 1e-12
+
+
+def test_pooling_taken_out_of_the_step_and_streamed_batches():
+    """``run(pooled=...)`` with the feature maps reduced beforehand -- by the default pooling kernel or by the
+    co-resident ring kernel -- gives the same pass as ``run(imu, fmap)``; ``stream_host`` (copy ring that waits on the
+    slot's own event) returns every batch's results in order and equal to the synchronous ``run_host``."""
+    clf, xm, sd_c, sd_x = build()
+    B, T = 48, 16
+    x = torch.from_numpy(W.imu_windows(8, B)).to(DEV)
+    f = torch.from_numpy(W.video_feature_maps(9, B, T)).to(DEV).to(torch.bfloat16)
+    pipe = cm.CrossModalOODPipeline(clf, xm, None, frames=T, precision="bf16")
+    ref = pipe.run(x, f)
+    for coresident in (False, True):
+        pooled = xm.video_encoder.pool_features(f, T, coresident=coresident)
+        got = pipe.run(x, None, pooled=pooled)
+        torch.cuda.synchronize()
+        assert torch.allclose(got["video_proj"], ref["video_proj"], rtol=0, atol=2e-6)
+        assert torch.equal(got["pred"], ref["pred"]) and abs(float(got["loss"]) - float(ref["loss"])) < 1e-6
+    # streamed host batches: 5 different batches through a 2-deep ring
+    batches = [(torch.from_numpy(W.imu_windows(20 + i, B)), torch.from_numpy(W.video_feature_maps(30 + i, B, T)).to(torch.bfloat16)) for i in range(5)]
+    sync = [{k: v.clone() for k, v in pipe.run_host(a, b).items()} for a, b in batches]
+    streamed = [{k: v.clone() for k, v in r.items()} for r in pipe.stream_host(iter(batches), depth=2)]
+    assert len(streamed) == len(sync)
+    for s, w in zip(streamed, sync):
+        assert torch.equal(s["pred"], w["pred"]) and torch.equal(s["energy"], w["energy"]) and float(s["loss"]) == float(w["loss"])
+
+
+def test_local_mahalanobis_fit_never_enters_a_collective():
+    """``fit(all_reduce=False)`` is what rank-0-only code (bench.py's scoring block) must use: same statistics as the
+    default on a single process, and no torch.distributed call."""
+    feats, labels = W.class_features(3, 3000)
+    f, y = torch.from_numpy(feats).to(DEV), torch.from_numpy(labels).to(DEV)
+    a = cm.MahalanobisOOD(32, DEV, ridge=1e-3).fit(f, y)
+    b = cm.MahalanobisOOD(32, DEV, ridge=1e-3).fit(f, y, all_reduce=False)
+    np.testing.assert_array_equal(a.fit_["whiten"], b.fit_["whiten"])
+    q = torch.from_numpy(W.class_features(4, 777, ood_fraction=0.3)[0]).to(DEV)
+    assert torch.equal(a.score(q, precision="bf16"), b.score(q, precision="bf16"))
