@@ -104,7 +104,7 @@ constexpr int TLOG_CAP = 1024;
 
 // ======================================================================================== kernel
 template <int NQ>
-__global__ void __maxnreg__(NQ == 2 ? 152 : 104) imu_forward_bf16_kernel(const Bf16Args args) {
+__global__ void __maxnreg__(NQ == 2 ? 152 : 96) imu_forward_bf16_kernel(const Bf16Args args) {
     constexpr int NT_EPI = 128 * NQ, CW = 128 / NQ, MMA_WARP = 4 * NQ, LOAD_WARP = 4 * NQ + 1;
     auto epi_bar = [] { epi_bar_n<NT_EPI>(); };
     extern __shared__ __align__(1024) uint8_t smem_tc[];
