@@ -143,9 +143,10 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restri
 // an SM whose tensor-core CTA (the encoder: 320 threads x 168 registers, 224 KiB of shared memory) leaves only
 // ~9 K registers and 2.8 KiB free, so the HBM-bound pooling of one batch overlaps the encoder of another.
 constexpr int POOL_NT = 128;
-template <typename T, int VEC /* elements per 16-byte vector, 0 = scalar path */>
+constexpr int POOL_UNROLL = 4;                // frames per explicit load batch (x up to two 16-byte loads each)
+template <typename T, int VEC /* elements per 16-byte vector, 0 = scalar path */, int U = POOL_UNROLL /* frames per load batch */>
 __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict__ fmap, long long n, int frames,
-                                                         int channels, int hw, float* __restrict__ pooled) {
+                                                         int channels, int hw, float* __restrict__ pooled, int batched) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= channels) return;
     const unsigned long long trace_t0 = (threadIdx.x == 0) ? trace_begin() : 0ull;
@@ -158,21 +159,52 @@ __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict
     float acc = 0.f;
     if constexpr (VEC > 0) {
         const int nv = hw / VEC;
-#pragma unroll 4
-        for (int t = 0; t < frames; ++t) {
-            const uint4* p = reinterpret_cast<const uint4*>(base + t * fstride);
-            for (int v = 0; v < nv; ++v) {
-                uint4 u;
-                asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                             : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p + v), "l"(stream_policy));
-                if (sizeof(T) == 2) {
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+        auto ld16 = [&](const uint4* q) {
+            uint4 u;
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(q), "l"(stream_policy));
+            return u;
+        };
+        auto add16 = [&](const uint4& u) {
+            if (sizeof(T) == 2) {
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h2[q]); acc += f.x + f.y; }
-                } else {
-                    const float* f = reinterpret_cast<const float*>(&u);
-                    acc += (f[0] + f[1]) + (f[2] + f[3]);
+                for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h2[q]); acc += f.x + f.y; }
+            } else {
+                const float* f = reinterpret_cast<const float*>(&u);
+                acc += (f[0] + f[1]) + (f[2] + f[3]);
+            }
+        };
+        if (nv <= 2 && batched) {
+            // explicit batches: the 8 loads of 4 frames are ALL issued before the first is consumed (the compiler otherwise
+            // pairs every volatile load with its use and keeps ~2 in flight per thread)
+            for (int t0 = 0; t0 < frames; t0 += U) {
+                uint4 u[U][2];
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        u[i][v] = make_uint4(0u, 0u, 0u, 0u);
+                        if (t0 + i < frames && v < nv) u[i][v] = ld16(reinterpret_cast<const uint4*>(base + (t0 + i) * fstride) + v);
+                    }
                 }
+                // fence for the scheduler: an empty volatile asm that "rewrites" every loaded register keeps all the adds behind
+                // all the loads
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) asm volatile("" : "+r"(u[i][v].x), "+r"(u[i][v].y), "+r"(u[i][v].z), "+r"(u[i][v].w));
+                }
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) add16(u[i][v]);
+                }
+            }
+        } else {
+            for (int t = 0; t < frames; ++t) {
+                const uint4* p = reinterpret_cast<const uint4*>(base + t * fstride);
+                for (int v = 0; v < nv; ++v) add16(ld16(p + v));
             }
         }
     } else {
@@ -470,6 +502,8 @@ int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frame
     if (mode < 0) { const char* e = getenv("CMHAR_POOL_MODE"); mode = e ? atoi(e) : 1; }        // 1 = flood (default), 2 = ring
     if (mode == 2 && pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw))
         return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, st);
+    static int batched = -1;
+    if (batched < 0) { const char* e = getenv("CMHAR_POOL_BATCH"); batched = e ? atoi(e) : 1; }      // development switch
     static int cap_y = -1;
     if (cap_y < 0) { const char* e = getenv("CMHAR_POOL_GRIDY"); cap_y = e ? atoi(e) : 0; }      // development switch
     long long gy = n < 32768 ? n : 32768;
@@ -478,14 +512,17 @@ int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frame
     const bool aligned = ((uintptr_t)fmap & 15) == 0;
     if (is_bf16) {
         if (aligned && hw % 8 == 0)
-            video_pool_kernel<__nv_bfloat16, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled);
+        {
+            if (batched == 8) video_pool_kernel<__nv_bfloat16, 8, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched);
+            else video_pool_kernel<__nv_bfloat16, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched);
+        }
         else
-            video_pool_kernel<__nv_bfloat16, 0><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled);
+            video_pool_kernel<__nv_bfloat16, 0><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched);
     } else {
         if (aligned && hw % 4 == 0)
-            video_pool_kernel<float, 4><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled);
+            video_pool_kernel<float, 4><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched);
         else
-            video_pool_kernel<float, 0><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled);
+            video_pool_kernel<float, 0><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched);
     }
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
