@@ -146,7 +146,7 @@ constexpr int POOL_NT = 128;
 constexpr int POOL_UNROLL = 4;                // frames per explicit load batch (x up to two 16-byte loads each)
 template <typename T, int VEC /* elements per 16-byte vector, 0 = scalar path */, int U = POOL_UNROLL /* frames per load batch */>
 __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict__ fmap, long long n, int frames,
-                                                         int channels, int hw, float* __restrict__ pooled, int batched) {
+                                                         int channels, int hw, float* __restrict__ pooled, int batched, uint8_t* __restrict__ img) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= channels) return;
     const unsigned long long trace_t0 = (threadIdx.x == 0) ? trace_begin() : 0ull;
@@ -214,7 +214,13 @@ __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict
                 else acc += reinterpret_cast<const float*>(base + t * fstride)[p];
             }
     }
-    pooled[b * channels + c] = acc / (float)(frames * hw);
+    const float mean = acc / (float)(frames * hw);
+    if (pooled) pooled[b * channels + c] = mean;
+    if (img) {      // the same value as one bf16 element of the operand image [ceil(n/128)][channels/64][128 x 64 SW128] the
+                    // projection layer's producer copies straight into its A ring (a warp writes 64 contiguous bytes)
+        uint8_t* chunk = img + ((size_t)(b >> 7) * (channels >> 6) + (c >> 6)) * 16384;
+        *reinterpret_cast<__nv_bfloat16*>(chunk + tc::sw128_off((int)(b & 127), (c & 63) >> 3) + (c & 7) * 2) = __float2bfloat16_rn(mean);
+    }
     }
     if (threadIdx.x == 0) trace_end(TRACE_POOL, trace_t0);
 }
@@ -337,7 +343,7 @@ bool linear_tc_eligible(int in_dim, int out_dim);                               
 size_t linear_tc_bytes(int in_dim, int out_dim);
 int pack_linear_tc(const float* wt_f32, int in_dim, int out_dim, uint8_t* dst, cudaStream_t st);
 int launch_linear_tc(const uint8_t* w_img, const float* bias, const float* x1, const float* x2, int K1, long long n, int K, int N,
-                     int relu, float* y, cudaStream_t st);
+                     int relu, float* y, cudaStream_t st, const uint8_t* a_img, uint8_t* y_img);
 static size_t linear_fp32_floats(int in_dim, int out_dim) { return (size_t)in_dim * out_dim + out_dim; }
 }  // namespace cmhar
 
@@ -397,7 +403,7 @@ static int linear_forward_impl(const void* blob, const float* x, const float* x2
         if (lookup_blob(blob, &bi) && bi.magic == LIN_MAGIC && bi.has_tc && bi.a == in_dim && bi.b == out_dim && (k1 % 32) == 0 &&
             ((uintptr_t)x & 15) == 0 && (!x2 || ((uintptr_t)x2 & 15) == 0) && ((uintptr_t)y & 15) == 0)
             return launch_linear_tc(reinterpret_cast<const uint8_t*>(blob) + tc_section_offset(linear_fp32_floats(in_dim, out_dim)),
-                                    f + (size_t)in_dim * out_dim, x, x2, k1, n, in_dim, out_dim, relu, y, (cudaStream_t)s);
+                                    f + (size_t)in_dim * out_dim, x, x2, k1, n, in_dim, out_dim, relu, y, (cudaStream_t)s, nullptr, nullptr);
     }
     const unsigned gx = (unsigned)((n + LT_ROWS - 1) / LT_ROWS), gy = (unsigned)((out_dim + LT_COLS - 1) / LT_COLS);
     // k-split only when the plain grid cannot fill the machine and the caller gave a workspace
@@ -432,6 +438,28 @@ int cmhar_concat_linear_forward(const void* blob, const float* x1, int32_t in_di
     CMHAR_REQUIRE(x2 && in_dim1 >= 4 && in_dim2 >= 4 && !(in_dim1 & 3) && !(in_dim2 & 3),
                   "cmhar_concat_linear_forward: both inputs need a multiple-of-4 width (%d, %d)", in_dim1, in_dim2);
     return linear_forward_impl(blob, x1, x2, in_dim1, n, in_dim1 + in_dim2, out_dim, relu, y, work, work_bytes, precision, s);
+}
+
+size_t cmhar_operand_image_bytes(int64_t n, int32_t dim) {
+    if (n <= 0 || dim < 64 || dim % 64) return 0;
+    return (size_t)((n + 127) / 128) * (size_t)(dim / 64) * 16384;
+}
+
+int cmhar_linear_forward_img(const void* blob, const float* x, const void* x_img, int64_t n, int32_t in_dim, int32_t out_dim,
+                             int32_t relu, float* y, void* y_img, cmhar_stream_t s) {
+    CMHAR_REQUIRE(blob && (x || x_img) && (y || y_img), "cmhar_linear_forward_img: needs an input and an output");
+    CMHAR_REQUIRE(!y_img || out_dim % 64 == 0, "cmhar_linear_forward_img: an output image needs out_dim %% 64 == 0 (got %d)", out_dim);
+    if (n <= 0) return CMHAR_OK;
+    BlobInfo bi{};
+    CMHAR_REQUIRE(lookup_blob(blob, &bi) && bi.magic == LIN_MAGIC && bi.has_tc && bi.a == in_dim && bi.b == out_dim,
+                  "cmhar_linear_forward_img: the blob has no tensor-core section for (%d,%d)", in_dim, out_dim);
+    CMHAR_REQUIRE(x_img || (in_dim % 32 == 0 && ((uintptr_t)x & 15) == 0), "cmhar_linear_forward_img: misaligned fp32 input");
+    CMHAR_REQUIRE((!y || ((uintptr_t)y & 15) == 0) && (!x_img || ((uintptr_t)x_img & 15) == 0) && (!y_img || ((uintptr_t)y_img & 15) == 0),
+                  "cmhar_linear_forward_img: misaligned buffer");
+    const float* f = reinterpret_cast<const float*>(reinterpret_cast<const char*>(blob) + sizeof(BlobHeader));
+    return launch_linear_tc(reinterpret_cast<const uint8_t*>(blob) + tc_section_offset(linear_fp32_floats(in_dim, out_dim)),
+                            f + (size_t)in_dim * out_dim, x, nullptr, in_dim, n, in_dim, out_dim, relu, y, (cudaStream_t)s,
+                            reinterpret_cast<const uint8_t*>(x_img), reinterpret_cast<uint8_t*>(y_img));
 }
 
 int cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmhar_stream_t s) {
@@ -488,9 +516,10 @@ int cmhar_video_pool_coresident(const void* fmap, int32_t is_bf16, int64_t n, in
     return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, (cudaStream_t)s);
 }
 
-int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
-                     float* pooled, cmhar_stream_t s) {
-    CMHAR_REQUIRE(fmap && pooled && frames > 0 && channels > 0 && hw > 0, "cmhar_video_pool: bad argument");
+static int video_pool_impl(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
+                           float* pooled, uint8_t* img, cmhar_stream_t s) {
+    CMHAR_REQUIRE(fmap && (pooled || img) && frames > 0 && channels > 0 && hw > 0, "cmhar_video_pool: bad argument");
+    CMHAR_REQUIRE(!img || channels % 64 == 0, "cmhar_video_pool_img: an operand image needs channels %% 64 == 0 (got %d)", channels);
     if (n <= 0) return CMHAR_OK;
     cudaStream_t st = (cudaStream_t)s;
     // Default: the flooding kernel below (101 % of the measured copy bandwidth at 2 048 clips; 60 % at 256).  The
@@ -500,7 +529,7 @@ int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frame
     // 29.9 us on one B200 box and 34.3 us on another, against a steady 32.5 us for the flooding kernel.
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("CMHAR_POOL_MODE"); mode = e ? atoi(e) : 1; }        // 1 = flood (default), 2 = ring
-    if (mode == 2 && pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw))
+    if (mode == 2 && !img && pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw))
         return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, st);
     static int batched = -1;
     if (batched < 0) { const char* e = getenv("CMHAR_POOL_BATCH"); batched = e ? atoi(e) : 1; }      // development switch
@@ -513,19 +542,30 @@ int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frame
     if (is_bf16) {
         if (aligned && hw % 8 == 0)
         {
-            if (batched == 8) video_pool_kernel<__nv_bfloat16, 8, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched);
-            else video_pool_kernel<__nv_bfloat16, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched);
+            if (batched == 8) video_pool_kernel<__nv_bfloat16, 8, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
+            else video_pool_kernel<__nv_bfloat16, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
         }
         else
-            video_pool_kernel<__nv_bfloat16, 0><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched);
+            video_pool_kernel<__nv_bfloat16, 0><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
     } else {
         if (aligned && hw % 4 == 0)
-            video_pool_kernel<float, 4><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched);
+            video_pool_kernel<float, 4><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img);
         else
-            video_pool_kernel<float, 0><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched);
+            video_pool_kernel<float, 0><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img);
     }
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
+}
+
+int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
+                     float* pooled, cmhar_stream_t s) {
+    CMHAR_REQUIRE(pooled, "cmhar_video_pool: null output");
+    return video_pool_impl(fmap, is_bf16, n, frames, channels, hw, pooled, nullptr, s);
+}
+
+int cmhar_video_pool_img(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
+                         float* pooled, void* pooled_img, cmhar_stream_t s) {
+    return video_pool_impl(fmap, is_bf16, n, frames, channels, hw, pooled, reinterpret_cast<uint8_t*>(pooled_img), s);
 }
 
 }  // extern "C"

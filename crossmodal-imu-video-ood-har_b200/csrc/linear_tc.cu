@@ -37,6 +37,8 @@ struct Args {
     int relu;
     float* y;                  // (n, N)
     int ns;                    // ring depth (2..NS): 2 stages = 64 KiB of shared memory, three CTAs of different layers / batches per SM
+    const uint8_t* a_img;      // activations already as bf16 chunk images [row tile][k chunk] (the previous layer's y_img), or null
+    uint8_t* y_img;            // also / instead write the output as bf16 chunk images [row tile][N/64] for the next layer, or null
 };
 
 // folded fp32 W^T (K, N) row-major -> bf16 chunk images [ceil(N/128)][K/64][128 x 64 SW128], zero padded rows
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(NT, 2) linear_tc_kernel(const Args p) {
 
     if (tid == 0) {
         for (int s = 0; s < ns; ++s) {
-            mbar_init(BAR(B_AFULL + s), 8); mbar_init(BAR(B_AEMPTY + s), 1);
+            mbar_init(BAR(B_AFULL + s), p.a_img ? 1 : 8); mbar_init(BAR(B_AEMPTY + s), 1);
             mbar_init(BAR(B_BFULL + s), 1); mbar_init(BAR(B_BEMPTY + s), 1);
         }
         mbar_init(BAR(B_ACC), 1);
@@ -93,6 +95,11 @@ __global__ void __launch_bounds__(NT, 2) linear_tc_kernel(const Args p) {
                 mbar_wait(BAR(B_BEMPTY + stage), parity, 80);
                 mbar_expect_tx(BAR(B_BFULL + stage), CHUNK);
                 bulk_g2s(sbase + OFF_B + stage * CHUNK, p.w_img + ((size_t)nt * kc_n + kc) * CHUNK, CHUNK, BAR(B_BFULL + stage));
+                if (p.a_img) {      // the activation tile is a ready-made operand image: a plain bulk copy, no staging warps
+                    mbar_wait(BAR(B_AEMPTY + stage), parity, 85);
+                    mbar_expect_tx(BAR(B_AFULL + stage), CHUNK);
+                    bulk_g2s(sbase + OFF_A + stage * CHUNK, p.a_img + ((size_t)blockIdx.x * kc_n + kc) * CHUNK, CHUNK, BAR(B_AFULL + stage));
+                }
                 if (++stage == ns) { stage = 0; parity ^= 1; }
             }
         }
@@ -128,8 +135,8 @@ __global__ void __launch_bounds__(NT, 2) linear_tc_kernel(const Args p) {
             for (int i = 0; i < 8; ++i) t[i] = ok ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         float4 cur[8], nxt[8];
-        fetch(0, cur);
-        for (int kc = 0; kc < kc_n; ++kc) {
+        if (!p.a_img) fetch(0, cur);
+        for (int kc = 0; kc < (p.a_img ? 0 : kc_n); ++kc) {
             if (kc + 1 < kc_n) fetch(kc + 1, nxt);
             float f[32];
 #pragma unroll
@@ -150,8 +157,8 @@ __global__ void __launch_bounds__(NT, 2) linear_tc_kernel(const Args p) {
         TMEM_LD32(lane_base + half * 64, v);
         TMEM_LD32(lane_base + half * 64 + 32, (v + 32));
         tc_wait_ld();
-        if (ok) {
-            const int c0 = nt * 128 + half * 64;
+        const int c0 = nt * 128 + half * 64;
+        if (ok && p.y) {
             float* dst = p.y + r * p.N + c0;
 #pragma unroll
             for (int i = 0; i < 64; i += 4) {
@@ -162,6 +169,23 @@ __global__ void __launch_bounds__(NT, 2) linear_tc_kernel(const Args p) {
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     *reinterpret_cast<float4*>(dst + i) = o;
                 }
+            }
+        }
+        if (p.y_img && c0 < p.N) {
+            // the same 64 columns as one row of chunk (nt*2 + half) of this row tile's operand image (N % 64 == 0): what the
+            // next layer's producer copies straight into its A ring.  Rows past n are written as zeros.
+            uint8_t* chunk = p.y_img + ((size_t)blockIdx.x * (p.N / 64) + (c0 >> 6)) * CHUNK;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o[e] = ok ? __uint_as_float(v[8 * j + e]) + __ldg(p.bias + c0 + 8 * j + e) : 0.f;
+                    if (p.relu) o[e] = fmaxf(o[e], 0.f);
+                }
+                uint4 u;
+                u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+                *reinterpret_cast<uint4*>(chunk + sw128_off(row, j)) = u;
             }
         }
     }
@@ -187,7 +211,7 @@ int pack_linear_tc(const float* wt_f32, int in_dim, int out_dim, uint8_t* dst, c
 }
 
 int launch_linear_tc(const uint8_t* w_img, const float* bias, const float* x1, const float* x2, int K1, long long n, int K, int N,
-                     int relu, float* y, cudaStream_t st) {
+                     int relu, float* y, cudaStream_t st, const uint8_t* a_img = nullptr, uint8_t* y_img = nullptr) {
     static bool configured[64] = {};
     int dev = 0;
     CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -197,7 +221,7 @@ int launch_linear_tc(const uint8_t* w_img, const float* bias, const float* x1, c
     }
     static int ns = 0;
     if (ns == 0) { const char* e = getenv("CMHAR_LINEAR_NS"); ns = e ? atoi(e) : 2; if (ns < 2 || ns > lintc::NS) ns = 2; }      // development switch
-    lintc::Args p{w_img, bias, x1, x2, x2 ? K1 : K, K, N, n, relu, y, ns};
+    lintc::Args p{w_img, bias, x1, x2, x2 ? K1 : K, K, N, n, relu, y, ns, a_img, y_img};
     const long long mt = (n + 127) / 128;
     CMHAR_REQUIRE(mt <= 0x7fffffffLL, "too many rows");
     lintc::linear_tc_kernel<<<dim3((unsigned)mt, (unsigned)((N + 127) / 128)), lintc::NT, lintc::smem_bytes(ns), st>>>(p);

@@ -333,6 +333,29 @@ class _PackedLinear:
                                              N.stream_ptr(x.device)))
         return y
 
+    def forward_img(self, n: int, relu: bool, x: Optional[torch.Tensor] = None, x_img: Optional[torch.Tensor] = None,
+                    want_rows: bool = True, want_img: bool = False):
+        """Tensor-core path with operand images on either side (bf16 precision only): the input is fp32 rows ``x`` or the
+        previous layer's image ``x_img``; returns (rows or None, image or None)."""
+        dev = (x if x is not None else x_img).device
+        y = torch.empty((n, self.out_dim), dtype=torch.float32, device=dev) if want_rows else None
+        img = operand_image(n, self.out_dim, dev) if want_img else None
+        if x is not None:
+            x = N.f32c(x)
+        with torch.cuda.device(dev):
+            N.check(N.lib().cmhar_linear_forward_img(self.blob.data_ptr(), N.ptr(x), N.ptr(x_img), n, self.in_dim, self.out_dim,
+                                                     int(relu), N.ptr(y), N.ptr(img), N.stream_ptr(dev)))
+        return y, img
+
+    def img_capable(self) -> bool:
+        return self.in_dim % 64 == 0 and self.out_dim % 64 == 0
+
+
+def operand_image(n: int, dim: int, device) -> torch.Tensor:
+    """Uninitialised bf16 operand image for (n, dim) activations: [ceil(n/128)][dim/64] SWIZZLE_128B chunks of 16 KiB
+    (what ``cmhar_linear_forward_img`` writes for the next layer and ``cmhar_similarity`` builds for its operands)."""
+    return N.alloc_blob(N.lib().cmhar_operand_image_bytes(n, dim), device)
+
 
 def l2_normalize_native(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     x = N.f32c(x)
@@ -390,10 +413,12 @@ class VideoEncoder(_PackedMixin, nn.Module):
         return self._packed[key]
 
     def pool_features(self, fmap: torch.Tensor, frames: int, out: Optional[torch.Tensor] = None,
-                      coresident: bool = False) -> torch.Tensor:
+                      coresident: bool = False, want_img: bool = False, want_rows: bool = True):
         """HBM-bound half of the native tail: fmap (B*T, F, h, w) bf16/fp32 -> spatio-temporal mean (B, F) fp32
         (reference models.py:210-211,215 commuted in front of the linear projection).  ``coresident`` selects the
-        one-small-CTA-per-SM ring kernel that can run next to the encoder's CTAs (see include/cmhar_b200.h)."""
+        one-small-CTA-per-SM ring kernel that can run next to the encoder's CTAs (see include/cmhar_b200.h).
+        ``want_img``: returns ``(rows or None, image)`` with the result (also) as a bf16 operand image for
+        ``project_pooled(..., x_img=image)`` -- the projection then reads no fp32 rows at all."""
         N.require_cuda(fmap, "VideoEncoder")
         if fmap.dtype not in (torch.float32, torch.bfloat16):
             fmap = fmap.float()
@@ -403,16 +428,36 @@ class VideoEncoder(_PackedMixin, nn.Module):
         if BT % frames:
             raise ValueError(f"{BT} frames do not split into clips of {frames}")
         B = BT // frames
-        pooled = out if out is not None else torch.empty((B, Fd), dtype=torch.float32, device=fmap.device)
+        want_img = want_img and Fd % 64 == 0 and B > 0 and not coresident
+        pooled = out
+        if pooled is None and (want_rows or not want_img):
+            pooled = torch.empty((B, Fd), dtype=torch.float32, device=fmap.device)
         with torch.cuda.device(fmap.device):
+            if want_img:
+                img = operand_image(B, Fd, fmap.device)
+                N.check(N.lib().cmhar_video_pool_img(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw,
+                                                     N.ptr(pooled), img.data_ptr(), N.stream_ptr(fmap.device)))
+                return pooled, img
             fn = N.lib().cmhar_video_pool_coresident if coresident else N.lib().cmhar_video_pool
             N.check(fn(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw,
                        pooled.data_ptr(), N.stream_ptr(fmap.device)))
         return pooled
 
-    def project_pooled(self, pooled: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
-        """(B, F) pooled features -> (B, video_d_model): the reference's ``projection`` (models.py:213)."""
-        return self._packed_projection(pooled.device)(pooled, relu=False, precision=precision)
+    def project_pooled(self, pooled: Optional[torch.Tensor], precision: Optional[str] = None, want_img: bool = False,
+                       x_img: Optional[torch.Tensor] = None, n: Optional[int] = None):
+        """(B, F) pooled features -> (B, video_d_model): the reference's ``projection`` (models.py:213).  ``want_img``
+        (bf16 precision): also returns the feature as a bf16 operand image for the projection head that follows;
+        ``x_img`` (+ ``n`` rows): the pooled features as an operand image from ``pool_features(want_img=True)``."""
+        dev = (pooled if pooled is not None else x_img).device
+        lin = self._packed_projection(dev)
+        rows = pooled.shape[0] if pooled is not None else int(n)
+        if (want_img or x_img is not None) and _prec_code(precision) == N.BF16 and lin.img_capable() and rows > 0:
+            y, img = lin.forward_img(rows, False, x=pooled if x_img is None else None, x_img=x_img, want_rows=True, want_img=want_img)
+            return (y, img) if want_img else y
+        if pooled is None:
+            raise ValueError("project_pooled: the operand-image input needs the bf16 tensor-core path")
+        y = lin(pooled, relu=False, precision=precision)
+        return (y, None) if want_img else y
 
     def forward_features(self, fmap: torch.Tensor, frames: int, precision: Optional[str] = None) -> torch.Tensor:
         """Native tail: fmap (B*T, F, h, w) bf16/fp32 -> (B, video_d_model) fp32."""
@@ -475,10 +520,17 @@ class ProjectionHead(_PackedMixin, nn.Module):
                                  _PackedLinear(self.net[3], None, device))
         return self._packed[key]
 
-    def forward_native(self, x, precision: Optional[str] = None):
-        """Inference route with an explicit precision ('bf16' = tcgen05 tiles, 'fp32' = CUDA-core tiles)."""
+    def forward_native(self, x, precision: Optional[str] = None, x_img: Optional[torch.Tensor] = None):
+        """Inference route with an explicit precision ('bf16' = tcgen05 tiles, 'fp32' = CUDA-core tiles).  ``x_img``:
+        the input already as a bf16 operand image (``VideoEncoder.project_pooled(..., want_img=True)``)."""
         N.require_cuda(x, "ProjectionHead")
         l0, l1 = self._packed_layers(x.device)
+        if _prec_code(precision) == N.BF16 and l0.img_capable() and l1.in_dim % 64 == 0 and x.dim() == 2 and x.shape[0] > 0:
+            # the hidden activation goes from layer to layer as a bf16 operand image (never as fp32 rows): the second
+            # layer's A operand is a plain bulk copy.  Same bits as the fp32-row hand-off (both round to bf16 once).
+            n = x.shape[0]
+            _, h_img = l0.forward_img(n, True, x=x if x_img is None else None, x_img=x_img, want_rows=False, want_img=True)
+            return l1.forward_img(n, False, x_img=h_img, want_rows=True)[0]
         return l1(l0(x, relu=True, precision=precision), relu=False, precision=precision)
 
     def forward(self, x):

@@ -23,7 +23,7 @@ import torch
 from . import _native as N
 from .losses import similarity_native
 from .fusion import LateFusionClassifier
-from .models import CrossModalModel, IMUClassifier, imu_forward_native, l2_normalize_native
+from .models import CrossModalModel, IMUClassifier, imu_forward_native, l2_normalize_native, _prec_code
 from .ood import MahalanobisOOD
 
 __all__ = ["CrossModalOODPipeline"]
@@ -65,10 +65,15 @@ class CrossModalOODPipeline:
         side = self._side
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            ve, pimg, nclips = self.xm.video_encoder, None, None
             if pooled is None:
-                pooled = self.xm.video_encoder.pool_features(fmap, self.frames)
-            vfeat = self.xm.video_encoder.project_pooled(pooled, precision=self.precision)
-            vp = l2_normalize_native(self.xm.video_proj.forward_native(vfeat, self.precision))
+                if _prec_code(self.precision) == N.BF16:      # pooled features go straight into a bf16 operand image
+                    nclips = fmap.shape[0] // self.frames
+                    pooled, pimg = ve.pool_features(fmap, self.frames, want_img=True, want_rows=False)
+                else:
+                    pooled = ve.pool_features(fmap, self.frames)
+            vfeat, vimg = ve.project_pooled(pooled, precision=self.precision, want_img=True, x_img=pimg, n=nclips)
+            vp = l2_normalize_native(self.xm.video_proj.forward_native(vfeat, self.precision, x_img=vimg))
         if self.fusion is None:
             out = self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
         else:

@@ -179,6 +179,17 @@ int    cmhar_linear_forward(const void* blob, const float* x, int64_t n, int32_t
 int    cmhar_concat_linear_forward(const void* blob, const float* x1, int32_t in_dim1, const float* x2,
                                    int32_t in_dim2, int64_t n, int32_t out_dim, int32_t relu, float* y,
                                    void* work, size_t work_bytes, int32_t precision, cmhar_stream_t s);
+/* Tensor-core dense layer (CMHAR_BF16 tiles) with operand images on either side: a chain of layers hands its
+ * activations over as bf16 SWIZZLE_128B chunk images [ceil(n/128)][dim/64][128 x 64] (16 KiB each, the layout
+ * cmhar_similarity builds for its operands) instead of fp32 rows, so the consumer's A operand is a plain
+ * cp.async.bulk copy -- no staging warps, no per-chunk L2 round trip (reference ProjectionHead.forward,
+ * src/models/models.py:226-234: Linear -> BN -> ReLU -> Linear).  x / x_img: exactly one input form is used (x_img
+ * wins); y / y_img: either or both outputs.  Bit-identical to cmhar_linear_forward(CMHAR_BF16): both round the
+ * activation to bf16 (RN) before the MMA. */
+size_t cmhar_operand_image_bytes(int64_t n, int32_t dim);
+int    cmhar_linear_forward_img(const void* blob, const float* x, const void* x_img, int64_t n, int32_t in_dim,
+                                int32_t out_dim, int32_t relu, float* y, void* y_img, cmhar_stream_t s);
+
 /* rows x / max(||x||_2, 1e-12)   (F.normalize(dim=1), models.py:288-289); in place allowed */
 int    cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmhar_stream_t s);
 
@@ -219,6 +230,11 @@ int    cmhar_conv_encoder_forward(const void* blob, const float* x, int64_t n, i
  * pooled (n, channels) fp32 = mean over frames and hw.  The projection is cmhar_linear_forward. */
 int cmhar_video_pool(const void* fmap, int32_t fmap_is_bf16, int64_t n, int32_t frames,
                      int32_t channels, int32_t hw, float* pooled, cmhar_stream_t s);
+
+/* Same reduction, with the result (also) written as a bf16 operand image [ceil(n/128)][channels/64][128 x 64] for
+ * cmhar_linear_forward_img (the projection layer then needs no fp32 staging); pooled may be NULL. channels % 64 == 0. */
+int cmhar_video_pool_img(const void* fmap, int32_t fmap_is_bf16, int64_t n, int32_t frames, int32_t channels,
+                         int32_t hw, float* pooled, void* pooled_img, cmhar_stream_t s);
 
 /* Same reduction by the co-resident kernel: ONE 128-thread CTA per SM streams [128 channels x hw] slabs through a
  * 32 KiB cp.async.bulk ring (<= 40 registers per thread), small enough to be resident next to an encoder CTA, so

@@ -151,3 +151,41 @@ def test_local_mahalanobis_fit_never_enters_a_collective():
     np.testing.assert_array_equal(a.fit_["whiten"], b.fit_["whiten"])
     q = torch.from_numpy(W.class_features(4, 777, ood_fraction=0.3)[0]).to(DEV)
     assert torch.equal(a.score(q, precision="bf16"), b.score(q, precision="bf16"))
+
+
+@pytest.mark.parametrize("n", [5, 128, 300])
+def test_projection_head_operand_image_chain_is_bit_identical(n):
+    """bf16 path: the hidden activation handed from layer to layer as a bf16 operand image (cmhar_linear_forward_img)
+    gives exactly the bits of the fp32-row hand-off -- both round the activation to bf16 once -- for both heads
+    (K = 128 and K = 768), ragged and multi-tile row counts, and for the video feature handed over as an image."""
+    clf, xm, sd_c, sd_x = build()
+    rs = np.random.RandomState(n)
+    for head, k in ((xm.imu_proj, 128), (xm.video_proj, 768)):
+        x = torch.from_numpy(rs.standard_normal((n, k)).astype(np.float32)).to(DEV)
+        l0, l1 = head._packed_layers(x.device)
+        rows = l1(l0(x, relu=True, precision="bf16"), relu=False, precision="bf16")
+        chained = head.forward_native(x, "bf16")
+        torch.cuda.synchronize()
+        assert torch.equal(rows, chained)
+    pooled = torch.from_numpy(np.maximum(rs.standard_normal((n, 512)), 0).astype(np.float32)).to(DEV)
+    vfeat, vimg = xm.video_encoder.project_pooled(pooled, precision="bf16", want_img=True)
+    assert torch.equal(vfeat, xm.video_encoder.project_pooled(pooled, precision="bf16"))
+    assert torch.equal(xm.video_proj.forward_native(vfeat, "bf16", x_img=vimg), xm.video_proj.forward_native(vfeat, "bf16"))
+
+
+@pytest.mark.parametrize("n", [3, 129, 256])
+def test_pooling_into_operand_image_matches_row_path(n):
+    """cmhar_video_pool_img: the pooled features written directly as a bf16 operand image feed the projection layer with
+    the same bits as the fp32-row route (the staging path rounds the same fp32 value to bf16)."""
+    clf, xm, sd_c, sd_x = build()
+    T = 16
+    f = torch.from_numpy(W.video_feature_maps(40 + n, n, T)).to(DEV).to(torch.bfloat16)
+    ve = xm.video_encoder
+    rows = ve.pool_features(f, T)
+    both_rows, img = ve.pool_features(f, T, want_img=True)
+    none_rows, img2 = ve.pool_features(f, T, want_img=True, want_rows=False)
+    torch.cuda.synchronize()
+    assert none_rows is None and torch.equal(rows, both_rows)
+    want = ve.project_pooled(rows, precision="bf16")
+    assert torch.equal(ve.project_pooled(None, precision="bf16", x_img=img, n=n), want)
+    assert torch.equal(ve.project_pooled(None, precision="bf16", x_img=img2, n=n), want)

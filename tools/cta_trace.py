@@ -13,7 +13,7 @@ cfg = cm.default_config()
 clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg).to(dev).eval()
 xm = cm.CrossModalModel(cfg).to(dev).eval()
 fus = cm.LateFusionClassifier(clf.imu_encoder, xm.video_encoder, cfg).to(dev).eval()
-B, L, STEPS = 256, 8, 400
+B, L, STEPS = 256, int(os.environ.get("LANES", "16")), 400
 xs = [torch.randn(B, 6, 250, device=dev) for _ in range(L)]
 fs = [torch.relu(torch.randn(B * 16, 512, 4, 4, device=dev)).to(torch.bfloat16) for _ in range(L)]
 pooled = [torch.empty(B, 512, device=dev) for _ in range(L)]
