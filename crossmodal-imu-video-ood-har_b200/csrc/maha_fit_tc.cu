@@ -6,14 +6,17 @@
 //
 // The CUDA-core kernel (ood.cu) is fp32-FMA bound at 4 % of the HBM roofline the stage should sit on (AI = 64
 // flop/B).  Here both reductions are GEMMs over the ROW dimension, K = rows:
-//     M       (128 x 128) += F^T F          A = B = F^T tile
-//     sum     (128 x 128) += O^T F          A = one-hot(labels)^T tile (class slots x rows), B = F^T tile
+//     M    (128 x 128) += F^T F          A = B = F^T tile
+//     sum  (128 x 64)  += F^T O          A = F^T tile, B = one-hot(labels)^T tile (class slots x rows)
 // with F split as hi + lo bf16 (all four hi/lo products for M -- the lo*lo term removes the only systematic bias,
 // on the diagonal -- and both for the class sums; one-hot entries are exact in bf16), fp32 accumulation in TMEM
 // across all the tiles of a CTA, flushed with fp64 atomics every 256 tiles.
-// F^T has rows contiguous along K, i.e. it is the TRANSPOSE of the feature tile in memory: the 8 staging warps
-// read feature rows (coalesced float4) and scatter 2-byte elements into K-major SWIZZLE_128B tiles -- a warp's 32
-// lanes hold consecutive rows of the same feature, so each store instruction covers 64 contiguous bytes.
+// F^T is never materialised: the feature tile is stored exactly as the score kernel stores it -- [128 rows x 64
+// features] SWIZZLE_128B chunks, coalesced 512-byte row loads and conflict-free 8-byte stores -- and handed to the
+// tensor core as an MN-MAJOR operand (instruction-descriptor bits 15/16; canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO))
+// in 16-byte units, cute/atom/mma_traits_sm100.hpp: LBO = 16 KiB between the two 64-feature groups, SBO = 1 KiB
+// between 8-row groups, a K = 16 step advances the start address by 2 KiB).  The first version scattered 2-byte
+// elements into a transposed K-major tile (192 stores per thread per tile) and was staging-bound at 29 % of HBM.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -22,19 +25,30 @@ namespace fittc {
 
 using namespace tc;
 
-constexpr int CHUNK = 16384;                       // [128 m-rows x 64 k] bf16
-constexpr int TILE = 2 * CHUNK;                    // 128 rows of K
-constexpr int OFF_THI = 0, OFF_TLO = TILE, OFF_OH = 2 * TILE, BUF = 3 * TILE;     // one staging buffer = 96 KiB
+constexpr int CHUNK = 16384;                       // [128 rows x 64 features] bf16, SWIZZLE_128B
+constexpr int TILE = 2 * CHUNK;                    // 128 rows x 128 features
+constexpr int OFF_THI = 0, OFF_TLO = TILE, OFF_OH = 2 * TILE, BUF = 2 * TILE + CHUNK;     // one staging buffer = 80 KiB
 constexpr int OFF_CNT = 2 * BUF;                   // int counters [128]
 constexpr int OFF_BAR = OFF_CNT + 512;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 enum { B_STAGED = 0, B_FREE = 2, B_ACC = 4, B_DRAINED = 5, B_COUNT = 6 };
 constexpr int NT = 8 * 32 + 32;                    // 8 staging warps + the MMA warp
 constexpr int FLUSH_TILES = 256;                   // 32 768 rows of fp32 accumulation between fp64 flushes
+constexpr int NCLS = 64;                           // class slots of the one-hot tile (classes <= 64)
 constexpr uint32_t TM_M = 0, TM_S = 128;
 
-// byte offset of element (m, k) inside a [128 x 128] K-major SW128 tile made of two [128 x 64] chunks
-__device__ __forceinline__ uint32_t t_off(int m, int k) { return (uint32_t)((k >> 6) * CHUNK) + sw128_off(m, (k & 63) >> 3) + (uint32_t)((k & 7) * 2); }
+// MN-major SWIZZLE_128B descriptor of a [128 rows(K) x 128 features(MN)] tile made of two 64-feature chunks
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(CHUNK >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+constexpr uint32_t MN_BOTH = (1u << 15) | (1u << 16);      // instruction descriptor: A and B are MN-major
+
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 
 __global__ void __launch_bounds__(NT, 1) maha_fit_tc_kernel(const float* __restrict__ feat, const long long* __restrict__ labels,
                                                             long long n, int C, double* __restrict__ count,
@@ -66,7 +80,6 @@ __global__ void __launch_bounds__(NT, 1) maha_fit_tc_kernel(const float* __restr
 
     if (warp == MMA_WARP) {
         const bool leader = elect_one();
-        constexpr uint32_t ID128 = idesc_bf16(128, 128);
         uint32_t staged_parity[2] = {0, 0}, drained_parity = 0;
         long long it = 0;
         int since_flush = 0;
@@ -76,22 +89,19 @@ __global__ void __launch_bounds__(NT, 1) maha_fit_tc_kernel(const float* __restr
             staged_parity[b] ^= 1;
             tc_fence_after();
             const uint32_t base = sbase + b * BUF;
-#pragma unroll 1
-            for (int kc = 0; kc < 2; ++kc) {
-                const uint64_t dHi = sw128_desc(base + OFF_THI + kc * CHUNK), dLo = sw128_desc(base + OFF_TLO + kc * CHUNK),
-                               dOh = sw128_desc(base + OFF_OH + kc * CHUNK);
+            const uint64_t dHi = mn_desc(base + OFF_THI), dLo = mn_desc(base + OFF_TLO), dOh = mn_desc(base + OFF_OH);
+            constexpr uint32_t IDM = idesc_bf16(128, 128) | MN_BOTH, IDS = idesc_bf16(128, NCLS) | MN_BOTH;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t o = (uint64_t)(2 * k);
-                    const uint32_t first = (since_flush == 0 && kc == 0 && k == 0) ? 0u : 1u;
-                    if (leader) {
-                        umma(tmem + TM_M, dHi + o, dHi + o, ID128, first);
-                        umma(tmem + TM_M, dLo + o, dHi + o, ID128, 1u);
-                        umma(tmem + TM_M, dHi + o, dLo + o, ID128, 1u);
-                        umma(tmem + TM_M, dLo + o, dLo + o, ID128, 1u);
-                        umma(tmem + TM_S, dOh + o, dHi + o, ID128, first);
-                        umma(tmem + TM_S, dOh + o, dLo + o, ID128, 1u);
-                    }
+            for (int ks = 0; ks < 8; ++ks) {                       // K = 16 rows per step: two 8-row groups = 2 KiB
+                const uint64_t o = (uint64_t)(ks * (2048 >> 4));
+                const uint32_t first = (since_flush == 0 && ks == 0) ? 0u : 1u;
+                if (leader) {
+                    umma(tmem + TM_M, dHi + o, dHi + o, IDM, first);
+                    umma(tmem + TM_M, dLo + o, dHi + o, IDM, 1u);
+                    umma(tmem + TM_M, dHi + o, dLo + o, IDM, 1u);
+                    umma(tmem + TM_M, dLo + o, dLo + o, IDM, 1u);
+                    umma(tmem + TM_S, dHi + o, dOh + o, IDS, first);       // sum^T[feature][class] += F^T one-hot
+                    umma(tmem + TM_S, dLo + o, dOh + o, IDS, 1u);
                 }
             }
             if (leader) tc_commit(BAR(B_FREE + b));
@@ -107,46 +117,51 @@ __global__ void __launch_bounds__(NT, 1) maha_fit_tc_kernel(const float* __restr
         }
     } else {
         const int half = warp >> 2;
-        const int row = (warp & 3) * 32 + lane;                     // row inside the tile == accumulator row when flushing
+        const int row = (warp & 3) * 32 + lane;                     // accumulator row (feature) when flushing
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t free_parity[2] = {1, 1}, acc_parity = 0;
         long long it = 0;
         int since_flush = 0;
+        // staging role: warp w owns rows 16 w .. 16 w + 15 of the tile; lane l holds features [4 l, 4 l + 4) of a row
+        const int kc = lane >> 4, piece = (lane & 15) >> 1, sub = (lane & 1) * 8;
+        const int oh_row = warp * 16 + (lane >> 1), oh_half = lane & 1;      // one-hot tile: two lanes per row, 4 pieces each
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             const int b = (int)(it & 1);
-            const long long r = tile * 128 + row;
-            const bool ok = r < n;
+            const long long r_oh = tile * 128 + oh_row;
+            long long lab_oh = (r_oh < n) ? __ldg(labels + r_oh) : -1;
+            if (lab_oh < 0 || lab_oh >= C) lab_oh = -1;              // rows with a label outside [0, C) are skipped entirely
             float4 t[16];
-            const float4* src = reinterpret_cast<const float4*>(feat + r * D + 64 * half);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) t[i] = ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            long long lab = ok ? __ldg(labels + r) : -1;
-            if (lab < 0 || lab >= C) lab = -1;                       // rows with a label outside [0, C) are skipped entirely
-            if (lab < 0) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 16; ++j) {                           // issued together with the label load above, not after it
+                const long long r = tile * 128 + warp * 16 + j;
+                t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < n) t[j] = ld_stream(feat + r * D + 4 * lane);
             }
             mbar_wait(BAR(B_FREE + b), free_parity[b], 92);          // the MMAs that read this buffer are complete
             free_parity[b] ^= 1;
             uint8_t* buf = smem + b * BUF;
+            const unsigned keep_mask = __ballot_sync(0xffffffffu, lab_oh >= 0);      // row 16 w + j <-> lanes 2j, 2j+1
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float x4[4] = {t[i].x, t[i].y, t[i].z, t[i].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int f = 64 * half + 4 * i + e;
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(x4[e]);
-                    const __nv_bfloat16 lo = __float2bfloat16_rn(x4[e] - __bfloat162float(hi));
-                    const uint32_t off = t_off(f, row);
-                    *reinterpret_cast<__nv_bfloat16*>(buf + OFF_THI + off) = hi;
-                    *reinterpret_cast<__nv_bfloat16*>(buf + OFF_TLO + off) = lo;
-                }
+            for (int j = 0; j < 16; ++j) {
+                const float4 x = ((keep_mask >> (2 * j)) & 1u) ? t[j] : make_float4(0.f, 0.f, 0.f, 0.f);     // unlabeled rows contribute nothing
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+                const uint32_t off = (uint32_t)(kc * CHUNK) + sw128_off(warp * 16 + j, piece) + sub;
+                *reinterpret_cast<uint2*>(buf + OFF_THI + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                *reinterpret_cast<uint2*>(buf + OFF_TLO + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
             }
-            const unsigned short one = 0x3F80, zero = 0;             // bf16 1.0
-#pragma unroll 16
-            for (int c = 64 * half; c < 64 * half + 64; ++c)
-                *reinterpret_cast<unsigned short*>(buf + OFF_OH + t_off(c, row)) = (c == (int)lab) ? one : zero;
-            if (half == 0 && lab >= 0) atomicAdd(cnt + (int)lab, 1);
+            {   // one-hot row: 64 class slots = 8 pieces of 16 bytes, this lane writes pieces 4 oh_half .. 4 oh_half + 3
+                const int lab = (int)lab_oh;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int p = 4 * oh_half + q;
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+                    if (lab >= 0 && (lab >> 3) == p) w[(lab & 7) >> 1] = 0x3F80u << (16 * (lab & 1));      // bf16 1.0
+                    *reinterpret_cast<uint4*>(buf + OFF_OH + sw128_off(oh_row, p)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                if (oh_half == 0 && lab >= 0) atomicAdd(cnt + lab, 1);
+            }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_STAGED + b));
@@ -163,12 +178,12 @@ __global__ void __launch_bounds__(NT, 1) maha_fit_tc_kernel(const float* __restr
                 tc_wait_ld();
 #pragma unroll 8
                 for (int j = 0; j < 64; ++j) atomicAdd(second + (size_t)row * D + 64 * half + j, (double)__uint_as_float(v[j]));
-                TMEM_LD32(lane_base + TM_S + 64 * half, v);
-                TMEM_LD32(lane_base + TM_S + 64 * half + 32, (v + 32));
+                TMEM_LD32(lane_base + TM_S + 32 * half, v);           // sum^T: lane = feature, column = class slot
                 tc_wait_ld();
-                if (row < C) {
 #pragma unroll 8
-                    for (int j = 0; j < 64; ++j) atomicAdd(sum + (size_t)row * D + 64 * half + j, (double)__uint_as_float(v[j]));
+                for (int j = 0; j < 32; ++j) {
+                    const int c = 32 * half + j;
+                    if (c < C) atomicAdd(sum + (size_t)c * D + row, (double)__uint_as_float(v[j]));
                 }
                 tc_fence_before();
                 __syncwarp();
