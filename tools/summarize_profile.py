@@ -33,7 +33,9 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
 for kern, cmdline in (("imu_bf16", "python tools/profile_imu.py 65536 bf16 3 nohead"), ("head_tc", "python tools/profile_imu.py 65536 bf16 3"),
                       ("linear_tc", "python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-sweep --lanes 1"),
                       ("maha_score", "python tools/profile_scoring.py (2 M feature rows; 3rd launch captured)"),
-                      ("logit_ring", "python tools/profile_scoring.py (4 M logit rows; 3rd launch captured)")):
+                      ("logit_ring", "python tools/profile_scoring.py (4 M logit rows; 3rd launch captured)"),
+                      ("maha_fit", "python tools/profile_fit_pool.py (2 M feature rows; 3rd launch captured)"),
+                      ("video_pool", "python tools/profile_fit_pool.py (2 048 clips, 537 MB; 3rd launch captured)")):
     rep = os.path.join(go, f"prof_{kern}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
