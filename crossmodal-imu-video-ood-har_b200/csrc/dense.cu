@@ -533,6 +533,9 @@ static int video_pool_impl(const void* fmap, int32_t is_bf16, int64_t n, int32_t
         return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, st);
     static int batched = -1;
     if (batched < 0) { const char* e = getenv("CMHAR_POOL_BATCH"); batched = e ? atoi(e) : 1; }      // development switch
+    static int pad_smem = -1;
+    if (pad_smem < 0) { const char* e = getenv("CMHAR_POOL_SMEM"); pad_smem = e ? atoi(e) : 0; }      // development switch: unused dynamic
+                                                                                                      // smem that keeps the CTAs off SMs holding an encoder CTA
     static int cap_y = -1;
     if (cap_y < 0) { const char* e = getenv("CMHAR_POOL_GRIDY"); cap_y = e ? atoi(e) : 0; }      // development switch
     long long gy = n < 32768 ? n : 32768;
@@ -542,16 +545,16 @@ static int video_pool_impl(const void* fmap, int32_t is_bf16, int64_t n, int32_t
     if (is_bf16) {
         if (aligned && hw % 8 == 0)
         {
-            if (batched == 8) video_pool_kernel<__nv_bfloat16, 8, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
-            else video_pool_kernel<__nv_bfloat16, 8><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
+            if (batched == 8) video_pool_kernel<__nv_bfloat16, 8, 8><<<grid, POOL_NT, pad_smem, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
+            else video_pool_kernel<__nv_bfloat16, 8><<<grid, POOL_NT, pad_smem, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
         }
         else
-            video_pool_kernel<__nv_bfloat16, 0><<<grid, POOL_NT, 0, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
+            video_pool_kernel<__nv_bfloat16, 0><<<grid, POOL_NT, pad_smem, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
     } else {
         if (aligned && hw % 4 == 0)
-            video_pool_kernel<float, 4><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img);
+            video_pool_kernel<float, 4><<<grid, POOL_NT, pad_smem, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img);
         else
-            video_pool_kernel<float, 0><<<grid, POOL_NT, 0, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img);
+            video_pool_kernel<float, 0><<<grid, POOL_NT, pad_smem, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img);
     }
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
