@@ -31,7 +31,7 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warp_latency_issue_stalled_barrier.ratio"]
 for kern, cmdline in (("imu_bf16", "python tools/profile_imu.py 65536 bf16 3 nohead"), ("head_tc", "python tools/profile_imu.py 65536 bf16 3"),
-                      ("linear_tc", "python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-sweep --lanes 1"),
+                      ("linear_tc", "python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-sweep --lanes 1 (62nd linear_tc launch = the late-fusion layer, 896 -> 128, 2 CTAs, fp32-row staging path, 14 k chunks)"),
                       ("maha_score", "python tools/profile_scoring.py (2 M feature rows; 3rd launch captured)"),
                       ("logit_ring", "python tools/profile_scoring.py (4 M logit rows; 3rd launch captured)"),
                       ("maha_fit", "python tools/profile_fit_pool.py (2 M feature rows; 3rd launch captured)"),
