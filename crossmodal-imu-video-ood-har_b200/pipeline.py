@@ -152,13 +152,18 @@ class CrossModalOODPipeline:
         return res
 
     @torch.no_grad()
-    def stream_host(self, batches: Iterable, depth: int = 2):
+    def stream_host(self, batches: Iterable, depth: int = 2, graphs: bool = True):
         """Streaming form of ``run_host`` for a sequence of HOST batches ``(imu_host, fmap_host)``: the
         host->device copy of batch i+1 (copy engine, its own stream) overlaps the kernels of batch i, the
         per-window results of every batch are copied back to pinned memory, and the generator yields them in
         order -- what an evaluator loop over a DataLoader does (reference src/eval/evaluator.py:40-49, with
         the per-batch ``.cpu()`` sync replaced by a ``depth``-deep ring).  Every batch still pays its own
-        H2D and D2H; only their latency is hidden."""
+        H2D and D2H; only their latency is hidden.
+
+        IMU-only batches (``fmap_host is None``, the reference's ``Evaluator.predict`` workload) are small -- 246 KB in,
+        5 KB out, two kernel launches -- and host-bound when every copy and launch is issued from Python (~100 us per
+        batch).  With ``graphs`` each ring slot records its [H2D, encoder + head + scores, D2H] sequence once as a CUDA
+        graph on its own stream and replays it per batch: one host call instead of eight."""
         dev = next(self.clf.parameters()).device
         main = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(device=dev)
@@ -179,7 +184,7 @@ class CrossModalOODPipeline:
                 yield finish(pending.pop(0))
             key = (B, live, None if fmap_host is None else (tuple(fmap_host.shape), fmap_host.dtype))
             if sl["key"] != key:
-                sl.update(key=key, imu_pin=torch.empty((B, live), dtype=torch.float32).pin_memory(),
+                sl.update(key=key, graph=None, imu_pin=torch.empty((B, live), dtype=torch.float32).pin_memory(),
                           imu_dev=torch.empty((B, live), dtype=torch.float32, device=dev),
                           res_pin=torch.empty((4, B), dtype=torch.float32).pin_memory(),
                           pred_pin=torch.empty((B,), dtype=torch.int64).pin_memory(),
@@ -189,6 +194,32 @@ class CrossModalOODPipeline:
                     sl["fmap_pin"] = torch.empty_like(fmap_host).pin_memory()
                     sl["fmap_dev"] = torch.empty(fmap_host.shape, dtype=fmap_host.dtype, device=dev)
             sl["imu_pin"].copy_(imu_host[:, 0, :live] if imu_host.dim() == 3 else imu_host[:, :live])
+            if fmap_host is None and graphs:
+                if sl.get("graph") is None:
+                    lane = torch.cuda.Stream(device=dev)
+                    lane.wait_stream(main)
+                    with torch.cuda.stream(lane):                # warm-up outside capture: packs weights, sizes allocations
+                        self.run(sl["imu_dev"], None, window_stride=live)
+                    lane.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=lane):
+                        sl["imu_dev"].copy_(sl["imu_pin"], non_blocking=True)
+                        out = self.run(sl["imu_dev"], None, window_stride=live)
+                        sl["pred_pin"].copy_(out["pred"], non_blocking=True)
+                        sl["res_pin"][0].copy_(out["msp"], non_blocking=True)
+                        sl["res_pin"][1].copy_(out["energy"], non_blocking=True)
+                        if "maha" in out:
+                            sl["res_pin"][2].copy_(out["maha"], non_blocking=True)
+                    sl.update(graph=g, lane=lane, has_maha="maha" in out)
+                with torch.cuda.stream(sl["lane"]):
+                    sl["graph"].replay()
+                    sl["done"].record(sl["lane"])
+                res = {"pred": sl["pred_pin"], "msp": sl["res_pin"][0], "energy": sl["res_pin"][1]}
+                if sl["has_maha"]:
+                    res["maha"] = sl["res_pin"][2]
+                sl["res"] = res
+                pending.append(sl)
+                continue
             if sl.get("used"):
                 # the slot's device buffers were last read by batch i - depth: wait for THAT batch only (its `done`
                 # event), not for the whole compute stream -- waiting on the stream serialised copy(i) behind

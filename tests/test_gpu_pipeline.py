@@ -189,3 +189,21 @@ def test_pooling_into_operand_image_matches_row_path(n):
     want = ve.project_pooled(rows, precision="bf16")
     assert torch.equal(ve.project_pooled(None, precision="bf16", x_img=img, n=n), want)
     assert torch.equal(ve.project_pooled(None, precision="bf16", x_img=img2, n=n), want)
+
+
+def test_streamed_imu_only_batches_through_slot_graphs():
+    """IMU-only ``stream_host``: every ring slot replays one CUDA graph [H2D, encoder + head + scores, D2H]; results in
+    order and equal to the synchronous ``run_host`` and to the un-graphed streaming route, also when the batch shape
+    changes mid-stream (the slot re-records its graph) and with a Mahalanobis scorer attached."""
+    clf, xm, sd_c, sd_x = build()
+    feats, labels = W.class_features(7, 2000)
+    maha = cm.MahalanobisOOD(32, DEV, ridge=1e-3).fit(torch.from_numpy(feats).to(DEV), torch.from_numpy(labels).to(DEV))
+    pipe = cm.CrossModalOODPipeline(clf, xm, maha, frames=16, precision="bf16")
+    sizes = [64, 64, 64, 64, 200, 200, 200, 64, 7]
+    batches = [(torch.from_numpy(W.imu_windows(50 + i, b)), None) for i, b in enumerate(sizes)]
+    want = [{k: v.clone() for k, v in pipe.run_host(a, None).items()} for a, _ in batches]
+    for graphs in (True, False):
+        got = [{k: v.clone() for k, v in r.items()} for r in pipe.stream_host(iter(batches), depth=2, graphs=graphs)]
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert set(g) == set(w) and all(torch.equal(g[k], w[k]) for k in w)
