@@ -167,7 +167,11 @@ class CrossModalOODPipeline:
         dev = next(self.clf.parameters()).device
         main = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(device=dev)
-        slots: List[dict] = []
+        # ring slots (pinned / device buffers, events, recorded graphs) persist across calls: recording a slot's graph costs
+        # milliseconds, a short evaluation must not pay it again
+        if not hasattr(self, "_stream_slots"):
+            self._stream_slots = {}
+        slots: List[dict] = self._stream_slots.setdefault((str(dev), depth), [])
         pending: List[dict] = []
 
         def finish(sl):
