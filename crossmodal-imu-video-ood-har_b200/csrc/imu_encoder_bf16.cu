@@ -4,19 +4,24 @@
 //
 //   * one CTA owns a tile of 8 windows = 128 token rows (window w -> rows 16w..16w+15; for
 //     seq < 16 the tail rows of each 16-row group are padding, masked out of the softmax);
-//   * every GEMM is a chain of tcgen05.mma (M=128, K=16, bf16 in, fp32 accumulate in TMEM) issued
-//     by ONE thread; operands are K-major SWIZZLE_128B tiles in shared memory;
-//   * weights are pre-swizzled at pack time into 16 KiB chunks ([128 rows x 64 k] bf16) stored
-//     in consumption order, streamed L2 -> smem with cp.async.bulk (TMA engine, UBLKCP) through a
-//     4-stage mbarrier ring;
-//   * attention runs on the tensor cores too: per head S = Q_h K_h^T over the whole tile
-//     (128x128x16, cross-window entries ignored), softmax on the 16x16 diagonal blocks in
-//     registers, P (block-diagonal, bf16) back to smem, O_h = P V_h as eight 128x16x16 MMAs against
-//     V^T (V^T comes out of the QKV phase directly: V^T = W_v h^T, weights as the A operand);
+//   * every GEMM is a chain of tcgen05.mma (M=128, K=16, bf16 in, fp32 accumulate in TMEM) issued by ONE elected
+//     lane of a converged warp; only h, K and V^T are K-major SWIZZLE_128B tiles in shared memory -- Q, P, O and the
+//     FFN hidden chunks are written by the epilogue as bf16 back into TMEM over their own accumulators and consumed as
+//     TMEM A operands;
+//   * weights are pre-swizzled at pack time into 16 KiB chunks ([128 rows x 64 k] bf16) stored in consumption
+//     order, streamed L2 -> smem with cp.async.bulk (TMA engine, UBLKCP, L2 evict-last) through a 4-stage mbarrier
+//     ring (as fast as 6 stages; the 32 KiB it frees leave room for a co-resident CTA of another kernel);
+//   * attention runs on the tensor cores too, compact: S[r][16h + k] = q_h(r) . k_h(key k of r's own window) as one
+//     128x16x16 MMA per (head, window) restricted to that window's 16 TMEM lanes by the disable-output-lane mask;
+//     softmax in registers (ex2, scale folded into W_q); O = P V likewise lane-masked against V^T (V^T comes out of
+//     the QKV phase directly: V^T = W_v h^T, weights as the A operand).  The score MMAs start as soon as Q and K are
+//     in place (B_QKV) and overlap the V^T drain (B_V);
 //   * the fp32 residual stream never leaves TMEM: LayerNorm epilogues write (LN(x) + next bias)
 //     back into the accumulator columns and the next GEMM accumulates on top of it;
 //   * TMEM map (512 columns): A=[0,128) B=[128,256) C=[256,384) scratch accumulators,
 //     R=[384,512) residual/accumulator.
+//   * registers capped at 152 per thread and the largest shared-memory carveout requested, so that a small CTA of
+//     another kernel (<= 1 792 registers per SM sub-partition, <= 34 KiB) can be resident next to this one.
 //
 // Roles: warps 0-7 epilogue (thread = (row, column half)), warp 8 lane 0 = MMA issuer,
 // warp 9 lane 0 = weight producer.
