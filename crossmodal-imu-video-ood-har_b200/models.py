@@ -56,6 +56,15 @@ def _native_mode(module: nn.Module) -> bool:
     return (not module.training) and (not torch.is_grad_enabled())
 
 
+_PACK_GENERATION = [0]
+
+
+def pack_generation() -> int:
+    """Bumped whenever any module drops its packed blobs (parameters may have changed): recorded CUDA graphs hold raw
+    pointers into those blobs and must be re-recorded when this number moves."""
+    return _PACK_GENERATION[0]
+
+
 class _PackedMixin:
     """Cache of packed device blobs, invalidated whenever parameters may have changed."""
 
@@ -64,6 +73,7 @@ class _PackedMixin:
         self.register_load_state_dict_post_hook(lambda m, _: m.invalidate_packed())
 
     def invalidate_packed(self):
+        _PACK_GENERATION[0] += 1
         self._packed.clear()
         for child in self.children():
             if isinstance(child, _PackedMixin):
@@ -648,6 +658,7 @@ class IMUClassifier(_PackedMixin, nn.Module):
     def set_mahalanobis(self, maha) -> None:
         """Attach a fitted ``ood.MahalanobisOOD`` so ``forward_scores`` also emits its score."""
         self._maha_state = maha
+        _PACK_GENERATION[0] += 1          # recorded graphs of this model now compute a different set of outputs
 
     # ------------------------------------------------------------------ forward
     def forward(self, imu):

@@ -124,6 +124,8 @@ class MahalanobisOOD:
         self.fit_ = finalize_mahalanobis(host[:c], host[c:c + c * FEAT_DIM].reshape(c, FEAT_DIM),
                                          host[c + c * FEAT_DIM:].reshape(FEAT_DIM, FEAT_DIM), self.ridge)
         self._blobs.clear()
+        from .models import _PACK_GENERATION
+        _PACK_GENERATION[0] += 1          # a re-fit replaces the packed scorer state recorded graphs point into
         return self
 
     def fit(self, feats: torch.Tensor, labels: torch.Tensor, all_reduce: bool = True) -> "MahalanobisOOD":

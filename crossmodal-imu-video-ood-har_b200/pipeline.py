@@ -23,7 +23,7 @@ import torch
 from . import _native as N
 from .losses import similarity_native
 from .fusion import LateFusionClassifier
-from .models import CrossModalModel, IMUClassifier, imu_forward_native, l2_normalize_native, _prec_code
+from .models import CrossModalModel, IMUClassifier, imu_forward_native, l2_normalize_native, _prec_code, pack_generation
 from .ood import MahalanobisOOD
 
 __all__ = ["CrossModalOODPipeline"]
@@ -199,7 +199,7 @@ class CrossModalOODPipeline:
                     sl["fmap_dev"] = torch.empty(fmap_host.shape, dtype=fmap_host.dtype, device=dev)
             sl["imu_pin"].copy_(imu_host[:, 0, :live] if imu_host.dim() == 3 else imu_host[:, :live])
             if fmap_host is None and graphs:
-                if sl.get("graph") is None:
+                if sl.get("graph") is None or sl.get("generation") != pack_generation():      # weights re-packed: re-record
                     lane = torch.cuda.Stream(device=dev)
                     lane.wait_stream(main)
                     with torch.cuda.stream(lane):                # warm-up outside capture: packs weights, sizes allocations
@@ -214,7 +214,7 @@ class CrossModalOODPipeline:
                         sl["res_pin"][1].copy_(out["energy"], non_blocking=True)
                         if "maha" in out:
                             sl["res_pin"][2].copy_(out["maha"], non_blocking=True)
-                    sl.update(graph=g, lane=lane, has_maha="maha" in out)
+                    sl.update(graph=g, lane=lane, has_maha="maha" in out, generation=pack_generation())
                 with torch.cuda.stream(sl["lane"]):
                     sl["graph"].replay()
                     sl["done"].record(sl["lane"])

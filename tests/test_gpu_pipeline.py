@@ -207,3 +207,17 @@ def test_streamed_imu_only_batches_through_slot_graphs():
         assert len(got) == len(want)
         for g, w in zip(got, want):
             assert set(g) == set(w) and all(torch.equal(g[k], w[k]) for k in w)
+
+
+def test_slot_graphs_follow_reloaded_weights():
+    """The recorded per-slot graphs hold raw pointers into the packed weight blobs: after ``load_state_dict`` (which drops
+    the blobs) the next ``stream_host`` call must re-record and return the NEW model's results."""
+    clf, xm, sd_c, sd_x = build(31)
+    pipe = cm.CrossModalOODPipeline(clf, xm, None, frames=16, precision="bf16")
+    batches = [(torch.from_numpy(W.imu_windows(70 + i, 64)), None) for i in range(4)]
+    first = [r["energy"].clone() for r in pipe.stream_host(iter(batches))]
+    clf.load_state_dict(tsd(W.classifier_state(32)), strict=True)
+    want = [pipe.run_host(a, None)["energy"].clone() for a, _ in batches]
+    got = [r["energy"].clone() for r in pipe.stream_host(iter(batches))]
+    assert all(torch.equal(g, w) for g, w in zip(got, want))
+    assert not all(torch.equal(g, f) for g, f in zip(got, first))
