@@ -214,3 +214,22 @@ def test_ood_table_generator(tmp_path):
     assert tables["ood_fpr95"].loc["pretrained", ("holdout_8_of_32", "maha")] == "22.00 ± 2.00"
     files = cm.save_tables(tables, tmp_path, prefix="table_ood")
     assert len(files) == 9 and all(os.path.getsize(f) > 0 for f in files)
+
+
+def test_pack_generation_moves_whenever_packed_blobs_are_dropped():
+    """Recorded CUDA graphs (stream_host ring slots) key on this counter: it must move on every event that can change
+    the packed blobs -- mode switches, load_state_dict, .to(), attaching a Mahalanobis scorer."""
+    import crossmodal_imu_video_ood_har_b200 as cm
+    from crossmodal_imu_video_ood_har_b200.models import pack_generation
+    cfg = cm.default_config()
+    clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg)
+    g0 = pack_generation()
+    clf.eval()
+    g1 = pack_generation()
+    clf.load_state_dict(clf.state_dict(), strict=True)
+    g2 = pack_generation()
+    clf.float()
+    g3 = pack_generation()
+    clf.set_mahalanobis(None)
+    g4 = pack_generation()
+    assert g0 < g1 < g2 < g3 < g4
