@@ -119,7 +119,6 @@ __global__ void __maxnreg__(NQ == 2 ? 152 : 96) imu_forward_bf16_kernel(const Bf
     const unsigned long long trace_t0 = (tid == 0) ? trace_begin() : 0ull;
     const BlobHeader* eh = reinterpret_cast<const BlobHeader*>(a.enc_blob);
     const int S = eh->a, n_layers = eh->b;
-    const float* encf = reinterpret_cast<const float*>(a.enc_blob + 1024);
     const size_t fp32_bytes = (EncLayout::fp32_floats(n_layers) * sizeof(float) + 1023) / 1024 * 1024;
     const uint8_t* wchunks = reinterpret_cast<const uint8_t*>(a.enc_blob) + 1024 + fp32_bytes;
     const int n_chunks = 1 + n_layers * CHUNKS_PER_LAYER;
