@@ -51,6 +51,10 @@ class HeadParams(C.Structure):
                    "w2", "b2")]
 
 
+class ImuOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("cls", "cls_img", "tokens", "logits", "pred", "msp", "energy", "maha")]
+
+
 class ConvLayerParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("weight", "bias", "bn_weight", "bn_bias", "bn_mean", "bn_var")]
 
@@ -72,6 +76,23 @@ _SIGNATURES = {
     "cmhar_imu_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int32, C.c_void_p]),
+    "cmhar_imu_forward_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                       C.POINTER(ImuOutputs), C.c_int32, C.c_void_p]),
+    "cmhar_head_kernel_kind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "cmhar_fused_head_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cmhar_mlp2_forward_img": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cmhar_similarity_img_work_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "cmhar_similarity_img": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_int32,
+                                       C.c_float, C.c_float, C.c_double, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_void_p]),
+    "cmhar_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cmhar_peer_free": (C.c_int, [C.c_void_p]),
+    "cmhar_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cmhar_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cmhar_peer_close": (C.c_int, [C.c_void_p]),
+    "cmhar_peer_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
+                                     C.c_void_p, C.c_void_p]),
     "cmhar_video_pool_img": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmhar_operand_image_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
@@ -188,6 +209,14 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t if t.is_contiguous() else t.contiguous()
+
+
+UNSUPPORTED = -3
+
+
+def ptr_array(ptrs):
+    """HOST array of device pointers (``void* const*`` arguments)."""
+    return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
 
 
 def alloc_blob(nbytes: int, device) -> torch.Tensor:

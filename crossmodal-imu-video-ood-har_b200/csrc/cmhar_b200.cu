@@ -10,6 +10,7 @@ namespace cmhar { struct FwdArgs; }
 #include "head_tc.cu"
 #include "dense.cu"
 #include "linear_tc.cu"
+#include "mlp2_tc.cu"
 #include "similarity.cu"
 #include "similarity_tc.cu"
 #include "fusion.cu"
@@ -17,4 +18,5 @@ namespace cmhar { struct FwdArgs; }
 #include "maha_score_tc.cu"
 #include "ood.cu"
 #include "maha_fit_tc.cu"
+#include "peer.cu"
 #include "api.cu"

@@ -243,8 +243,9 @@ __global__ void __launch_bounds__(NT) head_scores_kernel(const FwdArgs a) {
 
 }  // namespace headk
 
+struct HeadPreLayer;
 int launch_head_forward_tc(const FwdArgs& a, const uint8_t* head_tc, const float* head_f32, const HeadLayout& hl,
-                           const uint8_t* maha_tc, cudaStream_t stream);                          // head_tc.cu
+                           const uint8_t* maha_tc, cudaStream_t stream, const HeadPreLayer* pre);  // head_tc.cu
 
 // x = features (n, xstride >= 128) fp32.
 // CMHAR_BF16 and blobs that carry the tensor-core section: the tcgen05 split-bf16 kernel (head_tc.cu).
@@ -262,7 +263,7 @@ int launch_head_forward(const FwdArgs& a, int precision, cudaStream_t stream) {
             const uint8_t* htc = a.head_blob ? reinterpret_cast<const uint8_t*>(a.head_blob) + tc_section_offset(hl.total()) : nullptr;
             const float* hf32 = a.head_blob ? reinterpret_cast<const float*>(a.head_blob + sizeof(BlobHeader)) : nullptr;
             const uint8_t* mtc = want_maha ? reinterpret_cast<const uint8_t*>(a.maha_blob) + tc_section_offset(MahaLayout{mi.a}.total()) : nullptr;
-            return launch_head_forward_tc(a, htc, hf32, hl, mtc, stream);
+            return launch_head_forward_tc(a, htc, hf32, hl, mtc, stream, nullptr);
         }
     }
     static bool configured[64] = {};

@@ -40,7 +40,7 @@ constexpr int OFF_BAR = OFF_MISC + 1024;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB");
 enum { B_FULL = 0, B_EMPTY = B_FULL + NSLOT, B_F = B_EMPTY + NSLOT, B_ACC_Y, B_ACC_H1A, B_ACC_H1B, B_ACC_H2, B_ACC_OUT,
-       B_Y_RDY, B_H1_RDY, B_H2_RDY, B_COUNT };
+       B_Y_RDY, B_H1_RDY, B_H2_RDY, B_ACC_PRE, B_COUNT };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier area too small");
 constexpr uint32_t TM_H1 = 0, TM_Y = 256, TM_H2 = 384, TM_Z = 0, TM_G = 32;
 constexpr int NT = 8 * 32 + 64;
@@ -95,6 +95,14 @@ struct Args {
     const float *b0, *b1, *b2;   // folded fp32 biases (b2: Cp() entries)
     const uint8_t* maha_tc;      // Wh | Mu images | mu norms, or null
     int classes;
+    // optional late-fusion pre-layer (spec row A6): F = relu([x1 | x2] Wf'^T + bf') computed here from bf16 operand images
+    // (plain bf16 MMAs, fp32 accumulate) instead of being read from global memory; f.x is unused then
+    const uint8_t* pre_w;        // [kc] chunk images of Wf' (128 output rows), or null
+    const float* pre_bias;       // (128) folded
+    const uint8_t* pre_x1;       // [row tile][pre_kc1] chunk images
+    const uint8_t* pre_x2;       // [row tile][pre_kc2] chunk images
+    int pre_kc1, pre_kc2;
+    float* fused_out;            // (n,128) fp32 rows of F, or null
 };
 
 __global__ void __launch_bounds__(NT, 1) head_tc_kernel(const Args p) {
@@ -114,6 +122,7 @@ __global__ void __launch_bounds__(NT, 1) head_tc_kernel(const Args p) {
         mbar_init(BAR(B_F), 8);
         for (int i = B_ACC_Y; i <= B_ACC_OUT; ++i) mbar_init(BAR(i), 1);
         mbar_init(BAR(B_Y_RDY), 8); mbar_init(BAR(B_H1_RDY), 8); mbar_init(BAR(B_H2_RDY), 8);
+        mbar_init(BAR(B_ACC_PRE), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -136,6 +145,18 @@ __global__ void __launch_bounds__(NT, 1) head_tc_kernel(const Args p) {
                 if (++slot == NSLOT) { slot = 0; parity ^= 1; }
             };
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                if (p.pre_w) {          // pre-layer: one slot per 64-wide k chunk = [activation chunk | weight chunk]
+                    const int kcn = p.pre_kc1 + p.pre_kc2;
+                    for (int kc = 0; kc < kcn; ++kc) {
+                        const uint8_t* xa = (kc < p.pre_kc1) ? p.pre_x1 + ((size_t)tile * p.pre_kc1 + kc) * 16384
+                                                             : p.pre_x2 + ((size_t)tile * p.pre_kc2 + (kc - p.pre_kc1)) * 16384;
+                        mbar_wait(BAR(B_EMPTY + slot), parity, 72);
+                        mbar_expect_tx(BAR(B_FULL + slot), STAGE);
+                        bulk_g2s(sbase + OFF_RING + slot * STAGE, xa, 16384, BAR(B_FULL + slot));
+                        bulk_g2s(sbase + OFF_RING + slot * STAGE + 16384, p.pre_w + (size_t)kc * 16384, 16384, BAR(B_FULL + slot));
+                        if (++slot == NSLOT) { slot = 0; parity ^= 1; }
+                    }
+                }
                 if (do_maha) for (int s = 0; s < 2; ++s) push(p.maha_tc + s * STAGE, STAGE);
                 if (do_head) {
                     for (int s = 0; s < 4; ++s) push(p.head_tc + s * STAGE, STAGE);                      // W0: (h0,k0) (h0,k1) (h1,k0) (h1,k1)
@@ -187,6 +208,22 @@ __global__ void __launch_bounds__(NT, 1) head_tc_kernel(const Args p) {
         const uint64_t dFhi = sw128_desc(sbase + OFF_FHI), dFlo = sw128_desc(sbase + OFF_FLO);
         const uint64_t CH = 16384 >> 4;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            if (p.pre_w) {
+                // accumulates in the H2 columns: free until this tile's H1 is done, and the previous tile's Z / G MMAs that read
+                // H2 / Y from TMEM precede these in the (in-order) tensor pipe
+                const int kcn = p.pre_kc1 + p.pre_kc2;
+                for (int kc = 0; kc < kcn; ++kc) {
+                    mbar_wait(BAR(B_FULL + slot), parity, 73);
+                    tc_fence_after();
+                    const uint64_t dA = sw128_desc(sbase + OFF_RING + slot * STAGE), dB = sw128_desc(sbase + OFF_RING + slot * STAGE + 16384);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (leader) umma(tmem + TM_H2, dA + (uint64_t)(2 * k), dB + (uint64_t)(2 * k), ID128, (kc > 0 || k > 0) ? 1u : 0u);
+                    if (leader) tc_commit(BAR(B_EMPTY + slot));
+                    if (++slot == NSLOT) { slot = 0; parity ^= 1; }
+                }
+                if (leader) tc_commit(BAR(B_ACC_PRE));
+            }
             mbar_wait(BAR(B_F), ph.next(B_F), 63);                 // F staged (and the previous tile's TMEM fully consumed)
             tc_fence_after();
             if (do_maha) {
@@ -250,10 +287,27 @@ __global__ void __launch_bounds__(NT, 1) head_tc_kernel(const Args p) {
             const bool ok = r < a.n;
             // ---- stage F: this thread's 64 features -> hi / lo bf16 rows of the SS A tiles
             {
-                const float4* src = reinterpret_cast<const float4*>(a.x + r * a.xstride + c0);
                 float4 t[16];
+                if (p.pre_w) {      // F = relu(pre-layer accumulator + bias): this thread's 64 columns of the H2 buffer
+                    mbar_wait(BAR(B_ACC_PRE), ph.next(B_ACC_PRE), 74);
+                    tc_fence_after();
+                    load64(lane_base + TM_H2 + c0);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) t[i] = ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.pre_bias + c0) + i);
+                        t[i] = make_float4(fmaxf(__uint_as_float(v[4 * i]) + b.x, 0.f), fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f),
+                                           fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f));
+                    }
+                    if (ok && p.fused_out) {
+                        float4* dst = reinterpret_cast<float4*>(p.fused_out + r * D + c0);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dst[i] = t[i];
+                    }
+                } else {
+                    const float4* src = reinterpret_cast<const float4*>(a.x + r * a.xstride + c0);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) t[i] = ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 uint8_t* chunk_hi = smem + OFF_FHI + half * 16384;
                 uint8_t* chunk_lo = smem + OFF_FLO + half * 16384;
 #pragma unroll
@@ -417,8 +471,12 @@ int pack_maha_tc(const float* f32, const MahaLayout& ml, uint8_t* dst, cudaStrea
 }
 
 // head_tc / maha_tc: device pointers to the tensor-core sections of the blobs (null = stage absent)
+struct HeadPreLayer {          // optional late-fusion layer in front of the head (see headtc::Args)
+    const uint8_t* w; const float* bias; const uint8_t* x1; const uint8_t* x2; int kc1, kc2; float* fused_out;
+};
+
 int launch_head_forward_tc(const FwdArgs& a, const uint8_t* head_tc, const float* head_f32, const HeadLayout& hl,
-                           const uint8_t* maha_tc, cudaStream_t stream) {
+                           const uint8_t* maha_tc, cudaStream_t stream, const HeadPreLayer* pre) {
     static bool configured[64] = {};
     int dev = 0;
     CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -431,6 +489,7 @@ int launch_head_forward_tc(const FwdArgs& a, const uint8_t* head_tc, const float
     p.head_tc = head_tc;
     if (head_tc) { p.b0 = head_f32 + hl.b0(); p.b1 = head_f32 + hl.b1(); p.b2 = head_f32 + hl.b2(); p.classes = hl.C; }
     p.maha_tc = maha_tc;
+    if (pre) { p.pre_w = pre->w; p.pre_bias = pre->bias; p.pre_x1 = pre->x1; p.pre_x2 = pre->x2; p.pre_kc1 = pre->kc1; p.pre_kc2 = pre->kc2; p.fused_out = pre->fused_out; }
     const long long tiles = (a.n + 127) / 128;
     const int grid = (int)(tiles < (long long)sm_count() ? tiles : (long long)sm_count());
     headtc::head_tc_kernel<<<grid, headtc::NT, headtc::SMEM_BYTES, stream>>>(p);

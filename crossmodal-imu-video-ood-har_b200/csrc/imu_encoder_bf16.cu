@@ -624,6 +624,19 @@ __global__ void __maxnreg__(NQ == 2 ? 152 : 96) imu_forward_bf16_kernel(const Bf
 #pragma unroll
                             for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
                         }
+                        if (a.cls_img) {
+                            // the same CLS row as row (w % 128) of the bf16 operand image the projection-head / fusion kernels
+                            // stream as their A operand; windows past n (last tile) are written as zero rows
+                            if (!valid) {
+#pragma unroll
+                                for (int i = 0; i < CW; ++i) y[i] = 0.f;
+                            }
+                            const long long w = w0 + win;
+                            uint8_t* img = reinterpret_cast<uint8_t*>(a.cls_img) + (size_t)(w >> 7) * (2 * CHUNK);
+#pragma unroll
+                            for (int cc = 0; cc < CW; cc += 32)
+                                store_bf16_32(img + chunk_of(c0 + cc), (int)(w & 127), piece_of(c0 + cc), y + cc);
+                        }
                     }
                 }
             }

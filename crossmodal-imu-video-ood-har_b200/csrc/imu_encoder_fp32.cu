@@ -31,6 +31,7 @@ struct FwdArgs {
     float* msp_out;
     float* energy_out;
     float* maha_out;
+    void* cls_img;             // nullable: CLS features also as a bf16 operand image [ceil(n/128)][2][128 x 64] (bf16 path only)
 };
 
 // acc[i][j] = sum_k A[warp*8+i][k] * Wt[k][lane*4+j]

@@ -221,10 +221,14 @@ int launch_linear_tc(const uint8_t* w_img, const float* bias, const float* x1, c
     }
     static int ns = 0;
     if (ns == 0) { const char* e = getenv("CMHAR_LINEAR_NS"); ns = e ? atoi(e) : 2; if (ns < 2 || ns > lintc::NS) ns = 2; }      // development switch
-    lintc::Args p{w_img, bias, x1, x2, x2 ? K1 : K, K, N, n, relu, y, ns, a_img, y_img};
+    // operand-image input: both rings are plain bulk copies, so a 4-deep ring keeps 128 KiB in flight per CTA and the k loop
+    // stops being a chain of serial L2 round trips (K = 512: 16 us -> ~4 us per tile); fp32-row input keeps the 2-deep ring
+    // (its staging warps are the bound) so that two CTAs of different layers / batches fit one SM
+    const int depth = a_img ? lintc::NS : ns;
+    lintc::Args p{w_img, bias, x1, x2, x2 ? K1 : K, K, N, n, relu, y, depth, a_img, y_img};
     const long long mt = (n + 127) / 128;
     CMHAR_REQUIRE(mt <= 0x7fffffffLL, "too many rows");
-    lintc::linear_tc_kernel<<<dim3((unsigned)mt, (unsigned)((N + 127) / 128)), lintc::NT, lintc::smem_bytes(ns), st>>>(p);
+    lintc::linear_tc_kernel<<<dim3((unsigned)mt, (unsigned)((N + 127) / 128)), lintc::NT, lintc::smem_bytes(depth), st>>>(p);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }

@@ -28,7 +28,7 @@ constexpr int OFF_B = MAX_KC * CHUNK;                       // B ring
 constexpr int OFF_BAR = OFF_B + NSTAGE * CHUNK;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 enum { B_AFULL = 0, B_FULL = 1, B_EMPTY = B_FULL + NSTAGE, B_ACCFULL = B_EMPTY + NSTAGE, B_ACCEMPTY = B_ACCFULL + 2, B_COUNT = B_ACCEMPTY + 2 };
-static_assert(B_COUNT * 8 + 8 <= 256, "barrier area too small");
+static_assert(B_COUNT * 8 + 8 <= 160, "barrier area too small (the per-warp loss partials sit at +160)");
 constexpr int NT = 8 * 32 + 64;                             // 8 epilogue warps, MMA warp, producer warp
 
 struct Args {
@@ -44,6 +44,17 @@ struct Args {
     float lse_scale;           // v * log2(e)... see kernel
     float2* row_part;          // [2 * n_col_tiles][na] or null
     float* diag_out;
+    // B operand partitioned over several buffers (ranks' shards, possibly peer-GPU memory mapped over NVLink):
+    // column tile ct lives in b_parts[ct / tiles_per_part] at local tile ct % tiles_per_part.  tiles_per_part == 0: b_img.
+    const uint8_t* b_parts[CMHAR_MAX_PEERS];
+    long long tiles_per_part;
+    // deterministic loss reduction without a zeroed accumulator: every CTA stores its partial into cta_part[cta], the
+    // last CTA to finish (ticket) adds them in index order, scales, stores the result to every sum_dst and re-arms the ticket
+    double* cta_part;
+    unsigned int* ticket;
+    double* sum_dst[CMHAR_MAX_PEERS];
+    int n_dst;
+    double out_scale;
 };
 
 // fp32 (n, dim) row-major -> bf16 chunk images [ceil(n/128)][dim/64][128 x 64 SW128]
@@ -110,7 +121,10 @@ __global__ void __launch_bounds__(NT, 1) similarity_tc_kernel(const Args p) {
                 for (int kc = 0; kc < p.kc; ++kc) {
                     mbar_wait(BAR(B_EMPTY + stage), parity, 50);
                     mbar_expect_tx(BAR(B_FULL + stage), CHUNK);
-                    bulk_g2s(sbase + OFF_B + stage * CHUNK, p.b_img + ((size_t)ct * p.kc + kc) * CHUNK, CHUNK, BAR(B_FULL + stage));
+                    const uint8_t* src = p.tiles_per_part
+                        ? p.b_parts[ct / p.tiles_per_part] + ((size_t)(ct % p.tiles_per_part) * p.kc + kc) * CHUNK
+                        : p.b_img + ((size_t)ct * p.kc + kc) * CHUNK;
+                    bulk_g2s(sbase + OFF_B + stage * CHUNK, src, CHUNK, BAR(B_FULL + stage));
                     if (++stage == NSTAGE) { stage = 0; parity ^= 1; }
                 }
             }
@@ -177,7 +191,7 @@ __global__ void __launch_bounds__(NT, 1) similarity_tc_kernel(const Args p) {
                     for (int i = 0; i < 64; ++i) if (c_base + i < p.nb) p.sim_out[(c_base + i) * p.na + r] = __uint_as_float(v[i]);
                 }
             }
-            if (p.sigmoid_sum) {        // softplus(-z) = max(-z, 0) + ln2 * log2(1 + 2^(-|z| log2 e)); z log2 e = s * zscale + zbias
+            if (p.sigmoid_sum || p.cta_part) {        // softplus(-z) = max(-z, 0) + ln2 * log2(1 + 2^(-|z| log2 e)); z log2 e = s * zscale + zbias
                 float acc = 0.f;
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
@@ -209,15 +223,35 @@ __global__ void __launch_bounds__(NT, 1) similarity_tc_kernel(const Args p) {
                 }
             }
         }
-        if (p.sigmoid_sum) {
+        if (p.sigmoid_sum || p.cta_part) {
             double d = (double)sp * 0.6931471805599453;                  // log2 units -> natural log
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            if (lane == 0) atomicAdd(p.sigmoid_sum, d);
+            if (lane == 0) {
+                if (p.cta_part) reinterpret_cast<double*>(smem + OFF_BAR + 160)[warp] = d;
+                else atomicAdd(p.sigmoid_sum, d);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0 && p.cta_part) {
+        const double* wp = reinterpret_cast<const double*>(smem + OFF_BAR + 160);
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += wp[w];                              // fixed order
+        const unsigned int n_cta = gridDim.x * gridDim.y;
+        p.cta_part[blockIdx.y * gridDim.x + blockIdx.x] = s;
+        __threadfence();
+        if (atomicAdd(p.ticket, 1u) == n_cta - 1) {                          // last CTA of the launch
+            __threadfence();
+            double tot = 0.0;
+            for (unsigned int i = 0; i < n_cta; ++i) tot += *reinterpret_cast<volatile double*>(p.cta_part + i);
+            tot *= p.out_scale;
+            for (int i = 0; i < p.n_dst; ++i) *reinterpret_cast<volatile double*>(p.sum_dst[i]) = tot;
+            *p.ticket = 0u;                                                  // re-armed for the next launch (graph replays)
+            __threadfence_system();                                          // a destination may be peer-GPU memory
+        }
+    }
     if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
@@ -288,6 +322,50 @@ int launch_similarity_tc(const float* a, const float* b, long long na, long long
         rc = launch_lse_merge(col_part, nb, (int)(2 * rt), col_lse_out, st);
         if (rc) return rc;
     }
+    return CMHAR_OK;
+}
+
+// Operands already as bf16 chunk images (what the projection-head kernel writes): no conversion pre-pass.  The B operand
+// may be partitioned over `n_parts` buffers of `rows_per_part` rows (the ranks' shards; peer pointers are read over NVLink
+// by the same cp.async.bulk ring that feeds the MMAs, so the transfer overlaps the math tile by tile).
+size_t similarity_img_work_bytes(long long na, long long nb) {
+    const long long rt = (na + 127) / 128, ct = (nb + 127) / 128;
+    long long G = (2LL * sm_count() + rt - 1) / rt;
+    if (G > ct) G = ct;
+    if (G < 1) G = 1;
+    return 64 + (size_t)(G * rt) * sizeof(double);
+}
+
+int launch_similarity_img(const uint8_t* a_img, long long na, const uint8_t* const* b_parts, int n_parts, long long rows_per_part,
+                          long long nb, int dim, long long diag_offset, float sig_scale, float sig_bias, double out_scale,
+                          double* const* sum_dst, int n_dst, void* work, cudaStream_t st) {
+    static bool configured[64] = {};
+    int dev = 0;
+    CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        CMHAR_CHECK_CUDA(cudaFuncSetAttribute(simtc::similarity_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, simtc::SMEM_BYTES));
+        configured[dev & 63] = true;
+    }
+    simtc::Args p{};
+    p.a_img = a_img;
+    p.na = na; p.nb = nb; p.kc = dim / 64; p.diag_offset = diag_offset;
+    const float LOG2E_F = 1.4426950408889634f;
+    p.zscale = sig_scale * LOG2E_F; p.zbias = sig_bias * LOG2E_F;
+    p.lse_scale = 1.f;
+    if (n_parts == 1) { p.b_img = b_parts[0]; p.tiles_per_part = 0; }
+    else { for (int i = 0; i < n_parts; ++i) p.b_parts[i] = b_parts[i]; p.tiles_per_part = rows_per_part / 128; }
+    p.ticket = reinterpret_cast<unsigned int*>(work);
+    p.cta_part = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(work) + 64);
+    p.n_dst = n_dst;
+    for (int i = 0; i < n_dst; ++i) p.sum_dst[i] = sum_dst[i];
+    p.out_scale = out_scale;
+    const long long r_tiles = (na + 127) / 128, c_tiles = (nb + 127) / 128;
+    long long G = (2LL * sm_count() + r_tiles - 1) / r_tiles;
+    if (G > c_tiles) G = c_tiles;
+    if (G < 1) G = 1;
+    CMHAR_REQUIRE(r_tiles <= 65535, "too many row tiles");
+    simtc::similarity_tc_kernel<<<dim3((unsigned)G, (unsigned)r_tiles), simtc::NT, simtc::SMEM_BYTES, st>>>(p);
+    CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }
 

@@ -80,7 +80,9 @@ class _FusionBase(_PackedMixin, nn.Module):
 
     def set_mahalanobis(self, maha) -> None:
         """Attach a fitted ``ood.MahalanobisOOD`` (on the fused 128-d feature)."""
+        from .models import _PACK_GENERATION
         self._maha_state = maha
+        _PACK_GENERATION[0] += 1          # recorded graphs of this model now compute a different set of outputs
 
     def _head_blob(self, device) -> torch.Tensor:
         key = ("head", str(device))
@@ -138,6 +140,35 @@ class LateFusionClassifier(_FusionBase):
                                                     pl.out_dim, 1, y.data_ptr(), N.ptr(work), wbytes, _prec_code(precision),
                                                     N.stream_ptr(a.device)))
         return y
+
+    @torch.no_grad()
+    def forward_scores_img(self, cls_img: torch.Tensor, vfeat_img: torch.Tensor, n: int,
+                           out: Optional[Dict[str, torch.Tensor]] = None) -> Optional[Dict[str, torch.Tensor]]:
+        """Fusion layer + head + arg-max / MSP / energy (+ Mahalanobis) as ONE launch (``cmhar_fused_head_forward``) from
+        the two inputs' bf16 operand images.  Returns None when the dimensions are not served by the fused kernel."""
+        self._check()
+        dev = cls_img.device
+        pl = self._fusion_packed(dev)
+        out = {} if out is None else out
+
+        def buf(name, shape, dtype=torch.float32):
+            t = out.get(name)
+            if t is None:
+                t = out[name] = torch.empty(shape, dtype=dtype, device=dev)
+            return t
+        maha_blob = self._maha_state.blob(dev) if self._maha_state is not None else None
+        fused, logits = buf("fused", (n, pl.out_dim)), buf("logits", (n, self.num_classes))
+        pred, msp, energy = buf("pred", (n,), torch.int64), buf("msp", (n,)), buf("energy", (n,))
+        maha = buf("maha", (n,)) if maha_blob is not None else None
+        k1 = self.imu_encoder.d_model
+        with torch.cuda.device(dev):
+            rc = N.lib().cmhar_fused_head_forward(pl.blob.data_ptr(), cls_img.data_ptr(), k1, vfeat_img.data_ptr(), pl.in_dim - k1, n,
+                                                  self._head_blob(dev).data_ptr(), N.ptr(maha_blob), fused.data_ptr(), logits.data_ptr(),
+                                                  pred.data_ptr(), msp.data_ptr(), energy.data_ptr(), N.ptr(maha), N.stream_ptr(dev))
+        if rc == N.UNSUPPORTED:
+            return None
+        N.check(rc)
+        return out
 
     @torch.no_grad()
     def forward_scores(self, imu, fmap, frames: int, *, precision: Optional[str] = None, window_stride: Optional[int] = None,

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from . import _native as N
 from .models import _prec_code
 
-__all__ = ["SigmoidContrastiveLoss", "InfoNCELoss", "similarity_native"]
+__all__ = ["SigmoidContrastiveLoss", "InfoNCELoss", "similarity_native", "similarity_img_native"]
 
 
 def similarity_native(a: torch.Tensor, b: torch.Tensor, *, materialize: bool = False,
@@ -48,6 +48,37 @@ def similarity_native(a: torch.Tensor, b: torch.Tensor, *, materialize: bool = F
         if v is not None:
             out[k] = v
     return out
+
+
+def similarity_img_native(a_img: torch.Tensor, na: int, b_imgs, nb: int, dim: int, *, sigmoid=(10.0, -10.0),
+                          rows_per_part: int = 0, out_scale: Optional[float] = None, dst_ptrs=None,
+                          work: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``cmhar_similarity_img``: the fused sigmoid contrastive loss from operands that already are bf16 operand images.
+    ``b_imgs``: one image (tensor) or a list of device pointers / tensors, one per shard of ``rows_per_part`` rows (other
+    ranks' shards are peer-mapped pointers read over NVLink inside the GEMM).  The result, ``out_scale`` (default 1/(na nb))
+    times the softplus sum of this (na x nb) block, is stored to ``loss`` (0-dim float64, returned) or to ``dst_ptrs``.
+    ``work`` must have been zeroed once (``similarity_img_work``); it is re-armed by the kernel."""
+    dev = a_img.device
+    parts = b_imgs if isinstance(b_imgs, (list, tuple)) else [b_imgs]
+    ptrs = [q.data_ptr() if isinstance(q, torch.Tensor) else int(q) for q in parts]
+    if work is None:
+        work = similarity_img_work(na, nb, dev)
+    if dst_ptrs is None:
+        if loss is None:
+            loss = torch.empty((), dtype=torch.float64, device=dev)
+        dst_ptrs = [loss.data_ptr()]
+    sc, sb = sigmoid
+    scale = float(out_scale) if out_scale is not None else 1.0 / (float(na) * float(nb))
+    with torch.cuda.device(dev):
+        N.check(N.lib().cmhar_similarity_img(a_img.data_ptr(), na, N.ptr_array(ptrs), len(ptrs), int(rows_per_part), nb, dim,
+                                             float(sc), float(sb), scale, N.ptr_array(dst_ptrs), len(dst_ptrs), work.data_ptr(),
+                                             N.stream_ptr(dev)))
+    return loss
+
+
+def similarity_img_work(na: int, nb: int, device) -> torch.Tensor:
+    """Zeroed workspace (ticket + per-CTA partials) of ``cmhar_similarity_img``; one per concurrently running launch."""
+    return torch.zeros(N.lib().cmhar_similarity_img_work_bytes(na, nb), dtype=torch.uint8, device=device)
 
 
 class SigmoidContrastiveLoss(nn.Module):

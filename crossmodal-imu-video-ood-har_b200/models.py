@@ -257,8 +257,9 @@ def imu_forward_native(encoder: "IMUEncoder", head_blob: Optional[torch.Tensor],
                        want_tokens=False, want_logits=False, want_pred=False, want_msp=False,
                        want_energy=False, want_maha=False, classes: int = 0,
                        precision: Optional[str] = None, window_stride: Optional[int] = None,
-                       out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
-    """One fused launch of ``cmhar_imu_forward`` on the current stream.
+                       out: Optional[Dict[str, torch.Tensor]] = None, want_cls_img: bool = False) -> Dict[str, torch.Tensor]:
+    """One fused launch of ``cmhar_imu_forward_ex`` on the current stream.  ``want_cls_img`` (bf16 precision): the CLS
+    features also as a bf16 operand image (``out['cls_img']``) for the fused projection-head / fusion kernels.
 
     ``x`` is either the reference layout (B, C, L) -- only channel 0 is read, through the row
     stride, never copied -- or an already compacted (B, L') channel-0 buffer with
@@ -299,11 +300,15 @@ def imu_forward_native(encoder: "IMUEncoder", head_blob: Optional[torch.Tensor],
     msp = buf("msp", want_msp, (B,))
     energy = buf("energy", want_energy, (B,))
     maha = buf("maha", want_maha, (B,))
+    cls_img = None
+    if want_cls_img and B > 0:
+        cls_img = out.get("cls_img")
+        if cls_img is None:
+            cls_img = out["cls_img"] = operand_image(B, encoder.d_model, dev, zero=True)
+    o = N.ImuOutputs(N.ptr(cls), N.ptr(cls_img), N.ptr(tokens), N.ptr(logits), N.ptr(pred), N.ptr(msp), N.ptr(energy), N.ptr(maha))
     with torch.cuda.device(dev):
-        N.check(N.lib().cmhar_imu_forward(
-            blob.data_ptr(), N.ptr(head_blob), N.ptr(maha_blob), x.data_ptr(), B, stride,
-            N.ptr(cls), N.ptr(tokens), N.ptr(logits), N.ptr(pred), N.ptr(msp), N.ptr(energy), N.ptr(maha),
-            _prec_code(precision), N.stream_ptr(dev)))
+        N.check(N.lib().cmhar_imu_forward_ex(blob.data_ptr(), N.ptr(head_blob), N.ptr(maha_blob), x.data_ptr(), B, stride,
+                                             C.byref(o), _prec_code(precision), N.stream_ptr(dev)))
     return out
 
 
@@ -361,10 +366,14 @@ class _PackedLinear:
         return self.in_dim % 64 == 0 and self.out_dim % 64 == 0
 
 
-def operand_image(n: int, dim: int, device) -> torch.Tensor:
-    """Uninitialised bf16 operand image for (n, dim) activations: [ceil(n/128)][dim/64] SWIZZLE_128B chunks of 16 KiB
-    (what ``cmhar_linear_forward_img`` writes for the next layer and ``cmhar_similarity`` builds for its operands)."""
-    return N.alloc_blob(N.lib().cmhar_operand_image_bytes(n, dim), device)
+def operand_image(n: int, dim: int, device, zero: bool = False) -> torch.Tensor:
+    """bf16 operand image for (n, dim) activations: [ceil(n/128)][dim/64] SWIZZLE_128B chunks of 16 KiB (what
+    ``cmhar_linear_forward_img`` / ``cmhar_mlp2_forward_img`` write for the next kernel).  ``zero``: rows no kernel writes
+    (past the last window) read as zeros instead of stale memory."""
+    img = N.alloc_blob(N.lib().cmhar_operand_image_bytes(n, dim), device)
+    if zero:
+        img.zero_()
+    return img
 
 
 def l2_normalize_native(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -542,6 +551,31 @@ class ProjectionHead(_PackedMixin, nn.Module):
             _, h_img = l0.forward_img(n, True, x=x if x_img is None else None, x_img=x_img, want_rows=False, want_img=True)
             return l1.forward_img(n, False, x_img=h_img, want_rows=True)[0]
         return l1(l0(x, relu=True, precision=precision), relu=False, precision=precision)
+
+    def forward_fused(self, x_img: torch.Tensor, n: int, *, normalize: bool = True, want_rows: bool = True,
+                      want_img: bool = True, img_out: Optional[int] = None):
+        """The whole head (+ ``F.normalize``) as ONE tensor-core launch (``cmhar_mlp2_forward_img``): input and output as
+        bf16 operand images, the hidden activation never leaves tensor memory.  Returns ``(rows (n, out) or None, image or
+        None)``, or ``None`` when the dimensions are not the reference's (.. -> 512 -> 256): the caller chains
+        ``forward_native`` + ``l2_normalize_native`` then.  ``img_out``: raw device pointer the output image is written to
+        instead of a fresh allocation (a rank's slice of a peer-mapped buffer, ``peer.PeerBuffer``); the image slot of the
+        result is then that pointer."""
+        dev = x_img.device
+        l0, l1 = self._packed_layers(dev)
+        y = torch.empty((n, l1.out_dim), dtype=torch.float32, device=dev) if want_rows else None
+        img = None
+        if img_out is None and want_img and l1.out_dim % 64 == 0:
+            img = operand_image(n, l1.out_dim, dev)
+        img_ptr = img_out if img_out is not None else N.ptr(img)
+        with torch.cuda.device(dev):
+            rc = N.lib().cmhar_mlp2_forward_img(l0.blob.data_ptr(), l1.blob.data_ptr(), x_img.data_ptr(), n, l0.in_dim, l0.out_dim,
+                                                l1.out_dim, int(normalize), N.ptr(y), img_ptr, N.stream_ptr(dev))
+        if img_out is not None:
+            img = img_out
+        if rc == N.UNSUPPORTED:
+            return None
+        N.check(rc)
+        return y, img
 
     def forward(self, x):
         if _native_mode(self):

@@ -21,7 +21,7 @@ from typing import Dict, Iterable, List, Optional
 import torch
 
 from . import _native as N
-from .losses import similarity_native
+from .losses import similarity_img_native, similarity_img_work, similarity_native
 from .fusion import LateFusionClassifier
 from .models import CrossModalModel, IMUClassifier, imu_forward_native, l2_normalize_native, _prec_code, pack_generation
 from .ood import MahalanobisOOD
@@ -43,10 +43,67 @@ class CrossModalOODPipeline:
         self.sig = (float(sigmoid_scale), float(sigmoid_bias))
         self._host = None
         self._side = None           # side stream: the video branch runs concurrently with the IMU kernel
+        self._fused_ok = True       # bf16: the 7-launch route (fused projection heads / fusion head / similarity on operand images)
+
+    def _fused_route(self, fmap: Optional[torch.Tensor], pooled) -> bool:
+        ve = self.xm.video_encoder
+        return (self._fused_ok and fmap is not None and pooled is None and _prec_code(self.precision) == N.BF16
+                and ve.feature_dim % 64 == 0 and ve.projection.out_features % 64 == 0
+                and self.clf.imu_encoder.d_model % 64 == 0 and fmap.shape[0] > 0)
+
+    def _run_fused(self, imu, fmap, window_stride, sim_work) -> Optional[Dict[str, torch.Tensor]]:
+        """bf16 route, 7 launches: [encoder -> IMU projection head] || [pooling -> video projection -> video projection head],
+        then [fusion layer + classifier head + scores] and [similarity + sigmoid loss].  Every hand-over between kernels is a
+        bf16 operand image (plain bulk copies on the consumer side); L2 normalisation, the fusion layer, the loss's
+        zero-initialisation and its 1/n live inside those kernels.  Returns None if a fused kernel does not serve the dimensions."""
+        dev = imu.device
+        B = imu.shape[0]
+        main = torch.cuda.current_stream(dev)
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
+        ve = self.xm.video_encoder
+        if fmap.shape[0] != B * self.frames:
+            raise ValueError(f"{fmap.shape[0]} frames for {B} windows of {self.frames} frames")
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _, pimg = ve.pool_features(fmap, self.frames, want_img=True, want_rows=False)
+            _, vimg = ve._packed_projection(dev).forward_img(B, False, x_img=pimg, want_rows=False, want_img=True)
+            r = self.xm.video_proj.forward_fused(vimg, B)
+        if r is None:
+            main.wait_stream(side)
+            return None
+        vp, vp_img = r
+        if self.fusion is None:
+            scored = self.clf
+            maha_blob = scored._maha_state.blob(dev) if scored._maha_state is not None else None
+            out = imu_forward_native(self.clf.imu_encoder, scored._head_blob(dev), maha_blob, imu, want_cls=True, want_logits=True,
+                                     want_pred=True, want_msp=True, want_energy=True, want_maha=maha_blob is not None,
+                                     classes=scored.num_classes, precision=self.precision, window_stride=window_stride,
+                                     want_cls_img=True)
+        else:
+            out = imu_forward_native(self.clf.imu_encoder, None, None, imu, want_cls=True, precision=self.precision,
+                                     window_stride=window_stride, want_cls_img=True)
+        r = self.xm.imu_proj.forward_fused(out["cls_img"], B)
+        main.wait_stream(side)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in (vimg, vp, vp_img):
+                t.record_stream(main)
+        if r is None:
+            return None
+        ip, ip_img = r
+        if self.fusion is not None:
+            if self.fusion.forward_scores_img(out["cls_img"], vimg, B, out) is None:
+                return None
+        if sim_work is None:
+            sim_work = similarity_img_work(B, B, dev)
+        loss = similarity_img_native(ip_img, B, vp_img, B, ip.shape[1], sigmoid=self.sig, work=sim_work)
+        out.update(imu_proj=ip, video_proj=vp, loss=loss, _video_img=vimg, _imu_proj_img=ip_img, _video_proj_img=vp_img, _sim_work=sim_work)
+        return out
 
     @torch.no_grad()
     def run(self, imu: torch.Tensor, fmap: Optional[torch.Tensor], window_stride: Optional[int] = None,
-            pooled: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+            pooled: Optional[torch.Tensor] = None, sim_work: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """imu (B,6,L) fp32 [or compact (B,live) with window_stride]; fmap (B*frames,F,h,w) bf16/fp32
         or None for the IMU-only path; ``pooled`` (B,F) = the feature maps already reduced by
         ``video_encoder.pool_features`` (the HBM-bound stage can then be scheduled separately from the
@@ -56,6 +113,11 @@ class CrossModalOODPipeline:
             if self.fusion is not None:
                 raise ValueError("a pipeline with a fusion classifier needs the video feature maps")
             return self.clf.forward_scores(imu, precision=self.precision, want_cls=True, window_stride=window_stride)
+        if self._fused_route(fmap, pooled):
+            out = self._run_fused(imu, fmap, window_stride, sim_work)
+            if out is not None:
+                return out
+            self._fused_ok = False          # dimensions outside the fused kernels: the chained route below, from now on
         # fork: the HBM-bound video tail + its projection head on a side stream, the tensor-bound IMU
         # kernel + its projection head on the current stream; join before the similarity kernel.
         # (Captured into a CUDA graph this becomes two parallel branches.)
@@ -95,12 +157,14 @@ class CrossModalOODPipeline:
         """Record ``run`` on static inputs into a CUDA graph; returns (graph, outputs)."""
         side = torch.cuda.Stream(device=imu.device)
         side.wait_stream(torch.cuda.current_stream(imu.device))
+        # the similarity kernel's ticket workspace is zeroed ONCE here, outside the graph (the kernel re-arms it itself)
+        work = similarity_img_work(imu.shape[0], imu.shape[0], imu.device) if self._fused_route(fmap, None) else None
         with torch.cuda.stream(side):
-            self.run(imu, fmap)                      # warm-up: packs weights, sizes allocations
+            self.run(imu, fmap, sim_work=work)       # warm-up: packs weights, sizes allocations
         torch.cuda.current_stream(imu.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out = self.run(imu, fmap)
+            out = self.run(imu, fmap, sim_work=work)
         return graph, out
 
     # ------------------------------------------------------------------ host-buffer entry (e2e)

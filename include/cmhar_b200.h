@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CMHAR_ABI_VERSION 2
+#define CMHAR_ABI_VERSION 3
 
 #define CMHAR_OK               0
 #define CMHAR_ERR_INVALID     -1   /* bad argument / unsupported shape                       */
@@ -48,6 +48,8 @@ extern "C" {
 #define CMHAR_PATCH      16        /* configs/config.py:77-78 (patch == stride)               */
 #define CMHAR_MAX_SEQ    16        /* 1 + (250-16)/16 + 1 tokens survive, models.py:122-123   */
 #define CMHAR_MAX_CLASSES 64
+#define CMHAR_MAX_PEERS   8         /* ranks of one NVSwitch box        */
+#define CMHAR_PEER_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t)                              */
 
 typedef void* cmhar_stream_t;      /* cudaStream_t */
 
@@ -129,6 +131,21 @@ int cmhar_imu_forward(const void* encoder_blob, const void* head_blob, const voi
                       float* maha_out       /* (n)  = min_c Mahalanobis^2     */,
                       int32_t precision, cmhar_stream_t s);
 
+/* Same launch(es) with the outputs in a struct, plus `cls_img`: the CLS features ALSO as a bf16 SWIZZLE_128B operand image
+ * [ceil(n/128)][2][128 x 64] (cmhar_operand_image_bytes(n, 128)) -- the A operand cmhar_mlp2_forward_img and
+ * cmhar_fused_head_forward stream with plain bulk copies, so the step's next kernels never read fp32 rows.
+ * cls_img needs CMHAR_BF16 (CMHAR_ERR_UNSUPPORTED otherwise).  Rows past n_windows inside the last 8-window encoder tile
+ * are written as zeros; rows past that are left untouched (allocate the image zeroed). */
+typedef struct {
+    float*   cls;      void* cls_img;
+    float*   tokens;   float* logits;
+    int64_t* pred;     float* msp;
+    float*   energy;   float* maha;
+} cmhar_imu_outputs;
+int cmhar_imu_forward_ex(const void* encoder_blob, const void* head_blob, const void* maha_blob,
+                         const float* x, int64_t n_windows, int64_t x_window_stride,
+                         const cmhar_imu_outputs* out, int32_t precision, cmhar_stream_t s);
+
 /* Diagnostic hook of the bf16 tcgen05 path (used by tests/tools only): runs the encoder on
  * n_windows and dumps the fp32 residual stream held in TMEM, (ceil(n/8)*128, 128) floats, right
  * after `stage`: 0 = patch embedding, 1 = layer-0 attention + LayerNorm1, 2 = layer-0 output. */
@@ -146,10 +163,25 @@ int cmhar_debug_cta_trace(uint64_t* device_buffer, int64_t capacity_records);
  * CMHAR_FP32: fp32 FMA arithmetic.  CMHAR_BF16: the tensor-core kernel -- every layer, the whitening and the
  * class-mean products are tcgen05 MMAs on split-bf16 operands (x = hi + lo, three products per term, fp32
  * accumulation in TMEM: ~2^-17 relative, fp32-grade logits) -- for the reference head layout (256, 128, <= 32
- * classes); other layouts, or blobs copied after packing, silently use the fp32 kernel. */
+ * classes); other layouts, or blobs copied after packing, run the fp32 CUDA-core kernel (more accurate, ~10x slower):
+ * cmhar_head_kernel_kind tells which one a call will launch, so the choice is never hidden from the caller. */
 int cmhar_head_forward(const void* head_blob, const void* maha_blob, const float* feat, int64_t n,
                        float* logits_out, int64_t* pred_out, float* msp_out, float* energy_out,
                        float* maha_out, int32_t precision, cmhar_stream_t s);
+
+/* Which kernel cmhar_head_forward / the head stage of cmhar_imu_forward launches for these blobs at this precision:
+ * 1 = tcgen05 split-bf16 kernel (head_tc_kernel), 0 = fp32 CUDA-core kernel (head_scores_kernel). */
+int cmhar_head_kernel_kind(const void* head_blob, const void* maha_blob, int32_t precision);
+
+/* Late-fusion classifier in ONE launch (spec row A6: fusion.py LateFusionClassifier; no reference implementation):
+ *   fused = relu(BN([x1 | x2] Wf^T + bf))  -- bf16 tcgen05 MMAs on the two inputs' operand images, never concatenated --
+ *   then the classifier head and the scores exactly as cmhar_head_forward(CMHAR_BF16) computes them (split-bf16, fp32-grade)
+ *   on `fused`, which stays on chip (fused_out, optional, receives its fp32 rows).
+ * fusion_blob: cmhar_linear_pack of Linear(in_dim1 + in_dim2 -> 128) + BatchNorm; in_dim1, in_dim2 multiples of 64;
+ * head_blob of the reference layout (256, 128, <= 32 classes), maha_blob optional.  CMHAR_ERR_UNSUPPORTED otherwise. */
+int cmhar_fused_head_forward(const void* fusion_blob, const void* x1_img, int32_t in_dim1, const void* x2_img, int32_t in_dim2,
+                             int64_t n, const void* head_blob, const void* maha_blob, float* fused_out, float* logits_out,
+                             int64_t* pred_out, float* msp_out, float* energy_out, float* maha_out, cmhar_stream_t s);
 
 /* MSP / energy from stored logits (spec rows A1, A2; no reference implementation). */
 int cmhar_logit_scores(const float* logits, int64_t n, int32_t classes, float temperature,
@@ -189,6 +221,15 @@ int    cmhar_concat_linear_forward(const void* blob, const float* x1, int32_t in
 size_t cmhar_operand_image_bytes(int64_t n, int32_t dim);
 int    cmhar_linear_forward_img(const void* blob, const float* x, const void* x_img, int64_t n, int32_t in_dim,
                                 int32_t out_dim, int32_t relu, float* y, void* y_img, cmhar_stream_t s);
+
+/* A whole projection head in ONE launch (reference ProjectionHead.forward, src/models/models.py:226-234, and the
+ * F.normalize(dim=1) that follows it in CrossModalModel.forward, :288-289):
+ *   y = normalize?(relu(BN(x W0^T + b0)) W1^T + b1), x as a bf16 operand image, the 512-wide hidden activation kept in
+ *   tensor memory, y as fp32 rows (n, 256) and / or as the bf16 operand image cmhar_similarity_img streams.
+ * blob0 / blob1: cmhar_linear_pack blobs of Linear(in_dim -> 512)+BN and Linear(512 -> 256); in_dim % 64 == 0.
+ * Other dimensions: CMHAR_ERR_UNSUPPORTED (chain cmhar_linear_forward_img + cmhar_l2_normalize instead). */
+int    cmhar_mlp2_forward_img(const void* blob0, const void* blob1, const void* x_img, int64_t n, int32_t in_dim,
+                              int32_t hidden, int32_t out_dim, int32_t l2_normalize, float* y, void* y_img, cmhar_stream_t s);
 
 /* rows x / max(||x||_2, 1e-12)   (F.normalize(dim=1), models.py:288-289); in place allowed */
 int    cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmhar_stream_t s);
@@ -263,6 +304,36 @@ int cmhar_similarity(const float* a, const float* b, int64_t na, int64_t nb, int
                      float* sim_out, float sig_scale, float sig_bias, double* sigmoid_sum_out,
                      float lse_scale, float* row_lse_out, float* col_lse_out, float* diag_out,
                      void* work, int32_t precision, cmhar_stream_t s);
+
+/* Sigmoid contrastive loss (losses.py:37-52) from operands that ALREADY are bf16 operand images (what
+ * cmhar_mlp2_forward_img writes), with the B operand optionally partitioned over `n_parts` buffers of `rows_per_part` rows
+ * each (rows_per_part % 128 == 0 when n_parts > 1): the ranks' shards of the video embeddings.  Pointers of other ranks
+ * (cmhar_peer_open) are read over NVLink by the same cp.async.bulk ring that feeds the MMAs -- the all-gather of
+ * SURVEY.md section 8e row 3 happens inside the GEMM, tile by tile, and no gathered copy is ever written.
+ *   result = out_scale * sum_ij softplus(-(a_i . b_j * sig_scale + sig_bias))   over this call's (na x nb) block,
+ * reduced deterministically (per-CTA partials added in index order by the last CTA; no zero-initialised accumulator, no
+ * atomics on the value) and stored to every pointer of sum_dst (n_dst >= 1; a rank's slot in every rank's slot array).
+ * b_imgs / sum_dst are HOST arrays of device pointers.  work: cmhar_similarity_img_work_bytes, zeroed once by the caller.
+ * dim % 64 == 0, dim <= 256. */
+size_t cmhar_similarity_img_work_bytes(int64_t na, int64_t nb);
+int cmhar_similarity_img(const void* a_img, int64_t na, const void* const* b_imgs, int32_t n_parts, int64_t rows_per_part,
+                         int64_t nb, int32_t dim, float sig_scale, float sig_bias, double out_scale,
+                         double* const* sum_dst, int32_t n_dst, void* work, cmhar_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer-GPU memory (one process per GPU).  The ONLY entry points that allocate: a buffer other ranks
+ * read over NVLink must come from cudaMalloc (CUDA IPC), not from a caching allocator's sub-allocation.
+ * ------------------------------------------------------------------------------------------ */
+int cmhar_peer_alloc(size_t bytes, void** ptr_out);                 /* zero-filled; synchronous                         */
+int cmhar_peer_free(void* ptr);
+int cmhar_peer_export(const void* ptr, void* handle_out /* CMHAR_PEER_HANDLE_BYTES */);
+int cmhar_peer_open(const void* handle, void** ptr_out);            /* maps another rank's buffer into this process      */
+int cmhar_peer_close(void* ptr);
+/* Barrier across the ranks of one box, enqueued on the stream: flag_blocks (HOST array of `world` device pointers, [rank] = the
+ * local block, the others peer-mapped; CMHAR_MAX_PEERS uint64 each, zeroed at allocation), local_epoch = one uint64 of local
+ * device memory (zeroed).  Optionally finishes a reduction after the barrier: *sum_out = scale * sum(slots[0..n_slots)). */
+int cmhar_peer_barrier(void* const* flag_blocks, int32_t rank, int32_t world, void* local_epoch, const double* slots,
+                       int32_t n_slots, double scale, double* sum_out, cmhar_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Mahalanobis OOD (spec rows A3/A4 -- no reference implementation)

@@ -120,7 +120,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(cm._native.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert cm._native.lib().cmhar_abi_version() == 2
+    assert cm._native.lib().cmhar_abi_version() == 3
     # argument validation happens before any CUDA call
     assert cm._native.lib().cmhar_imu_encoder_blob_bytes(16, 4) > 3_000_000
     assert cm._native.lib().cmhar_imu_encoder_blob_bytes(17, 4) == 0
