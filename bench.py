@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--lanes", type=int, default=16, help="CUDA streams independent steps are pipelined over (1 = serial)")
+    ap.add_argument("--regions", type=int, default=15, help="the K-step timed region is repeated this many times; the median is reported")
+    ap.add_argument("--workloads", default="all", help="comma list of the extra BASELINE configs measured in the same run: similarity (configs[2]), mahalanobis (configs[3]), sweep (configs[4]), all, none")
+    ap.add_argument("--sweep-windows", type=int, default=10_000_000, help="configs[4]: global number of test windows (plus 1/10 of it for the fit)")
+    ap.add_argument("--maha-rows", type=int, default=1_000_000, help="configs[3]: feature rows fitted AND scored per GPU")
     return ap.parse_args()
 
 
@@ -149,6 +153,18 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def captured_traffic(kernel, units):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` at `units` rows / windows per launch,
+    looked up in the COMMITTED capture index profiles/traffic.json ({"<kernel>@<units>": {"bytes": .., "source": "profiles/.."}});
+    (None, None) when no capture of that launch shape is committed -- nothing is pasted into this file."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        ent = json.load(open(path)).get(f"{kernel}@{units}")
+    except (OSError, ValueError):
+        ent = None
+    return (ent["bytes"], ent["source"]) if ent else (None, None)
+
+
 # ----------------------------------------------------------------------------- CPU baseline / reference arm
 def cpu_workload(clf, xm, fus, batch, budget_s=15.0, min_iters=3):
     """The oracle port (oracle/oracle.py = CPU restatement of the reference modules, torch CPU ops,
@@ -222,6 +238,234 @@ def run_reference(args):
     emit(line)
 
 
+# ----------------------------------------------------------------------------- the other BASELINE configs (same run)
+def _median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+def _time_region(fn, iters, stream, dev, barrier, dist, world, regions=5):
+    """`iters` calls of fn bracketed by barrier + synchronize, CUDA events on `stream`, MAX over ranks; median of `regions`."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = []
+    for _ in range(regions):
+        barrier()
+        e0.record(stream)
+        for i in range(iters):
+            fn(i)
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out.append(float(t) / iters)
+    return _median(out)
+
+
+def workload_sharded_similarity(cm, cfg, clf, xm, dev, rank, world, barrier, dist, precision, steps, warmup):
+    """BASELINE configs[2]: cross-attention fusion classifier + the contrastive IMU<->video similarity matrix of the FULL batch
+    of 4096, rows sharded over the ranks (strong scaling).  The reference computes that loss on the outputs DataParallel gathered
+    on GPU 0 (main.py:89-95, src/train/trainer.py:135-136, src/models/losses.py:37-52); here every rank keeps its rows and the
+    all-gather of the video embeddings happens INSIDE the similarity GEMM: the kernel streams the other ranks' operand-image
+    tiles out of their HBM over NVLink (peer memory), bracketed by two NVLink barrier kernels, the second of which sums the
+    per-rank partial losses in rank order.  The NCCL route (all_gather_into_tensor + the same kernel + all_reduce) is timed
+    beside it as the baseline.  The timed region contains the exchange."""
+    import torch
+    from crossmodal_imu_video_ood_har_b200.losses import similarity_img_native, similarity_img_work
+    from crossmodal_imu_video_ood_har_b200.models import imu_forward_native, operand_image
+    from crossmodal_imu_video_ood_har_b200.sharded import ShardedSimilarity
+    G = 4096
+    rows = G // world
+    torch.manual_seed(5)
+    xfus = cm.CrossAttentionFusionClassifier(xm.imu_encoder, xm.video_encoder, cfg).to(dev).eval()
+    n_sets = 2 if rows >= 2048 else max(2, min(8, -(-300_000_000 // (rows * 268_144))))       # rotating inputs > L2
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    sets = [(torch.randn(rows, 6, WINDOW, device=dev, generator=g),
+             torch.relu(torch.randn(rows * FRAMES, FEAT_C, FEAT_HW, FEAT_HW, device=dev, generator=g)).to(torch.bfloat16)) for _ in range(n_sets)]
+    ss = ShardedSimilarity(rows, 256, dev, transport="peer")
+    ve = xm.video_encoder
+    keep = [dict() for _ in range(n_sets)]
+
+    def step(i, sim=ss):
+        imu, fmap = sets[i % n_sets]
+        o = keep[i % n_sets]
+        out = imu_forward_native(clf.imu_encoder, None, None, imu, want_cls=True, want_tokens=True, precision=precision,
+                                 want_cls_img=True, out=o.setdefault("enc", {}))
+        frame_feats = ve.forward_frame_features(fmap, precision=precision)
+        fused = xfus.fuse_native(out["tokens"], frame_feats.view(rows, FRAMES, -1), precision)
+        xfus._scores(fused, o.setdefault("sc", {}), precision)
+        _, pimg = ve.pool_features(fmap, FRAMES, want_img=True, want_rows=False)
+        _, vimg = ve._packed_projection(dev).forward_img(rows, False, x_img=pimg, want_rows=False, want_img=True)
+        r1 = xm.video_proj.forward_fused(vimg, rows, want_rows=False, img_out=sim.video_image_ptr)
+        r2 = xm.imu_proj.forward_fused(out["cls_img"], rows, want_rows=False)
+        if r1 is None or r2 is None:
+            raise RuntimeError("fused projection head does not serve these dimensions")
+        o["ip_img"] = r2[1]
+        return sim(r2[1])
+
+    stream = torch.cuda.current_stream(dev)
+    for i in range(max(3, warmup)):
+        step(i)
+    barrier()
+    n_iter = max(5, min(steps, 40))
+    step_ms = _time_region(step, n_iter, stream, dev, barrier, dist, world)
+    loss = float(ss.loss)
+    # the exchange alone: barrier + similarity over every rank's tiles + barrier/sum, on the images of the last step
+    ip_img = keep[0]["ip_img"]
+    sim_peer_ms = _time_region(lambda i: ss(ip_img), 50, stream, dev, barrier, dist, world)
+    # the same GEMM with every B tile in LOCAL memory (no exchange): what the peer reads cost on top
+    local_b = operand_image(G, 256, dev, zero=True)
+    work = similarity_img_work(rows, G, dev)
+    part = torch.zeros((), dtype=torch.float64, device=dev)
+    sim_local_ms = _time_region(lambda i: similarity_img_native(ip_img, rows, local_b, G, 256, sigmoid=ss.sigmoid, work=work, loss=part),
+                                50, stream, dev, barrier, dist, world)
+    sim_nccl_ms = None
+    if world > 1:
+        sn = ShardedSimilarity(rows, 256, dev, transport="nccl")
+        sn.video_image().copy_(ss.video_image())
+        for _ in range(3):
+            sn(ip_img)
+        sim_nccl_ms = _time_region(lambda i: sn(ip_img), 50, stream, dev, barrier, dist, world)
+        loss_nccl = float(sn.loss)
+        barrier()
+        sn.close()
+    barrier()
+    ss.close()
+    res = {"workload": f"configs[2] cross-attention fusion classifier + contrastive similarity matrix, global batch {G} sharded over {world} GPU(s) ({rows} rows/GPU): "
+                       "IMU encoder (tokens + CLS), per-frame video features, cross-attention fusion + head + scores, both projection heads, "
+                       f"{rows}x{G}x256 similarity + sigmoid loss with the other ranks' video embeddings read over NVLink inside the GEMM",
+           "metric": "windows/s", "scaling": "strong", "value": G / (step_ms * 1e-3), "ms_per_step": step_ms, "global_batch": G,
+           "rows_per_gpu": rows, "steps": n_iter, "loss": loss,
+           "exchange": {"transport": "peer memory (cp.async.bulk from the peers' HBM over NVLink/NVSwitch) + 2 NVLink barrier kernels",
+                        "ms": sim_peer_ms, "share_of_step": sim_peer_ms / step_ms, "same_gemm_all_local_ms": sim_local_ms,
+                        "nccl_all_gather_route_ms": sim_nccl_ms, "bytes_read_from_peers": (world - 1) * rows * 256 * 2,
+                        "flop": 2.0 * rows * G * 256, "tflops": 2.0 * rows * G * 256 / (sim_peer_ms * 1e-3) / 1e12}}
+    if world > 1:
+        res["exchange"]["loss_nccl_route"] = loss_nccl
+    return res
+
+
+def workload_mahalanobis(cm, dev, rank, world, barrier, dist, precision, n_rows, peaks):
+    """BASELINE configs[3]: Mahalanobis class-mean / tied-covariance fit with the NCCL all-reduce of the statistics INSIDE the
+    timed region, then `n_rows` test rows scored, per GPU (weak scaling: every rank owns its shard of stored 128-d features).
+    One step = accumulate (tensor-core GEMMs over the rows) -> all-reduce of 20 512 doubles -> host fp64 Cholesky + pack ->
+    score (streaming GEMM + per-row reduction)."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(99)
+    mu = 2.0 * torch.randn(32, 128, device=dev, generator=g)               # same class means on every rank
+    g.manual_seed(1000 + rank)
+    y = torch.randint(0, 32, (n_rows,), device=dev, generator=g)
+    feats = mu[y] + torch.randn(n_rows, 128, device=dev, generator=g)
+    test = mu[torch.randint(0, 32, (n_rows,), device=dev, generator=g)] + torch.randn(n_rows, 128, device=dev, generator=g)
+    stream = torch.cuda.current_stream(dev)
+    m = cm.MahalanobisOOD(32, dev, ridge=1e-3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    rec = {"accumulate": [], "allreduce_finalize": [], "score": [], "total": []}
+    for it in range(2 + 7):
+        barrier()
+        m.reset()
+        ev[0].record(stream)
+        m.accumulate(feats, y, precision=precision)
+        ev[1].record(stream)
+        m.finalize()                          # NCCL all-reduce + D2H + host fp64 Cholesky (synchronises)
+        m.blob(dev)                           # pack the scorer state
+        ev[2].record(stream)
+        sc = m.score(test, precision=precision)
+        ev[3].record(stream)
+        barrier()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), ev[0].elapsed_time(ev[3])],
+                         device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it >= 2:
+            for k, v in zip(rec, t.tolist()):
+                rec[k].append(v)
+    med = {k: _median(v) for k, v in rec.items()}
+    # the collective alone (device time of the all-reduce of the statistics buffer)
+    coll_ms = 0.0
+    if world > 1:
+        buf = m._stats.clone()
+        for _ in range(3):
+            dist.all_reduce(buf)
+        coll_ms = _time_region(lambda i: dist.all_reduce(buf), 20, stream, dev, barrier, dist, world)
+    acc_gbs = n_rows * (512 + 8) / (med["accumulate"] * 1e-3) / 1e9
+    sc_gbs = n_rows * (512 + 4) / (med["score"] * 1e-3) / 1e9
+    return {"workload": f"configs[3] Mahalanobis fit (class means + tied covariance) with the NCCL all-reduce of the statistics inside the region + {n_rows} test rows scored, per GPU",
+            "metric": "rows fitted and scored / s", "scaling": "weak", "value": world * n_rows / (med["total"] * 1e-3), "ms_per_step": med["total"],
+            "rows_per_gpu": n_rows, "steps": len(rec["total"]),
+            "breakdown_ms": {"accumulate": med["accumulate"], "allreduce_finalize_pack": med["allreduce_finalize"], "score": med["score"]},
+            "collective": {"op": "all_reduce(SUM) of 20 512 doubles (164 KB), torch.distributed NCCL", "ms": coll_ms,
+                           "share_of_step": coll_ms / med["total"] if med["total"] else None},
+            "roofline": {"maha_fit_tc_kernel": {"bound": "hbm", "achieved": acc_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": acc_gbs / peaks["hbm_gbs"],
+                                                "traffic": captured_traffic("maha_fit_tc_kernel", n_rows)[0]},
+                         "maha_score_tc_kernel": {"bound": "hbm", "achieved": sc_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sc_gbs / peaks["hbm_gbs"],
+                                                  "traffic": captured_traffic("maha_score_tc_kernel", n_rows)[0]}},
+            "min_score_mean": float(sc.mean())}
+
+
+def workload_sweep(cm, clf, dev, rank, world, barrier, dist, precision, total_windows):
+    """BASELINE configs[4]: full evaluation sweep -- ID vs held-out-activity OOD split, all three scorers, results table --
+    over `total_windows` synthetic test windows (+ 1/10 of that for the Mahalanobis fit), sharded over the ranks (strong
+    scaling).  Windows are generated on the device in the compact live-sample layout (960 B per window), scores stay on the
+    device until the histogram metrics are final; rank 0 formats the table with tables.generate_ood_table."""
+    import torch
+    from crossmodal_imu_video_ood_har_b200.sweep import OODSweep
+    lo, hi = cm.shard_bounds(total_windows, rank, world)
+    n_test = hi - lo
+    n_fit = max(4096, n_test // 10)
+    CH = 65536
+    live = 240
+    held = [29, 30, 31]
+    g = torch.Generator(device=dev).manual_seed(31 + rank)
+    tgrid = torch.arange(live, device=dev, dtype=torch.float32) / 50.0
+
+    def synth(n):      # activity c = a class-specific pair of frequencies + noise (50 Hz sampling)
+        y = torch.randint(0, 32, (n,), device=dev, generator=g)
+        f1 = (0.5 + 0.25 * y.float())[:, None]
+        x = torch.sin(6.2831853 * f1 * tgrid[None]) + 0.5 * torch.sin(6.2831853 * (2.0 + 0.1 * y.float())[:, None] * tgrid[None])
+        return (x + 0.3 * torch.randn(n, live, device=dev, generator=g)).contiguous(), y
+
+    def batches(n):
+        for s in range(0, n, CH):
+            yield synth(min(CH, n - s))
+    # the generator above is part of the data source, not of the measured path: materialise the shard first when it fits
+    mat = (n_test + n_fit) * live * 4 < 40e9
+    fit_b = list(batches(n_fit)) if mat else None
+    test_b = list(batches(n_test)) if mat else None
+    sw = OODSweep(clf, held, precision=precision, ridge=1e-3, window_stride=live)
+    sw.fit(batches(4096))                      # warm-up: packs weights, sizes allocations
+    sw = OODSweep(clf, held, precision=precision, ridge=1e-3, window_stride=live)
+    barrier()
+    t0 = time.perf_counter()
+    sw.fit(fit_b if mat else batches(n_fit))
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    sw.score(test_b if mat else batches(n_test))
+    torch.cuda.synchronize(dev)
+    t2 = time.perf_counter()
+    table = sw.metrics()
+    torch.cuda.synchronize(dev)
+    t3 = time.perf_counter()
+    barrier()
+    t = torch.tensor([t1 - t0, t2 - t1, t3 - t2, t3 - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fit_s, score_s, metric_s, total_s = t.tolist()
+    clf.set_mahalanobis(None)
+    md = None
+    if rank == 0:
+        import pandas as pd
+        rows = cm.ood_rows("imu_classifier_random_init", "holdout_29_30_31", table)
+        md = cm.generate_ood_table(pd.DataFrame(rows))["ood_summary"].reset_index().to_dict(orient="records")
+    return {"workload": f"configs[4] full eval sweep: {total_windows} synthetic test windows (+{n_fit * world} fit windows), ID vs held-out activities {held}, "
+                        f"MSP / energy / Mahalanobis -> AUROC / FPR95 -> OOD table, sharded over {world} GPU(s)",
+            "metric": "windows/s (test windows / whole sweep incl. fit and metrics)", "scaling": "strong",
+            "value": total_windows / total_s, "seconds": {"fit": fit_s, "score": score_s, "metrics": metric_s, "total": total_s},
+            "score_pass_windows_per_s": total_windows / score_s, "inputs_materialised": mat,
+            "results": {k: {"auroc": v["auroc"], "fpr95": v["fpr95"]} for k, v in table.items()}, "accuracy_id": sw.accuracy, "table": md}
+
+
 # ----------------------------------------------------------------------------- GPU arm
 _REAL_STDOUT = None
 
@@ -287,6 +531,9 @@ def main():
     pipe = cm.CrossModalOODPipeline(clf, xm, maha, frames=FRAMES, precision=precision, fusion=fus)
 
     bytes_per_set = B * (6 * WINDOW * 4 + FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2)
+    peaks = measured_peaks()
+    # algorithmic bytes of one step: live IMU samples + feature maps in; logits, pred, 3 scores, fused feature, both embeddings out
+    bytes_step = B * (960 + FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2 + 32 * 4 + 8 + 12 + 128 * 4 + 2 * 256 * 4)
     n_sets = max(2, -(-300_000_000 // bytes_per_set))           # rotate over > 2x L2 worth of inputs
     n_sets = min(max(n_sets, args.lanes), 64)
     sets = synth_inputs(dev, B, n_sets, rank)
@@ -335,19 +582,24 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    e0.record(stream)
-    t_host0 = time.perf_counter()
-    run_steps(args.steps, offset=args.warmup)
-    host_issue_ms = (time.perf_counter() - t_host0) * 1e3        # CPU time to enqueue the K steps (no sync inside)
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    # the K-step region is timed `regions` times (each bracketed by barrier + synchronize, CUDA events on the launching
+    # stream, MAX over ranks per region); the MEDIAN region is reported -- one sub-millisecond sample is not a measurement
+    region_ms, host_issue_ms = [], 0.0
+    for r in range(max(1, args.regions)):
+        barrier()
+        e0.record(stream)
+        t_host0 = time.perf_counter()
+        run_steps(args.steps, offset=args.warmup + r * args.steps)
+        host_issue_ms = (time.perf_counter() - t_host0) * 1e3    # CPU time to enqueue the K steps (no sync inside)
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        region_ms.append(float(t))
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t)
+    srt = sorted(region_ms)
+    ms_total = srt[len(srt) // 2]
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- dominant kernel alone (roofline): the fused IMU launch, timed with CUDA events
@@ -394,11 +646,11 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize(dev)
     pool_ms = e0.elapsed_time(e1) / k_iters
-    peaks = measured_peaks()
     tf = FLOP_ENC * B / (imu_ms * 1e-3) / 1e12
     gbs = (B * FRAMES * FEAT_C * FEAT_HW * FEAT_HW * 2 + B * FEAT_C * 4) / (pool_ms * 1e-3) / 1e9
     roofline = {"kernel": f"imu_forward_{precision}_kernel", "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"],
-                "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " burst (kernel timed alone)",
+                "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "traffic": captured_traffic(f"imu_forward_{precision}_kernel", B)[0],
+                "traffic_source": captured_traffic(f"imu_forward_{precision}_kernel", B)[1], "peak_source": peaks["source"] + " burst (kernel timed alone)",
                 "launch_ms": imu_ms, "flop_per_window": FLOP_ENC, "windows_per_launch": B}
     tf_lanes = FLOP_ENC * B / (imu_lanes_ms * 1e-3) / 1e12
     roofline_lanes = {"kernel": f"imu_forward_{precision}_kernel", "bound": "tensor", "achieved": tf_lanes, "peak": peaks["bf16_tflops_sustained"],
@@ -406,7 +658,8 @@ def main():
                       "ms_per_launch_amortised": imu_lanes_ms,
                       "note": "the step-sized launches of independent batches issued over the lanes: 32-CTA launches overlap on the 148 SMs"}
     roofline_video = {"kernel": "video_pool_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                      "frac": gbs / peaks["hbm_gbs"], "traffic": None, "launch_ms": pool_ms}
+                      "frac": gbs / peaks["hbm_gbs"], "traffic": captured_traffic("video_pool_kernel", B)[0],
+                      "traffic_source": captured_traffic("video_pool_kernel", B)[1], "launch_ms": pool_ms}
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the region
     imu_host = sets[0][0].cpu().pin_memory()
@@ -438,6 +691,19 @@ def main():
         checksum += int(res["pred"][0])
     torch.cuda.synchronize(dev)
     e2e_imu = B * e2e_steps / (time.perf_counter() - t0)
+
+    # ---- the other BASELINE configs, measured in the same run on every rank (collectives inside their timed regions)
+    workloads = {}
+    want = set(("similarity", "mahalanobis", "sweep") if args.workloads == "all" else
+               (w.strip() for w in args.workloads.split(",") if w.strip() not in ("", "none")))
+    if precision == "bf16":
+        for key, name, fn in (("configs[2]", "similarity", lambda: workload_sharded_similarity(cm, cfg, clf, xm, dev, rank, world, barrier, dist, precision, args.steps, args.warmup)),
+                              ("configs[3]", "mahalanobis", lambda: workload_mahalanobis(cm, dev, rank, world, barrier, dist, precision, args.maha_rows, peaks)),
+                              ("configs[4]", "sweep", lambda: workload_sweep(cm, clf, dev, rank, world, barrier, dist, precision, args.sweep_windows))):
+            if name in want:
+                torch.cuda.empty_cache()
+                workloads[key] = fn()
+    barrier()
 
     # ---- batch sweep of the fused IMU launch (information only; rank 0)
     sweep = {}
@@ -491,11 +757,9 @@ def main():
             torch.cuda.synchronize(dev)
             ms = e0.elapsed_time(e1) / 10
             gb = nbytes / (ms * 1e-3) / 1e9
-            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full captures of the same launches
-            # (profiles/logit_ring_kernel_r1m.md, profiles/maha_score_kernel_r1m.md): within 1 % of the algorithmic bytes
-            traffic = {"logit_scores_ring_kernel": 569_077_760, "maha_score_tc_kernel": 1_031_729_816}[name]
+            tr, tr_src = captured_traffic(name, n_rows if name.startswith("logit") else n_feat)
             scoring[name] = {"bound": "hbm", "achieved": gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb / peaks["hbm_gbs"],
-                             "launch_ms": ms, "bytes_per_launch": nbytes, "traffic": traffic}
+                             "launch_ms": ms, "bytes_per_launch": nbytes, "traffic": tr, "traffic_source": tr_src}
         del logits, feat
 
     cpu_baseline = None
@@ -513,7 +777,9 @@ def main():
         if sat:
             roofline_sat = {"kernel": f"imu_forward_{precision}_kernel", "bound": "tensor", "achieved": sat["tflops"],
                             "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": sat["tflops"] / peaks["bf16_tflops_sustained"],
-                            "traffic": 82_703_616, "peak_source": peaks["source"] + " sustained (back-to-back launches)",
+                            "traffic": captured_traffic(f"imu_forward_{precision}_kernel", 65536)[0],
+                            "traffic_source": captured_traffic(f"imu_forward_{precision}_kernel", 65536)[1],
+                            "peak_source": peaks["source"] + " sustained (back-to-back launches)",
                             "windows_per_launch": 65536, "flop_per_window": FLOP_ENC}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -529,6 +795,13 @@ def main():
                         "note": "pinned host buffers; fmap H2D (262 KB/clip) is the PCIe-bound term"},
                 "gpu_launches": launches_per_step * args.steps,
                 "launches_per_step": launches_per_step,
+                "timed_regions": {"count": len(region_ms), "reported": "median", "ms_per_step_min": srt[0] / args.steps,
+                                  "ms_per_step_median": ms_total / args.steps, "ms_per_step_max": srt[-1] / args.steps},
+                "roofline_step": {"bound": "hbm", "bytes_per_step": bytes_step, "achieved": bytes_step / (ms_total / args.steps * 1e-3) / 1e9,
+                                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bytes_step / (ms_total / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                  "note": "algorithmic bytes of one step per GPU (inputs read once + per-window outputs) over the measured time per step: "
+                                          "the step is HBM-bound (feature maps), floor = bytes_per_step / peak"},
+                "workloads": workloads,
                 "roofline": roofline, "roofline_overlapped_launches": roofline_lanes, "roofline_saturated_batch": roofline_sat, "roofline_video_tail": roofline_video,
                 "roofline_scoring": scoring,
                 "cpu_baseline": cpu_baseline, "imu_batch_sweep": sweep}

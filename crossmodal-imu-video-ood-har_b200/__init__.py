@@ -17,5 +17,6 @@ from .evaluator import Evaluator, classification_metrics, shard_bounds
 from .pipeline import CrossModalOODPipeline
 from .shards import WindowShard, write_shard, pack_npy_windows, live_samples
 from .tables import generate_ood_table, ood_rows, save_tables
+from .sweep import OODSweep, held_out_activity_split
 
 __version__ = "0.1.0"

@@ -105,12 +105,13 @@ class Evaluator:
         return dv
 
     @torch.no_grad()
-    def predict_scores(self, dataloader: Iterable, want_cls: bool = False) -> Dict[str, np.ndarray]:
-        """One pass over the loader: preds, labels, logits, msp, energy (+ maha, + cls)."""
+    def _predict_device(self, dataloader: Iterable, want_cls: bool = False):
+        """One pass over the loader; per-window results merged into DEVICE tensors (no device->host copy), host labels."""
         if not isinstance(self.model, IMUClassifier):
             raise TypeError("Evaluator needs an IMUClassifier")
         outs = []
         labels = []
+        merged: Dict[str, torch.Tensor] = {}
         with torch.cuda.device(self.device):
             for i, batch in enumerate(dataloader):
                 x = self._upload(batch["imu"], i & 1)
@@ -119,13 +120,19 @@ class Evaluator:
                 outs.append(res)
                 if "label" in batch:
                     labels.append(torch.as_tensor(batch["label"]).reshape(-1))
-            merged = {}
             if outs:
                 for k in outs[0]:
-                    merged[k] = torch.cat([o[k] for o in outs]).cpu().numpy()     # single D2H per field
+                    merged[k] = torch.cat([o[k] for o in outs])
+        return merged, (torch.cat(labels).numpy() if labels else np.zeros(0, np.int64))
+
+    @torch.no_grad()
+    def predict_scores(self, dataloader: Iterable, want_cls: bool = False) -> Dict[str, np.ndarray]:
+        """One pass over the loader: preds, labels, logits, msp, energy (+ maha, + cls) as numpy arrays."""
+        dev, labels = self._predict_device(dataloader, want_cls)
+        merged = {k: v.cpu().numpy() for k, v in dev.items()}                     # single D2H per field
         out = {"predictions": merged.get("pred", np.zeros(0, np.int64)),
                "logits": merged.get("logits", np.zeros((0, self.model.num_classes), np.float32)),
-               "labels": torch.cat(labels).numpy() if labels else np.zeros(0, np.int64)}
+               "labels": labels}
         for k in ("msp", "energy", "maha", "cls"):
             if k in merged:
                 out[k] = merged[k]
@@ -167,13 +174,13 @@ class Evaluator:
     @torch.no_grad()
     def evaluate_ood(self, id_loader, ood_loader, scorers=("msp", "energy", "maha")) -> Dict[str, Dict[str, float]]:
         """AUROC / FPR95 per scorer, ID loader vs held-out-activity (OOD) loader."""
-        rid, rood = self.predict_scores(id_loader), self.predict_scores(ood_loader)
+        # scores never leave the device between the scoring launches and the histogram kernels (SURVEY.md 8f.1)
+        rid, _ = self._predict_device(id_loader)
+        rood, _ = self._predict_device(ood_loader)
         table = {}
         for name in scorers:
-            if name not in rid:
+            if name not in rid or name not in rood:
                 continue
-            a = torch.from_numpy(rid[name]).to(self.device)
-            b = torch.from_numpy(rood[name]).to(self.device)
-            r = auroc_fpr95(a, b)
+            r = auroc_fpr95(rid[name], rood[name])
             table[name] = {"auroc": r["auroc"], "fpr95": r["fpr"], "auroc_bound": r["auroc_bound"]}
         return table

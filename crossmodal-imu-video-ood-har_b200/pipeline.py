@@ -239,9 +239,20 @@ class CrossModalOODPipeline:
         pending: List[dict] = []
 
         def finish(sl):
+            # the slot's pinned buffers are overwritten when the slot is re-enqueued `depth` batches later: hand out OWNED
+            # copies (5 KB per batch), so `list(pipe.stream_host(...))` and consumers that hold results stay correct
             sl["done"].synchronize()
-            return sl["res"]
+            return {k: v.clone() for k, v in sl["res"].items()}
 
+        try:
+            yield from self._stream_host_loop(batches, depth, graphs, dev, main, copy, slots, pending, finish)
+        finally:
+            # generator closed early (or raised): work of the handed-in batches may still be in flight on the copy / lane
+            # streams -- wait for it before the caller can re-key the slots or free what they point to
+            for sl in pending:
+                sl["done"].synchronize()
+
+    def _stream_host_loop(self, batches, depth, graphs, dev, main, copy, slots, pending, finish):
         for i, (imu_host, fmap_host) in enumerate(batches):
             B, L = imu_host.shape[0], imu_host.shape[-1]
             live = 16 * (self.clf.imu_encoder._check_native_dims(L) - 1)
@@ -252,7 +263,9 @@ class CrossModalOODPipeline:
                 yield finish(pending.pop(0))
             key = (B, live, None if fmap_host is None else (tuple(fmap_host.shape), fmap_host.dtype))
             if sl["key"] != key:
-                sl.update(key=key, graph=None, imu_pin=torch.empty((B, live), dtype=torch.float32).pin_memory(),
+                if sl.get("done") is not None and sl.get("used_any"):
+                    sl["done"].synchronize()               # the buffers about to be dropped may still be read by earlier work
+                sl.update(key=key, graph=None, used=False, imu_pin=torch.empty((B, live), dtype=torch.float32).pin_memory(),
                           imu_dev=torch.empty((B, live), dtype=torch.float32, device=dev),
                           res_pin=torch.empty((4, B), dtype=torch.float32).pin_memory(),
                           pred_pin=torch.empty((B,), dtype=torch.int64).pin_memory(),
@@ -282,6 +295,7 @@ class CrossModalOODPipeline:
                 with torch.cuda.stream(sl["lane"]):
                     sl["graph"].replay()
                     sl["done"].record(sl["lane"])
+                sl["used_any"] = True
                 res = {"pred": sl["pred_pin"], "msp": sl["res_pin"][0], "energy": sl["res_pin"][1]}
                 if sl["has_maha"]:
                     res["maha"] = sl["res_pin"][2]
@@ -293,7 +307,7 @@ class CrossModalOODPipeline:
                 # event), not for the whole compute stream -- waiting on the stream serialised copy(i) behind
                 # compute(i-1) and left the PCIe link idle for the length of a step (46 GB/s instead of 55)
                 copy.wait_event(sl["done"])
-            sl["used"] = True
+            sl["used"] = sl["used_any"] = True
             with torch.cuda.stream(copy):
                 sl["imu_dev"].copy_(sl["imu_pin"], non_blocking=True)
                 fdev = None

@@ -221,3 +221,56 @@ def test_slot_graphs_follow_reloaded_weights():
     got = [r["energy"].clone() for r in pipe.stream_host(iter(batches))]
     assert all(torch.equal(g, w) for g, w in zip(got, want))
     assert not all(torch.equal(g, f) for g, f in zip(got, first))
+
+
+def test_stream_host_results_are_owned_and_early_close_is_safe():
+    """``list(pipe.stream_host(...))`` WITHOUT cloning: every yielded result is an owned copy, not a view of the ring slot's
+    pinned buffers (which later batches overwrite).  Closing the generator early waits for the work in flight; a following
+    call with another batch shape re-keys the slots and still returns correct results."""
+    clf, xm, sd_c, sd_x = build()
+    pipe = cm.CrossModalOODPipeline(clf, xm, None, frames=16, precision="bf16")
+    batches = [(torch.from_numpy(W.imu_windows(90 + i, 64)), None) for i in range(7)]
+    want = [{k: v.clone() for k, v in pipe.run_host(a, None).items()} for a, _ in batches]
+    for graphs in (True, False):
+        got = list(pipe.stream_host(iter(batches), depth=2, graphs=graphs))           # no clone on purpose
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert all(torch.equal(g[k], w[k]) for k in w)
+    gen = pipe.stream_host(iter(batches), depth=2)
+    first = next(gen)
+    gen.close()                                                                        # abandons two batches in flight
+    assert torch.equal(first["pred"], want[0]["pred"])
+    other = [(torch.from_numpy(W.imu_windows(120 + i, 96)), None) for i in range(3)]
+    want2 = [{k: v.clone() for k, v in pipe.run_host(a, None).items()} for a, _ in other]
+    got2 = list(pipe.stream_host(iter(other), depth=2))
+    for g, w in zip(got2, want2):
+        assert all(torch.equal(g[k], w[k]) for k in w)
+
+
+def test_ood_sweep_matches_spec_on_held_out_activity_split():
+    """``OODSweep`` (configs[4]): fit on the ID rows only, one fused launch per batch, scores device resident, histogram
+    AUROC / FPR95 -- against the float64 spec computed from the same path's own outputs, to 3 decimals; held-out rows never
+    reach the fit (count check)."""
+    from oracle import ood_spec
+    clf, xm, sd_c, sd_x = build()
+    held = [3, 17, 30]
+    rs = np.random.RandomState(5)
+    xs = [torch.from_numpy(W.imu_windows(200 + i, 500)).to(DEV) for i in range(4)]
+    ys = [torch.from_numpy(rs.randint(0, 32, size=500).astype(np.int64)).to(DEV) for _ in range(4)]
+    sw = cm.OODSweep(clf, held, precision="fp32", ridge=1e-3)
+    maha = sw.fit(zip(xs[:2], ys[:2]))
+    y_fit = torch.cat(ys[:2]).cpu().numpy()
+    assert int(maha.fit_["count"].sum()) == int((~np.isin(y_fit, held)).sum())
+    assert all(maha.fit_["count"][h] == 0 for h in held)
+    sw.score(zip(xs[2:], ys[2:]))
+    table = sw.metrics()
+    res = [clf.forward_scores(x, precision="fp32") for x in xs[2:]]
+    y = torch.cat(ys[2:]).cpu().numpy()
+    ood = np.isin(y, held)
+    for k in ("msp", "energy", "maha"):
+        s = torch.cat([r[k] for r in res]).cpu().numpy()
+        assert round(table[k]["auroc"], 3) == round(ood_spec.auroc(s[~ood], s[ood]), 3)
+        assert round(table[k]["fpr95"], 3) == round(ood_spec.fpr_at_tpr_fast(s[~ood], s[ood]), 3)
+    pred = torch.cat([r["pred"] for r in res]).cpu().numpy()
+    assert abs(sw.accuracy - 100.0 * (pred[~ood] == y[~ood]).mean()) < 1e-9
+    clf.set_mahalanobis(None)

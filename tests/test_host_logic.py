@@ -233,3 +233,19 @@ def test_pack_generation_moves_whenever_packed_blobs_are_dropped():
     clf.set_mahalanobis(None)
     g4 = pack_generation()
     assert g0 < g1 < g2 < g3 < g4
+
+
+def test_held_out_activity_split_numpy_and_torch():
+    """ID = labelled rows outside the held-out activities, OOD = rows of the held-out activities; unlabelled rows (-1) are in
+    neither population (the reference's datasets.py has no such split)."""
+    import numpy as np
+    import torch
+    from crossmodal_imu_video_ood_har_b200.sweep import held_out_activity_split
+    y = np.array([0, 5, 31, 5, -1, 7, 30, 30])
+    idm, oodm = held_out_activity_split(y, [30, 31, 31])
+    assert idm.tolist() == [True, True, False, True, False, True, False, False]
+    assert oodm.tolist() == [False, False, True, False, False, False, True, True]
+    idt, oodt = held_out_activity_split(torch.from_numpy(y), [30, 31])
+    assert idt.tolist() == idm.tolist() and oodt.tolist() == oodm.tolist()
+    idm2, oodm2 = held_out_activity_split(y, [])
+    assert oodm2.sum() == 0 and idm2.sum() == 7
