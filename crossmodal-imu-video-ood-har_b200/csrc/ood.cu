@@ -394,8 +394,8 @@ extern "C" {
 
 int cmhar_logit_scores(const float* logits, int64_t n, int32_t classes, float temperature, int64_t* pred_out,
                        float* msp_out, float* energy_out, cmhar_stream_t s) {
+    if (n <= 0) return CMHAR_OK;                 // empty shard
     CMHAR_REQUIRE(logits && classes >= 1 && temperature > 0.f, "cmhar_logit_scores: bad argument");
-    if (n <= 0) return CMHAR_OK;
     const float invT = 1.f / temperature;
     long long* pred = reinterpret_cast<long long*>(pred_out);
     cudaStream_t st = (cudaStream_t)s;
@@ -433,9 +433,9 @@ int cmhar_logit_scores(const float* logits, int64_t n, int32_t classes, float te
 
 int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float* score, int32_t precision,
                      cmhar_stream_t s) {
+    if (n <= 0) return CMHAR_OK;                 // empty shard
     CMHAR_REQUIRE(maha_blob && feat && score, "cmhar_maha_score: null argument");
     CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
-    if (n <= 0) return CMHAR_OK;
     if (precision == CMHAR_BF16) {       // tensor-core kernels (whitening + class-mean products as split-bf16 MMAs) when eligible
         BlobInfo mi{};
         if (((uintptr_t)feat & 15) == 0 && lookup_blob(maha_blob, &mi) && mi.magic == MAHA_MAGIC && mi.has_tc) {
@@ -465,10 +465,10 @@ int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float*
 
 int cmhar_maha_accumulate(const float* feat, const int64_t* labels, int64_t n, int32_t classes, double* count,
                           double* sum, double* second, int32_t precision, cmhar_stream_t s) {
+    if (n <= 0) return CMHAR_OK;                 // empty shard: the statistics stay as they are
     CMHAR_REQUIRE(feat && labels && count && sum && second, "cmhar_maha_accumulate: null argument");
     CMHAR_REQUIRE(classes >= 1 && classes <= 64, "classes=%d outside [1,64]", classes);
     CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
-    if (n <= 0) return CMHAR_OK;
     if (precision == CMHAR_BF16 && ((uintptr_t)feat & 15) == 0)       // both reductions as split-bf16 tcgen05 GEMMs over the rows
         return launch_maha_fit_tc(feat, reinterpret_cast<const long long*>(labels), n, classes, count, sum, second, (cudaStream_t)s);
     const size_t smem = sizeof(double) * ((size_t)D * D + (size_t)classes * D + ((classes + 1) & ~1)) + sizeof(float) * MA_ROWS * D + sizeof(int) * MA_ROWS;
@@ -487,8 +487,8 @@ int cmhar_maha_accumulate(const float* feat, const int64_t* labels, int64_t n, i
 }
 
 int cmhar_score_key_range(const float* scores, int64_t n, uint32_t* key_min_max, cmhar_stream_t s) {
+    if (n <= 0) return CMHAR_OK;                 // an empty shard (a rank that holds no row of one population) is legal
     CMHAR_REQUIRE(scores && key_min_max, "cmhar_score_key_range: null argument");
-    if (n <= 0) return CMHAR_OK;
     const long long blocks = (n + 255) / 256;
     const int grid = (int)((blocks < 8LL * sm_count()) ? blocks : 8LL * sm_count());
     score_key_range_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(scores, n, key_min_max);
@@ -498,8 +498,8 @@ int cmhar_score_key_range(const float* scores, int64_t n, uint32_t* key_min_max,
 
 int cmhar_score_histogram(const float* scores, int64_t n, uint32_t key_lo, int32_t shift, int32_t bins,
                           unsigned long long* hist, cmhar_stream_t s) {
+    if (n <= 0) return CMHAR_OK;                 // empty shard: nothing to add
     CMHAR_REQUIRE(scores && hist && bins >= 1 && shift >= 0 && shift < 32, "cmhar_score_histogram: bad argument");
-    if (n <= 0) return CMHAR_OK;
     const long long blocks = (n + 255) / 256;
     const int grid = (int)((blocks < 8LL * sm_count()) ? blocks : 8LL * sm_count());
     score_histogram_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(scores, n, key_lo, shift, bins, hist);

@@ -6,7 +6,8 @@
 // cmhar_peer_barrier is the only cross-GPU synchronisation: rank r release-stores a monotonically increasing epoch into slot r
 // of every rank's flag block and acquire-spins on its own block until all slots carry that epoch.  The epoch counter lives in
 // device memory, so the launch can be captured in a CUDA graph and replayed.  The kernel waits on kernels of OTHER GPUs
-// only (one rank per GPU, like NCCL); a rank that never arrives trips the watchdog (trap) instead of hanging the box.
+// only (one rank per GPU, like NCCL); a rank that never arrives trips the watchdog
+// (%globaltimer, 20 s by default, CMHAR_PEER_TIMEOUT_MS) and traps instead of hanging the box.
 #include "common.cuh"
 
 namespace cmhar {
@@ -20,7 +21,14 @@ struct BarrierArgs {
     int n_slots;
     double scale;
     double* sum_out;
+    unsigned long long timeout_ns;                   // watchdog: a rank that never arrives traps this kernel instead of hanging the box
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -37,10 +45,12 @@ __global__ void peer_barrier_kernel(const BarrierArgs a) {
     __syncwarp();
     if (t < a.world) {
         st_release_sys(a.flags[t] + a.rank, e);                     // tell rank t that this rank has arrived
-        unsigned long long spins = 0;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned int spins = 0;
         while (ld_acquire_sys(a.flags[a.rank] + t) < e) {           // wait for rank t's arrival in the local block
-            if (++spins > (1ull << 31)) {
-                printf("cmhar peer barrier: rank %d timed out waiting for rank %d (epoch %llu)\n", a.rank, t, e);
+            if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > a.timeout_ns) {
+                printf("cmhar peer barrier: rank %d timed out after %llu ms waiting for rank %d (epoch %llu, saw %llu)\n", a.rank,
+                       a.timeout_ns / 1000000ull, t, e, ld_acquire_sys(a.flags[a.rank] + t));
                 __trap();
             }
         }
@@ -113,6 +123,12 @@ int cmhar_peer_barrier(void* const* flag_blocks, int32_t rank, int32_t world, vo
     }
     a.rank = rank; a.world = world; a.epoch = reinterpret_cast<unsigned long long*>(local_epoch);
     a.slots = slots; a.n_slots = n_slots; a.scale = scale; a.sum_out = sum_out;
+    static unsigned long long timeout_ms = 0;
+    if (timeout_ms == 0) {
+        const char* e = getenv("CMHAR_PEER_TIMEOUT_MS");        // default 20 s: ranks may be seconds apart (first-use compilation, host jitter)
+        timeout_ms = (e && atoll(e) > 0) ? (unsigned long long)atoll(e) : 20000ull;
+    }
+    a.timeout_ns = timeout_ms * 1000000ull;
     peer::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)s>>>(a);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;

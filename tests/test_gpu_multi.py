@@ -34,14 +34,21 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def stage(msg):                      # progress trail on stderr: a hang is attributable from the log of a timed-out run
+        import sys
+        print(f"[multi rank {rank}] {msg}", file=sys.stderr, flush=True)
     try:
         res = {}
+        stage("process group up")
         # ---- Mahalanobis fit across ranks with the tensor-core accumulate kernel
         feats, labels = W.class_features(7, 40003)
         lo, hi = cm.shard_bounds(len(feats), rank, world)
         m = cm.MahalanobisOOD(32, dev, ridge=1e-3)
         m.accumulate(torch.from_numpy(feats[lo:hi]).to(dev), torch.from_numpy(labels[lo:hi]).to(dev), precision="bf16")
+        stage("accumulated")
         m.finalize()                                                       # NCCL all-reduce inside
+        stage("finalized")
         res["mean"], res["whiten"], res["count"] = m.fit_["mean"], m.fit_["whiten"], m.fit_["count"]
         q, ql = W.class_features(8, 30000, ood_fraction=0.4)
         lo2, hi2 = cm.shard_bounds(len(q), rank, world)
@@ -50,6 +57,7 @@ def _worker(rank, world, port, out_dir):
         r = cm.auroc_fpr95(sc[~is_ood].contiguous(), sc[is_ood].contiguous())   # all-reduced key range + histograms
         res["auroc"], res["fpr"], res["bound"] = r["auroc"], r["fpr"], r["auroc_bound"]
         res["scores"] = sc.cpu().numpy()
+        stage("auroc done")
         # ---- sharded similarity: 256 rows per rank, unit-norm embeddings from a shared seed
         rows, dim = 256, 256
         g = torch.Generator().manual_seed(99)
@@ -59,12 +67,14 @@ def _worker(rank, world, port, out_dir):
         a_img = tail.image_of(a[rank * rows:(rank + 1) * rows].to(dev))
         for transport in ("peer", "nccl"):
             ss = ShardedSimilarity(rows, dim, dev, transport=transport)
+            stage(f"{transport}: buffers mapped")
             ss.video_image().copy_(tail.image_of(b[rank * rows:(rank + 1) * rows].to(dev)))
             vals = []
             for _ in range(3):                                             # epochs advance, tickets re-arm
                 vals.append(float(ss(a_img)))
             torch.cuda.synchronize(dev)
             res[f"loss_{transport}"] = np.array(vals)
+            stage(f"{transport}: 3 eager steps done {vals}")
             # captured in a CUDA graph (peer transport only: barriers + similarity are plain kernel launches)
             if transport == "peer":
                 s = torch.cuda.Stream(device=dev)
@@ -76,11 +86,18 @@ def _worker(rank, world, port, out_dir):
                 gr.replay(); gr.replay()
                 torch.cuda.synchronize(dev)
                 res["loss_peer_graph"] = float(ss.loss)
+                stage("peer: graph replays done")
             dist.barrier(device_ids=[rank])
             ss.close()
+            stage(f"{transport}: closed")
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), **res)
-    finally:
-        dist.destroy_process_group()
+    except BaseException:
+        # a rank that fails must not sit in destroy_process_group while the others wait in a collective: report and die,
+        # mp.spawn then terminates the remaining ranks and raises in the parent
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
+    dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world", [2])

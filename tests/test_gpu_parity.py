@@ -501,3 +501,18 @@ def test_linear_tensor_core_path(n, k, m):
                                                     N.BF16, N.stream_ptr(x.device))) if k > k1 else None
         if k > k1:
             assert torch.equal(y, got16)
+
+
+def test_empty_shards_are_legal_for_the_scoring_entry_points():
+    """A rank may hold no row of a population (e.g. all OOD rows of a contiguously sharded set live on the last rank): the
+    scoring / histogram / fit entry points accept n = 0 (null data pointers included) and leave their outputs untouched."""
+    e = torch.zeros(0, device=DEV)
+    r = cm.auroc_fpr95(torch.randn(100, device=DEV), e)
+    assert r["auroc"] != r["auroc"]                                   # NaN: no OOD rows anywhere
+    assert cm.logit_scores(torch.zeros(0, 32, device=DEV))["msp"].numel() == 0
+    feats, labels = W.class_features(3, 500)
+    m = cm.MahalanobisOOD(32, DEV, ridge=1e-3)
+    m.accumulate(torch.zeros(0, 128, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), precision="bf16")
+    m.accumulate(torch.from_numpy(feats).to(DEV), torch.from_numpy(labels).to(DEV), precision="bf16")
+    m.finalize(all_reduce=False)
+    assert m.score(torch.zeros(0, 128, device=DEV), precision="bf16").numel() == 0
