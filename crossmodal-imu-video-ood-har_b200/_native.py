@@ -99,6 +99,7 @@ _SIGNATURES = {
     "cmhar_linear_forward_img": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmhar_debug_cta_trace": (C.c_int, [C.c_void_p, C.c_int64]),
+    "cmhar_debug_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
     "cmhar_debug_imu_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmhar_head_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

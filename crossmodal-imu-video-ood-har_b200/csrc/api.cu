@@ -83,6 +83,17 @@ int cmhar_debug_cta_trace(uint64_t* device_buffer, int64_t capacity_records) {
     return CMHAR_OK;
 }
 
+int cmhar_debug_set_option(const char* key, int32_t value) {
+    CMHAR_REQUIRE(key, "cmhar_debug_set_option: null key");
+    if (strcmp(key, "enc_kernel") == 0) {
+        CMHAR_REQUIRE(value >= 0 && value <= 2, "cmhar_debug_set_option: enc_kernel must be 0, 1 or 2");
+        cmhar::g_enc_kernel.store(value, std::memory_order_relaxed);
+        return CMHAR_OK;
+    }
+    set_error("cmhar_debug_set_option: unknown key '%s'", key);
+    return CMHAR_ERR_INVALID;
+}
+
 int cmhar_debug_imu_bf16(const void* encoder_blob, const float* x, int64_t n_windows, int64_t x_window_stride,
                          int32_t stage, float* residual_dump, float* cls_out, int32_t* progress_host_mapped,
                          cmhar_stream_t s) {

@@ -6,6 +6,7 @@ namespace cmhar { struct FwdArgs; }
 #include "pack.cu"
 #include "imu_encoder_fp32.cu"
 #include "imu_encoder_bf16.cu"
+#include "imu_encoder_bf16_pair.cu"
 #include "head.cu"
 #include "head_tc.cu"
 #include "dense.cu"

@@ -731,10 +731,15 @@ __global__ void pack_param_blocks_kernel(const float* __restrict__ fp32, const f
     dst[i] = v;
 }
 
-size_t encoder_bf16_bytes(int layers) {
-    return (size_t)(1 + layers * CHUNKS_PER_LAYER) * CHUNK +
-           (size_t)(SB_FLOATS + CMHAR_MAX_LAYERS * PB_FLOATS + CMHAR_MAX_LAYERS * D) * sizeof(float);
+// bytes of the single-tile kernel's images + the parameter blocks; the pair kernel's images (imu_encoder_bf16_pair.cu) follow
+__host__ __device__ constexpr size_t encoder_bf16_single_bytes(int layers) {
+    return (size_t)(1 + layers * tc::CHUNKS_PER_LAYER) * tc::CHUNK +
+           (size_t)(tc::SB_FLOATS + CMHAR_MAX_LAYERS * tc::PB_FLOATS + CMHAR_MAX_LAYERS * D) * sizeof(float);
 }
+static_assert(encoder_bf16_single_bytes(1) % 16 == 0, "the pair section must stay 16-byte aligned for cp.async.bulk");
+size_t encoder_bf16_pair_bytes(int layers);                                                    // imu_encoder_bf16_pair.cu
+int pack_encoder_bf16_pair(const cmhar_imu_encoder_params* p, void* dst_section, cudaStream_t st);
+size_t encoder_bf16_bytes(int layers) { return encoder_bf16_single_bytes(layers) + encoder_bf16_pair_bytes(layers); }
 
 int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_section, void* bf16_section, cudaStream_t st) {
     uint8_t* dst = reinterpret_cast<uint8_t*>(bf16_section);
@@ -772,7 +777,7 @@ int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_secti
     const int total = SB_FLOATS + p->layers * PB_FLOATS;
     pack_param_blocks_kernel<<<(total + 255) / 256, 256, 0, st>>>(fp32_section, fold, p->layers, params);
     CMHAR_LAUNCH_CHECK();
-    return CMHAR_OK;
+    return pack_encoder_bf16_pair(p, dst + encoder_bf16_single_bytes(p->layers), st);
 }
 
 static int ablate_mask() {
@@ -780,6 +785,9 @@ static int ablate_mask() {
     if (m < 0) { const char* e = getenv("CMHAR_ABLATE"); m = e ? atoi(e) : 0; }
     return m;
 }
+
+int launch_imu_forward_bf16_pair(const Bf16Args& args, cudaStream_t stream);                  // imu_encoder_bf16_pair.cu
+std::atomic<int> g_enc_kernel{0};          // 0 = automatic, 1 = single-tile kernel, 2 = pair kernel (development: cmhar_debug_set_option)
 
 static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
     static bool configured[64] = {};
@@ -799,6 +807,14 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
         configured[dev & 63] = true;
     }
     const long long tiles = (args.f.n + 7) / 8;
+    // two or more tiles: the two-tiles-in-flight kernel (imu_encoder_bf16_pair.cu); a lone tile, the timeline / progress
+    // instrumentation and the ablation switches stay on the single-tile kernel.  g_enc_kernel: cmhar_debug_set_option
+    const int force = g_enc_kernel.load(std::memory_order_relaxed);
+    if (force != 1 && (tiles >= 2 || force == 2) && !args.progress && !args.tlog && !args.ablate) {
+        const int rc = launch_imu_forward_bf16_pair(args, stream);
+        if (rc != CMHAR_OK) return rc;
+        return launch_head_after_encoder(args.f, CMHAR_BF16, stream);
+    }
     const int grid = (int)((tiles < (long long)sm_count()) ? tiles : (long long)sm_count());
     if (nq == 2) imu_forward_bf16_kernel<2><<<grid, 320, SMEM_BYTES, stream>>>(args);
     else imu_forward_bf16_kernel<4><<<grid, 576, SMEM_BYTES, stream>>>(args);

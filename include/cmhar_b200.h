@@ -159,6 +159,12 @@ int cmhar_debug_imu_bf16(const void* encoder_blob, const float* x, int64_t n_win
  * appends {kernel id, SM id, start ns, end ns} (globaltimer).  Word 0 counts the records.  Synchronous. */
 int cmhar_debug_cta_trace(uint64_t* device_buffer, int64_t capacity_records);
 
+/* Development switch (tools / A-B measurements only; never read from the environment, so a stray variable cannot change
+ * results): key "enc_kernel" = 0 automatic (two-tiles-in-flight kernel imu_forward_bf16_pair_kernel whenever a launch has
+ * >= 2 tiles of 8 windows), 1 always the single-tile kernel, 2 always the pair kernel.  Process wide.
+ * Returns CMHAR_ERR_INVALID for an unknown key / value. */
+int cmhar_debug_set_option(const char* key, int32_t value);
+
 /* Same head + scores from stored features (row-major (n,128) fp32).
  * CMHAR_FP32: fp32 FMA arithmetic.  CMHAR_BF16: the tensor-core kernel -- every layer, the whitening and the
  * class-mean products are tcgen05 MMAs on split-bf16 operands (x = hi + lo, three products per term, fp32
