@@ -807,10 +807,11 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
         configured[dev & 63] = true;
     }
     const long long tiles = (args.f.n + 7) / 8;
-    // two or more tiles: the two-tiles-in-flight kernel (imu_encoder_bf16_pair.cu); a lone tile, the timeline / progress
-    // instrumentation and the ablation switches stay on the single-tile kernel.  g_enc_kernel: cmhar_debug_set_option
+    // The two-tiles-in-flight kernel (imu_encoder_bf16_pair.cu) is opt-in (cmhar_debug_set_option("enc_kernel", 2)): measured on
+    // B200 it is bit-identical to this kernel and 3-6 % faster per launch from 4 096 windows up, but a CTA holds two tiles
+    // for twice as long, which doubles the latency of the 256-window launches of the benchmarked step.
     const int force = g_enc_kernel.load(std::memory_order_relaxed);
-    if (force != 1 && (tiles >= 2 || force == 2) && !args.progress && !args.tlog && !args.ablate) {
+    if (force == 2 && !args.progress) {
         const int rc = launch_imu_forward_bf16_pair(args, stream);
         if (rc != CMHAR_OK) return rc;
         return launch_head_after_encoder(args.f, CMHAR_BF16, stream);

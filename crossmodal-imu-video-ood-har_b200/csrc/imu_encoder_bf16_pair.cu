@@ -51,17 +51,19 @@ static_assert(P_PB % 16 == 0 && P_ST % 16 == 0 && P_BAR % 8 == 0, "alignment");
 
 enum {
     PB_WA_FULL = 0, PB_WA_EMPTY = 2, PB_WF_FULL = 4, PB_WF_EMPTY = 6,
-    PB_ACC = 8,            // [2] side's MMA step complete (tcgen05.commit)
-    PB_RDY = 10,           // [2] side's epilogue pass complete (8 warp arrivals)
-    PB_PBFULL = 12,        // [side][2]
-    PB_PBEMPTY = 16,       // [side][2]
-    PB_STATIC = 20,
-    PB_COUNT = 21
+    PB_ACC_A = 8,          // [side] attention-half MMA step complete (tcgen05.commit of the A-role MMA warp)
+    PB_ACC_F = 10,         // [side] feed-forward-half MMA step complete (F-role MMA warp)
+    PB_RDY_A = 12,         // [side] epilogue pass complete, next step is an attention-half step (8 warp arrivals)
+    PB_RDY_F = 14,         // [side] ... next step is a feed-forward-half step
+    PB_PBFULL = 16,        // [side][2]
+    PB_PBEMPTY = 20,       // [side][2]
+    PB_STATIC = 24,
+    PB_COUNT = 25
 };
 static_assert(PB_COUNT * 8 + 8 <= 256, "barrier area too small");
 
 constexpr uint32_t TP_AS = 256, TP_FS = 448;             // TMEM columns: R(side) = 128 * side
-constexpr int NT_PAIR = 576;                             // 16 epilogue warps + MMA warp + producer warp
+constexpr int NT_PAIR = 640;                             // 16 epilogue warps + 2 MMA warps (one per role) + 2 producer warps (one per ring)
 
 struct Slot {
     bool a_valid, f_valid;
@@ -94,6 +96,20 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 
+// mbarrier wait with an optional nanosleep back-off between polls (a warp that spins without sleeping takes issue slots from
+// the MMA-issuing warp of the same SM sub-partition)
+__device__ __forceinline__ void mbar_wait_bo(uint32_t bar, uint32_t parity, int site, unsigned sleep_ns) {
+    uint32_t spins = 0;
+    while (!mbar_test(bar, parity)) {
+        if (sleep_ns) __nanosleep(sleep_ns);
+        if (++spins > (1u << 24)) {
+            if ((threadIdx.x & 31) == 0) printf("cmhar pair kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u site %d)\n",
+                                                (int)blockIdx.x, (int)threadIdx.x, (bar & 0xffu) >> 3, parity, site);
+            __trap();
+        }
+    }
+}
+
 // ======================================================================================== kernel
 __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args) {
     constexpr int CW = 64;
@@ -111,6 +127,9 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
     const long long tiles = (a.n + 7) / 8;
     const int m = (int)((tiles - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x);   // tiles of this CTA
     const int n_slots = slot_count(m, n_layers);
+    int tlog_n = 0;          // development: (code, clock64) timeline of block 0, lane 0 of every warp (args.tlog, tools/timeline_pair.py)
+#define TL(code) do { if (args.tlog && blockIdx.x == 0 && lane == 0 && tlog_n < TLOG_CAP) { \
+        args.tlog[(warp * TLOG_CAP + tlog_n) * 2] = (code); args.tlog[(warp * TLOG_CAP + tlog_n) * 2 + 1] = clock64(); ++tlog_n; } } while (0)
 
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + P_BAR;
@@ -119,7 +138,10 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
 
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(BAR(PB_WA_FULL + i), 1);          // ring A / F full + empty
-        for (int g = 0; g < 2; ++g) { mbar_init(BAR(PB_ACC + g), 1); mbar_init(BAR(PB_RDY + g), 8); }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(BAR(PB_ACC_A + g), 1); mbar_init(BAR(PB_ACC_F + g), 1);
+            mbar_init(BAR(PB_RDY_A + g), 8); mbar_init(BAR(PB_RDY_F + g), 8);
+        }
         for (int i = 0; i < 4; ++i) { mbar_init(BAR(PB_PBFULL + i), 1); mbar_init(BAR(PB_PBEMPTY + i), 8); }
         mbar_init(BAR(PB_STATIC), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -133,188 +155,173 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 17) {
-        // ================================================================= weight / parameter producer (one lane, two rings)
+    // mbarrier polling is expensive on this machine (test_wait ~150 cycles, try_wait ~90 on a completed phase, ~60 to wake a
+    // sleeping warp), so nobody polls two barriers: every role has ONE next thing to wait for and sleeps on it.
+    if (warp == 18) {
+        // ================================================================= producer of ring A (+ parameter blocks)
         if (lane == 0) {
             const uint64_t keep = l2_policy_evict_last();
             mbar_expect_tx(BAR(PB_STATIC), P_SB_FLOATS * 4);
             bulk_g2s(sbase + P_SB, gparams + SB_FLN, P_SB_FLOATS * 4, BAR(PB_STATIC));
-            // cursor of a ring: (slot, index of the next chunk inside the slot's list); -1 = slot not opened yet
-            int sa = 0, ja = -1, sf = 0, jf = -1;
-            uint32_t stA = 0, parA = 1, stF = 0, parF = 1;            // fresh barriers: waiting on parity 1 passes
-            uint32_t pb_bits = 0xFu;                                  // parity per (side, layer & 1) parameter block, fresh = 1
-            Slot ca = slot_info(0, m, n_layers), cf = ca;
-            bool pb_pending = false;
-            unsigned spins = 0;
-            while (sa < n_slots || sf < n_slots) {
-                bool progressed = false;
-                // ---- ring A: [patch chunk if layer 0] + 8 chunks of the layer, after the layer's parameter block
-                if (sa < n_slots) {
-                    if (ja < 0) {
-                        ca = slot_info(sa, m, n_layers);
-                        if (!ca.a_valid) { ++sa; progressed = true; }
-                        else { ja = 0; pb_pending = true; }
+            uint32_t st = 0, par = 1;                       // fresh barriers: waiting on parity 1 passes
+            uint32_t pb_bits = 0xFu;
+            for (int s = 0; s < n_slots; ++s) {
+                const Slot sl = slot_info(s, m, n_layers);
+                if (!sl.a_valid) continue;
+                const int bi = sl.a_side * 2 + (sl.a_layer & 1);
+                mbar_wait(BAR(PB_PBEMPTY + bi), (pb_bits >> bi) & 1u, 19);
+                pb_bits ^= (1u << bi);
+                mbar_expect_tx(BAR(PB_PBFULL + bi), PB_FLOATS * 4);
+                bulk_g2s(sbase + P_PB + bi * PB_FLOATS * 4, gparams + SB_FLOATS + (size_t)sl.a_layer * PB_FLOATS, PB_FLOATS * 4, BAR(PB_PBFULL + bi));
+                const int first = (sl.a_layer == 0) ? 1 : 0;              // list = [patch chunk] + 8 chunks of the layer
+                for (int j = 0; j < first + 8; ++j) {
+                    const int c = (first && j == 0) ? 0 : 1 + sl.a_layer * PAIR_CHUNKS_PER_LAYER + (j - first);
+                    mbar_wait(BAR(PB_WA_EMPTY + st), par, 1);
+                    if (args.ablate & ABL_NO_TMA) mbar_arrive(BAR(PB_WA_FULL + st));
+                    else {
+                        mbar_expect_tx(BAR(PB_WA_FULL + st), CHUNK);
+                        bulk_g2s_hint(sbase + P_WA + st * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(PB_WA_FULL + st), keep);
                     }
-                    if (ja >= 0 && pb_pending) {
-                        const int bi = ca.a_side * 2 + (ca.a_layer & 1);
-                        if (mbar_test(BAR(PB_PBEMPTY + bi), (pb_bits >> bi) & 1u)) {
-                            pb_bits ^= (1u << bi);
-                            mbar_expect_tx(BAR(PB_PBFULL + bi), PB_FLOATS * 4);
-                            bulk_g2s(sbase + P_PB + bi * PB_FLOATS * 4, gparams + SB_FLOATS + (size_t)ca.a_layer * PB_FLOATS, PB_FLOATS * 4,
-                                     BAR(PB_PBFULL + bi));
-                            pb_pending = false; progressed = true;
-                        }
-                    }
-                    if (ja >= 0 && !pb_pending && mbar_test(BAR(PB_WA_EMPTY + stA), parA)) {
-                        const int first = (ca.a_layer == 0) ? 1 : 0;          // list = [patch] + 8
-                        const int c = (first && ja == 0) ? 0 : 1 + ca.a_layer * PAIR_CHUNKS_PER_LAYER + (ja - first);
-                        mbar_expect_tx(BAR(PB_WA_FULL + stA), CHUNK);
-                        bulk_g2s_hint(sbase + P_WA + stA * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(PB_WA_FULL + stA), keep);
-                        if (++stA == 2) { stA = 0; parA ^= 1; }
-                        if (++ja == first + 8) { ja = -1; ++sa; }
-                        progressed = true;
-                    }
+                    TL(c);
+                    if (++st == 2) { st = 0; par ^= 1; }
                 }
-                // ---- ring F: 16 chunks of the layer
-                if (sf < n_slots) {
-                    if (jf < 0) {
-                        cf = slot_info(sf, m, n_layers);
-                        if (!cf.f_valid) { ++sf; progressed = true; }
-                        else jf = 0;
+            }
+        }
+    } else if (warp == 19) {
+        // ================================================================= producer of ring F
+        if (lane == 0) {
+            const uint64_t keep = l2_policy_evict_last();
+            uint32_t st = 0, par = 1;
+            for (int s = 0; s < n_slots; ++s) {
+                const Slot sl = slot_info(s, m, n_layers);
+                if (!sl.f_valid) continue;
+                for (int j = 0; j < 16; ++j) {
+                    const int c = 1 + sl.f_layer * PAIR_CHUNKS_PER_LAYER + 8 + j;
+                    mbar_wait(BAR(PB_WF_EMPTY + st), par, 1);
+                    if (args.ablate & ABL_NO_TMA) mbar_arrive(BAR(PB_WF_FULL + st));
+                    else {
+                        mbar_expect_tx(BAR(PB_WF_FULL + st), CHUNK);
+                        bulk_g2s_hint(sbase + P_WF + st * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(PB_WF_FULL + st), keep);
                     }
-                    if (jf >= 0 && mbar_test(BAR(PB_WF_EMPTY + stF), parF)) {
-                        const int c = 1 + cf.f_layer * PAIR_CHUNKS_PER_LAYER + 8 + jf;
-                        mbar_expect_tx(BAR(PB_WF_FULL + stF), CHUNK);
-                        bulk_g2s_hint(sbase + P_WF + stF * CHUNK, wchunks + (size_t)c * CHUNK, CHUNK, BAR(PB_WF_FULL + stF), keep);
-                        if (++stF == 2) { stF = 0; parF ^= 1; }
-                        if (++jf == 16) { jf = -1; ++sf; }
-                        progressed = true;
-                    }
+                    TL(c);
+                    if (++st == 2) { st = 0; par ^= 1; }
                 }
-                if (progressed) spins = 0;
-                else if (++spins > (1u << 27)) { printf("cmhar pair kernel: producer stuck (block %d, slots %d/%d of %d)\n", (int)blockIdx.x, sa, sf, n_slots); __trap(); }
             }
         }
     } else if (warp == 16) {
-        // ================================================================= MMA issuer (warp converged, one elected lane issues)
+        // ================================================================= MMA issuer of the attention halves (warp converged)
         const bool leader = elect_one();
-        constexpr uint32_t ID128 = idesc_bf16(128, 128), ID64 = idesc_bf16(128, 64), ID16 = idesc_bf16(128, 16);
+        const bool no_dense = (args.ablate & ABL_NO_DENSE_MMA) != 0, no_attn = (args.ablate & ABL_NO_ATTN_MMA) != 0;     // timing ablations (development)
+        constexpr uint32_t ID128 = idesc_bf16(128, 128), ID16 = idesc_bf16(128, 16);
         const uint64_t CH = CHUNK >> 4;
         const uint64_t dK = sw128_desc(sbase + P_K), dVT = sw128_desc(sbase + P_VT);
-        uint32_t stA = 0, parA = 0, stF = 0, parF = 0;
-        uint32_t rdy_bits = 0;                                        // parity per side of the RDY barrier
+        uint32_t stA = 0, parA = 0;
+        uint32_t rdy_bits = 0;                                        // parity per side of RDY_A
         auto ringA = [&]() -> uint64_t {
             mbar_wait(BAR(PB_WA_FULL + stA), parA, 2);
             tc_fence_after();
             return sw128_desc(sbase + P_WA + stA * CHUNK);
         };
         auto ringA_done = [&]() { if (leader) tc_commit(BAR(PB_WA_EMPTY + stA)); if (++stA == 2) { stA = 0; parA ^= 1; } };
+        for (int s = 0; s < n_slots; ++s) {
+            const Slot sl = slot_info(s, m, n_layers);
+            if (!sl.a_valid) continue;
+            const int g = sl.a_side;
+            const uint32_t R = tmem + 128u * (uint32_t)g, AS = tmem + TP_AS;
+            const uint64_t dH = sw128_desc(sbase + P_H0 + g * 32768);
+            // steps: -1 patch embedding (layer 0 only), 0 K, 1 V^T, 2 Q, 3 scores, 4 P V, 5 out-projection
+            for (int step = (sl.a_layer == 0 ? -1 : 0); step < 6; ++step) {
+                mbar_wait(BAR(PB_RDY_A + g), (rdy_bits >> g) & 1u, 4);
+                rdy_bits ^= (1u << g);
+                tc_fence_after();
+                TL(1000 * g + 10 + step);
+                if (step == -1) {
+                    const uint64_t dW = ringA();
+                    for (int k = 0; k < 3; ++k)
+                        if (leader && !no_dense) umma(R, dH + (uint64_t)(2 * k), dW + (uint64_t)(2 * k), ID128, 1u);
+                    ringA_done();
+                } else if (step <= 2) {
+                    for (int c = 0; c < 2; ++c) {
+                        const uint64_t dW = ringA();
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t wa = dW + (uint64_t)(2 * k), oa = dH + (uint64_t)c * CH + (uint64_t)(2 * k);
+                            if (leader && !no_dense) umma(AS, step == 1 ? wa : oa, step == 1 ? oa : wa, ID128, (c > 0 || k > 0) ? 1u : 0u);
+                        }
+                        ringA_done();
+                    }
+                } else if (step == 3) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                        for (int h = 0; h < H; ++h) {
+                            const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)((h & 3) * 2);
+                            if (leader && !no_attn) umma_ts_rows16(AS + 16 * h, AS + 128 + 8 * h, dK + off + (uint64_t)(j * 128), ID16, j);
+                        }
+                    }
+                } else if (step == 4) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint64_t koff = (uint64_t)(j >> 2) * CH + (uint64_t)((j & 3) * 2);
+#pragma unroll
+                        for (int h = 0; h < H; ++h) {
+                            const uint32_t ocol = (h < 2) ? 32 + 16 * h : (h < 4) ? 96 + 16 * (h - 2) : 128 + 16 * (h - 4);
+                            if (leader && !no_attn) umma_ts_rows16(AS + ocol, AS + tm_bf16_col<CW>(16 * h), dVT + koff + (uint64_t)(h * 128), ID16, j);
+                        }
+                    }
+                } else {
+                    for (int kc = 0; kc < 2; ++kc) {
+                        const uint64_t dW = ringA();
+                        for (int k = 0; k < 4; ++k)
+                            if (leader && !no_dense) umma_ts(R, AS + tm_bf16_col<CW>(64 * kc + 16 * k), dW + (uint64_t)(2 * k), ID128, 1u);
+                        ringA_done();
+                    }
+                }
+                if (leader) tc_commit(BAR(PB_ACC_A + g));
+                TL(1000 * g + 510 + step);
+            }
+        }
+    } else if (warp == 17) {
+        // ================================================================= MMA issuer of the feed-forward halves (warp converged)
+        const bool leader = elect_one();
+        const bool no_dense = (args.ablate & ABL_NO_DENSE_MMA) != 0;
+        constexpr uint32_t ID128 = idesc_bf16(128, 128), ID64 = idesc_bf16(128, 64);
+        const uint64_t CH = CHUNK >> 4;
+        uint32_t stF = 0, parF = 0;
+        uint32_t rdy_bits = 0;                                        // parity per side of RDY_F
         auto ringF = [&]() -> uint64_t {
             mbar_wait(BAR(PB_WF_FULL + stF), parF, 3);
             tc_fence_after();
             return sw128_desc(sbase + P_WF + stF * CHUNK);
         };
         auto ringF_done = [&]() { if (leader) tc_commit(BAR(PB_WF_EMPTY + stF)); if (++stF == 2) { stF = 0; parF ^= 1; } };
-        // one attention-half step of side g: step -1 = patch embedding, 0 K, 1 V^T, 2 Q, 3 scores, 4 P V, 5 out-projection
-        auto issue_a = [&](int g, int step) {
-            const uint32_t R = tmem + 128u * (uint32_t)g, AS = tmem + TP_AS;
-            const uint64_t dH = sw128_desc(sbase + P_H0 + g * 32768);
-            if (step == -1) {
-                const uint64_t dW = ringA();
-                for (int k = 0; k < 3; ++k)
-                    if (leader) umma(R, dH + (uint64_t)(2 * k), dW + (uint64_t)(2 * k), ID128, 1u);
-                ringA_done();
-            } else if (step <= 2) {
-                for (int c = 0; c < 2; ++c) {
-                    const uint64_t dW = ringA();
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t wa = dW + (uint64_t)(2 * k), oa = dH + (uint64_t)c * CH + (uint64_t)(2 * k);
-                        if (leader) umma(AS, step == 1 ? wa : oa, step == 1 ? oa : wa, ID128, (c > 0 || k > 0) ? 1u : 0u);
-                    }
-                    ringA_done();
-                }
-            } else if (step == 3) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-#pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        const uint64_t off = (uint64_t)(h >> 2) * CH + (uint64_t)((h & 3) * 2);
-                        if (leader) umma_ts_rows16(AS + 16 * h, AS + 128 + 8 * h, dK + off + (uint64_t)(j * 128), ID16, j);
-                    }
-                }
-            } else if (step == 4) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint64_t koff = (uint64_t)(j >> 2) * CH + (uint64_t)((j & 3) * 2);
-#pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        const uint32_t ocol = (h < 2) ? 32 + 16 * h : (h < 4) ? 96 + 16 * (h - 2) : 128 + 16 * (h - 4);
-                        if (leader) umma_ts_rows16(AS + ocol, AS + tm_bf16_col<CW>(16 * h), dVT + koff + (uint64_t)(h * 128), ID16, j);
-                    }
-                }
-            } else {
-                for (int kc = 0; kc < 2; ++kc) {
-                    const uint64_t dW = ringA();
-                    for (int k = 0; k < 4; ++k)
-                        if (leader) umma_ts(R, AS + tm_bf16_col<CW>(64 * kc + 16 * k), dW + (uint64_t)(2 * k), ID128, 1u);
-                    ringA_done();
-                }
-            }
-            if (leader) tc_commit(BAR(PB_ACC + g));
-        };
-        // one feed-forward-half step of side g: step 0 = FFN1 chunk 0; 1..7 = FFN2 k-chunk (step-1) then FFN1 chunk step; 8 = FFN2 k-chunk 7
-        auto issue_f = [&](int g, int step) {
-            const uint32_t R = tmem + 128u * (uint32_t)g, FS = tmem + TP_FS;
-            const uint64_t dH = sw128_desc(sbase + P_H0 + g * 32768);
-            if (step >= 1) {
-                const uint64_t dW = ringF();
-                for (int k = 0; k < 4; ++k)
-                    if (leader) umma_ts(R, FS + tm_bf16_col<32>(16 * k), dW + (uint64_t)(2 * k), ID128, 1u);
-                ringF_done();
-            }
-            if (step <= 7) {
-                const uint64_t dW = ringF();
-                for (int kh = 0; kh < 2; ++kh)
-                    for (int k = 0; k < 4; ++k)
-                        if (leader) umma(FS, dH + (uint64_t)kh * CH + (uint64_t)(2 * k), dW + (uint64_t)kh * (8192 >> 4) + (uint64_t)(2 * k), ID64,
-                                         (kh > 0 || k > 0) ? 1u : 0u);
-                ringF_done();
-            }
-            if (leader) tc_commit(BAR(PB_ACC + g));
-        };
         for (int s = 0; s < n_slots; ++s) {
             const Slot sl = slot_info(s, m, n_layers);
-            int ia = sl.a_valid ? (sl.a_layer == 0 ? -1 : 0) : 6;        // next attention-half step (6 = done)
-            int jf = sl.f_valid ? 0 : 9;                                  // next feed-forward-half step (9 = done)
-            unsigned spins = 0;
-            while (ia < 6 || jf < 9) {
-                bool progressed = false;
-                if (ia < 6) {
-                    uint32_t ok = mbar_test(BAR(PB_RDY + sl.a_side), (rdy_bits >> sl.a_side) & 1u) ? 1u : 0u;
-                    ok = __shfl_sync(0xffffffffu, ok, 0);
-                    if (ok) {
-                        rdy_bits ^= (1u << sl.a_side);
-                        tc_fence_after();
-                        issue_a(sl.a_side, ia);
-                        ++ia; progressed = true;
-                    }
+            if (!sl.f_valid) continue;
+            const int g = sl.f_side;
+            const uint32_t R = tmem + 128u * (uint32_t)g, FS = tmem + TP_FS;
+            const uint64_t dH = sw128_desc(sbase + P_H0 + g * 32768);
+            // steps: 0 = FFN1 chunk 0; 1..7 = FFN2 k-chunk (step-1) then FFN1 chunk step; 8 = FFN2 k-chunk 7
+            for (int step = 0; step < 9; ++step) {
+                mbar_wait(BAR(PB_RDY_F + g), (rdy_bits >> g) & 1u, 5);
+                rdy_bits ^= (1u << g);
+                tc_fence_after();
+                TL(1000 * g + 100 + step);
+                if (step >= 1) {
+                    const uint64_t dW = ringF();
+                    for (int k = 0; k < 4; ++k)
+                        if (leader && !no_dense) umma_ts(R, FS + tm_bf16_col<32>(16 * k), dW + (uint64_t)(2 * k), ID128, 1u);
+                    ringF_done();
                 }
-                if (jf < 9) {
-                    uint32_t ok = mbar_test(BAR(PB_RDY + sl.f_side), (rdy_bits >> sl.f_side) & 1u) ? 1u : 0u;
-                    ok = __shfl_sync(0xffffffffu, ok, 0);
-                    if (ok) {
-                        rdy_bits ^= (1u << sl.f_side);
-                        tc_fence_after();
-                        issue_f(sl.f_side, jf);
-                        ++jf; progressed = true;
-                    }
+                if (step <= 7) {
+                    const uint64_t dW = ringF();
+                    for (int kh = 0; kh < 2; ++kh)
+                        for (int k = 0; k < 4; ++k)
+                            if (leader && !no_dense) umma(FS, dH + (uint64_t)kh * CH + (uint64_t)(2 * k), dW + (uint64_t)kh * (8192 >> 4) + (uint64_t)(2 * k), ID64,
+                                                          (kh > 0 || k > 0) ? 1u : 0u);
+                    ringF_done();
                 }
-                if (progressed) spins = 0;
-                else if (++spins > (1u << 26)) {
-                    if (lane == 0) printf("cmhar pair kernel: MMA warp stuck (block %d slot %d/%d, a-step %d side %d, f-step %d side %d)\n",
-                                          (int)blockIdx.x, s, n_slots, ia, sl.a_side, jf, sl.f_side);
-                    __trap();
-                }
+                if (leader) tc_commit(BAR(PB_ACC_F + g));
+                TL(1000 * g + 600 + step);
             }
         }
     } else {
@@ -333,21 +340,27 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
         auto piece_of = [](int c) { return (c & 63) >> 3; };
         auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
         uint32_t acc_par = 0;
+        const bool no_epi = (args.ablate & 64) != 0;          // timing ablation (development): hand-shakes only, no epilogue work
         uint32_t v[32];
         float f[32];
-        auto wait_acc = [&](int site) { mbar_wait(BAR(PB_ACC + g), acc_par, site); acc_par ^= 1; tc_fence_after(); };
-        auto publish = [&]() {            // generic-proxy smem writes + TMEM accesses visible to the MMA thread, then one arrival per warp
+        uint32_t accf_par = 0;
+        auto wait_acc = [&](int site) { TL(site); mbar_wait(BAR(PB_ACC_A + g), acc_par, site); acc_par ^= 1; tc_fence_after(); TL(100 + site); };
+        auto wait_acc_f = [&](int site) { TL(site); mbar_wait(BAR(PB_ACC_F + g), accf_par, site); accf_par ^= 1; tc_fence_after(); TL(100 + site); };
+        // `to_f`: the step this pass unblocks is issued by the feed-forward-half MMA warp (else the attention-half one)
+        auto publish = [&](bool to_f = false) {   // generic-proxy smem writes + TMEM accesses visible to the MMA thread, then one arrival per warp
             tc_wait_st();
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(PB_RDY + g));
+            if (lane == 0) mbar_arrive(BAR((to_f ? PB_RDY_F : PB_RDY_A) + g));
+            TL(200);
         };
-        auto publish_tmem = [&]() {
+        auto publish_tmem = [&](bool to_f = false) {
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(PB_RDY + g));
+            if (lane == 0) mbar_arrive(BAR((to_f ? PB_RDY_F : PB_RDY_A) + g));
+            TL(201);
         };
         // y (32 finished fp32 columns c0+cc..) -> h (bf16, A/B operand) and y + next_bias -> R
         auto write_h = [&](const float* y32, int cc, const float* next_bias) {
@@ -473,6 +486,7 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
             publish();
             // ---- h0 = R ; h = bf16(h0) ; R = h0 + b_o(layer 0)
             wait_acc(11);
+            if (!no_epi) {
 #pragma unroll
             for (int cc = 0; cc < CW; cc += 32) {
                 TMEM_LD32(tR + c0 + cc, v);
@@ -480,6 +494,7 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                 write_h(f, cc, SB + 256);
+            }
             }
             if (args.dbg_stage == 0) { tc_wait_st(); dump_R(tile); }
             publish();
@@ -493,6 +508,7 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
                 for (int mm = 0; mm < 2; ++mm) {
                     wait_acc(12);
                     uint8_t* dst = smem + (mm == 0 ? P_K : P_VT);
+                    if (!no_epi)
 #pragma unroll
                     for (int cc = 0; cc < CW; cc += 32) {
                         TMEM_LD32(tAS + c0 + cc, v);
@@ -507,6 +523,7 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
                 wait_acc(13);
                 mbar_wait(BAR(PB_PBFULL + pbi), (pb_bits >> (l & 1)) & 1u, 21);
                 pb_bits ^= (1u << (l & 1));
+                if (!no_epi)
 #pragma unroll
                 for (int cc = 0; cc < CW; cc += 32) {
                     TMEM_LD32(tAS + c0 + cc, v);
@@ -546,11 +563,13 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
                         store_tmem_bf16(tAS + c0 + (cc >> 1), f);         // P over the scores it came from
                     }
                 };
-                if (S == CMHAR_MAX_SEQ) softmax_rows(std::true_type{});
+                if (no_epi) {}
+                else if (S == CMHAR_MAX_SEQ) softmax_rows(std::true_type{});
                 else softmax_rows(std::false_type{});
                 publish_tmem();
                 // ---- O accumulators (scattered over the free columns of AS) -> bf16 pairs over P (A operand of the out-projection)
                 wait_acc(15);
+                if (!no_epi)
 #pragma unroll
                 for (int cc = 0; cc < CW; cc += 32) {
                     const uint32_t src = wq ? (uint32_t)(128 + cc) : (uint32_t)(32 + 2 * cc);      // heads 0,1 | 2,3 | 4..7
@@ -563,13 +582,14 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
                 publish_tmem();
                 // ---- LN1: h1 = LN(R) ; h = bf16(h1) ; R = h1 + b_2
                 wait_acc(16);
-                layer_norm_R(PB + PB_LN1, PB + PB_B2, nullptr);
+                if (!no_epi) layer_norm_R(PB + PB_LN1, PB + PB_B2, nullptr);
                 if (args.dbg_stage == 1 && l == 0) { tc_wait_st(); dump_R(tile); }
-                publish();
+                publish(true);
                 // ---- 8 FFN1 chunks of 64 hidden units: relu(acc + b_1) -> bf16 pairs over the accumulator (A operand of FFN2)
 #pragma unroll 1
                 for (int j = 0; j < 8; ++j) {
-                    wait_acc(17);
+                    wait_acc_f(17);
+                    if (!no_epi) {
                     TMEM_LD32(tFS + 32 * wq, v);
                     tc_wait_ld();
 #pragma unroll
@@ -584,12 +604,13 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
                         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16_relu(f[2 * i], f[2 * i + 1]);
                         TMEM_ST16(tFS + 32 * wq, pk);
                     }
-                    publish_tmem();
+                    }
+                    publish_tmem(true);
                 }
                 // ---- LN2: h2 = LN(R) ; h = bf16(h2) ; R = h2 + b_o(next layer)
-                wait_acc(18);
+                wait_acc_f(18);
                 if (!last) {
-                    layer_norm_R(PB + PB_LN2, PB + PB_BON, nullptr);
+                    if (!no_epi) layer_norm_R(PB + PB_LN2, PB + PB_BON, nullptr);
                     if (args.dbg_stage == 2 && l == 0) { tc_wait_st(); dump_R(tile); }
                     publish();
                     __syncwarp();
@@ -647,6 +668,7 @@ __global__ void __maxnreg__(96) imu_forward_bf16_pair_kernel(const Bf16Args args
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
     if (tid == 0) trace_end(TRACE_ENCODER, trace_t0);
+#undef TL
 }
 
 // ================================================================================ weight packing (pair order)

@@ -9,6 +9,8 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 nohead = len(sys.argv) > 4 and sys.argv[4] == "nohead"      # encoder only (CLS out), no classifier head / scores
+if os.environ.get("ENC_KERNEL"):            # 1 = single-tile kernel, 2 = two-tiles-in-flight kernel (development switch of the library)
+    cm._native.check(cm._native.lib().cmhar_debug_set_option(b"enc_kernel", int(os.environ["ENC_KERNEL"])))
 torch.manual_seed(0)
 cfg = cm.default_config()
 clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg).to("cuda").eval()
