@@ -120,6 +120,7 @@ _SIGNATURES = {
     "cmhar_conv_encoder_blob_bytes": (C.c_size_t, []),
     "cmhar_conv_encoder_pack": (C.c_int, [C.POINTER(ConvEncoderParams), C.c_void_p, C.c_void_p]),
     "cmhar_conv_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cmhar_conv_encoder_forward_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "cmhar_video_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]),
     "cmhar_video_pool_coresident": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from . import _native as N
 from .fusion import _head, head_scores_native
-from .models import _PackedMixin, _native_mode, pack_head_blob
+from .models import _PackedMixin, _native_mode, _prec_code, pack_head_blob
 
 __all__ = ["ConvIMUEncoder", "ConvIMUClassifier"]
 
@@ -65,7 +65,8 @@ class ConvIMUEncoder(_PackedMixin, nn.Module):
             self._packed[key] = blob
         return self._packed[key]
 
-    def forward_native(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_native(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, precision: Optional[str] = None) -> torch.Tensor:
+        """precision 'bf16' = the tensor-core implicit-GEMM kernel, 'fp32' = the CUDA-core kernel (default: the package default)."""
         N.require_cuda(x, "ConvIMUEncoder")
         x = N.f32c(x)
         B, Cc, L = x.shape
@@ -73,8 +74,8 @@ class ConvIMUEncoder(_PackedMixin, nn.Module):
             raise ValueError("expected (B, 6, L) windows")
         feat = out if out is not None else torch.empty((B, self.out_dim), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            N.check(N.lib().cmhar_conv_encoder_forward(self.packed_blob(x.device).data_ptr(), x.data_ptr(), B, L, Cc * L,
-                                                       feat.data_ptr(), N.stream_ptr(x.device)))
+            N.check(N.lib().cmhar_conv_encoder_forward_ex(self.packed_blob(x.device).data_ptr(), x.data_ptr(), B, L, Cc * L,
+                                                          feat.data_ptr(), _prec_code(precision), N.stream_ptr(x.device)))
         return feat
 
     def forward(self, x):
@@ -109,7 +110,7 @@ class ConvIMUClassifier(_PackedMixin, nn.Module):
                        ) -> Dict[str, torch.Tensor]:
         if self.training:
             raise RuntimeError("forward_scores is an inference entry point: call .eval() first")
-        feat = self.encoder.forward_native(imu)
+        feat = self.encoder.forward_native(imu, precision=precision)
         maha_blob = self._maha_state.blob(feat.device) if self._maha_state is not None else None
         res = head_scores_native(self._head_blob(feat.device), maha_blob, feat, self.num_classes, out, precision)
         res["cls"] = feat

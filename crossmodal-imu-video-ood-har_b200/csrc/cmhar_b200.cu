@@ -16,6 +16,7 @@ namespace cmhar { struct FwdArgs; }
 #include "similarity_tc.cu"
 #include "fusion.cu"
 #include "conv_encoder.cu"
+#include "conv_encoder_tc.cu"
 #include "maha_score_tc.cu"
 #include "ood.cu"
 #include "maha_fit_tc.cu"

@@ -18,6 +18,9 @@
 #include "common.cuh"
 
 namespace cmhar {
+size_t conv_tc_image_bytes();                                                                     // conv_encoder_tc.cu
+int pack_conv_tc(const cmhar_conv_encoder_params* p, void* img, cudaStream_t st);
+int launch_conv_encoder_tc(const void* img, const float* x, long long n, int L, long long xstride, float* feat, cudaStream_t st);
 namespace convenc {
 
 constexpr int NT = 128;
@@ -149,7 +152,7 @@ using namespace cmhar;
 
 extern "C" {
 
-size_t cmhar_conv_encoder_blob_bytes(void) { return sizeof(BlobHeader) + convenc::Layout::total * sizeof(float); }
+size_t cmhar_conv_encoder_blob_bytes(void) { return tc_section_offset(convenc::Layout::total) + conv_tc_image_bytes(); }
 
 int cmhar_conv_encoder_pack(const cmhar_conv_encoder_params* p, void* blob, cmhar_stream_t s) {
     using namespace convenc;
@@ -167,8 +170,14 @@ int cmhar_conv_encoder_pack(const cmhar_conv_encoder_params* p, void* blob, cmha
                                                             f + wo[l], f + bo[l]);
         CMHAR_LAUNCH_CHECK();
     }
+    // tensor-core section (bf16 path): weight images with the BatchNorm scale folded in, at the next 1 KiB boundary
+    {
+        const int rc = pack_conv_tc(p, reinterpret_cast<char*>(blob) + tc_section_offset(Layout::total), st);
+        if (rc != CMHAR_OK) return rc;
+    }
     BlobHeader h{};
     h.magic = CONV_MAGIC;
+    h.has_bf16 = 1;
     write_header_kernel<<<1, 1, 0, st>>>(reinterpret_cast<BlobHeader*>(blob), h);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
@@ -176,11 +185,20 @@ int cmhar_conv_encoder_pack(const cmhar_conv_encoder_params* p, void* blob, cmha
 
 int cmhar_conv_encoder_forward(const void* blob, const float* x, int64_t n, int32_t window, int64_t x_window_stride, float* feat_out,
                                cmhar_stream_t s) {
+    return cmhar_conv_encoder_forward_ex(blob, x, n, window, x_window_stride, feat_out, CMHAR_FP32, s);
+}
+
+int cmhar_conv_encoder_forward_ex(const void* blob, const float* x, int64_t n, int32_t window, int64_t x_window_stride, float* feat_out,
+                                  int32_t precision, cmhar_stream_t s) {
     using namespace convenc;
+    if (n <= 0) return CMHAR_OK;
     CMHAR_REQUIRE(blob && x && feat_out, "cmhar_conv_encoder_forward: null argument");
     CMHAR_REQUIRE(window >= 16 && window <= MAX_L, "window length %d outside [16, %d]", window, MAX_L);
     CMHAR_REQUIRE(x_window_stride >= (int64_t)C0 * window, "x_window_stride %lld shorter than 6 x window", (long long)x_window_stride);
-    if (n <= 0) return CMHAR_OK;
+    CMHAR_REQUIRE(precision == CMHAR_FP32 || precision == CMHAR_BF16, "bad precision %d", precision);
+    if (precision == CMHAR_BF16)        // implicit-GEMM tcgen05 kernel (conv_encoder_tc.cu)
+        return launch_conv_encoder_tc(reinterpret_cast<const char*>(blob) + tc_section_offset(Layout::total), x, n, window, x_window_stride,
+                                      feat_out, (cudaStream_t)s);
     const size_t smem = smem_bytes(window);
     static bool configured[64] = {};
     int dev = 0;

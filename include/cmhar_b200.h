@@ -268,6 +268,11 @@ int    cmhar_conv_encoder_pack(const cmhar_conv_encoder_params* p, void* blob, c
 /* x: window w at x + w*x_window_stride, (6, window) row-major; feat_out (n,128) */
 int    cmhar_conv_encoder_forward(const void* blob, const float* x, int64_t n, int32_t window,
                                   int64_t x_window_stride, float* feat_out, cmhar_stream_t s);
+/* Same with an explicit precision: CMHAR_FP32 = the CUDA-core kernel above (fp32 FMA); CMHAR_BF16 = the tensor-core kernel
+ * (conv_encoder_tc.cu): every layer an implicit GEMM (tcgen05.mma, bf16 operands, fp32 accumulation in TMEM) over im2col tiles
+ * that exist only in shared memory, BatchNorm scale folded into the weight images, split-precision (hi + lo) input samples. */
+int    cmhar_conv_encoder_forward_ex(const void* blob, const float* x, int64_t n, int32_t window,
+                                     int64_t x_window_stride, float* feat_out, int32_t precision, cmhar_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Video tail (replaces VideoEncoder.forward after the trunk, models.py:210-216:

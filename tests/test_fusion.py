@@ -124,5 +124,32 @@ def test_native_conv_encoder_matches_spec(L, B):
     assert rel(out["cls"], want_f) < 1e-5
     assert rel(out["logits"], want) < 1e-4
     assert np.array_equal(out["pred"].cpu().numpy(), oracle.predict(want))
-    out16 = model.forward_scores(torch.from_numpy(x).cuda(), precision="bf16")      # tensor-core head, same encoder
-    assert rel(out16["logits"], want) < 1e-4
+    out16 = model.forward_scores(torch.from_numpy(x).cuda(), precision="bf16")      # tensor-core conv stack + tensor-core head
+    assert rel(out16["cls"], want_f) < 2e-2 and rel(out16["logits"], want) < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,B", [(250, 1), (250, 2), (250, 77), (100, 33), (16, 5), (254, 40), (255, 9), (256, 300), (250, 2 * 148 * 3 + 5)])
+def test_tensor_core_conv_encoder_matches_spec(L, B):
+    """conv_encoder_tc_kernel (implicit GEMMs over shared-memory im2col tiles, bf16 operands, split-precision input) against
+    the float64 spec within the bf16 contract (2e-2; measured a few 1e-3) for every window length class -- one and two tiles of
+    positions, the 255 / 256-sample right-padding corner, odd window counts (an empty second slot), several pairs per CTA --
+    and against the fp32 CUDA-core kernel; a window's result does not depend on its slot or batch neighbours."""
+    model, sd = build_conv()
+    model = model.to("cuda:0")
+    x = W.imu_windows(7, B, W.Dims(imu_window=L))
+    xd = torch.from_numpy(x).cuda()
+    _, want_f = fusion_spec.conv_classifier(x, sd, dtype=torch.float64)
+    got = model.encoder.forward_native(xd, precision="bf16")
+    ref32 = model.encoder.forward_native(xd, precision="fp32")
+    torch.cuda.synchronize()
+    w = want_f.numpy()
+    err = float(np.abs(got.cpu().numpy().astype(np.float64) - w).max() / np.abs(w).max())
+    print(f"L={L} B={B}: tensor-core conv encoder rel err {err:.2e}")
+    assert torch.isfinite(got).all() and err < 2e-2
+    assert float((got - ref32).abs().max() / ref32.abs().max()) < 2e-2
+    again = model.encoder.forward_native(xd, precision="bf16")
+    assert torch.equal(got, again)
+    if B >= 5:
+        part = model.encoder.forward_native(xd[3:5].contiguous(), precision="bf16")
+        assert torch.equal(part, got[3:5])
