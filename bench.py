@@ -292,10 +292,10 @@ def workload_sharded_similarity(cm, cfg, clf, xm, dev, rank, world, barrier, dis
         o = keep[i % n_sets]
         out = imu_forward_native(clf.imu_encoder, None, None, imu, want_cls=True, want_tokens=True, precision=precision,
                                  want_cls_img=True, out=o.setdefault("enc", {}))
-        frame_feats = ve.forward_frame_features(fmap, precision=precision)
-        fused = xfus.fuse_native(out["tokens"], frame_feats.view(rows, FRAMES, -1), precision)
+        # ONE pass over the feature maps: clip means (contrastive branch) + per-frame means (cross-attention frame tokens)
+        pimg, frame_img = ve.pool_features_frames(fmap, FRAMES)
+        fused = xfus.fuse_native_img(out["tokens"], frame_img, FRAMES)      # projection folded into the kv GEMM
         xfus._scores(fused, o.setdefault("sc", {}), precision)
-        _, pimg = ve.pool_features(fmap, FRAMES, want_img=True, want_rows=False)
         _, vimg = ve._packed_projection(dev).forward_img(rows, False, x_img=pimg, want_rows=False, want_img=True)
         r1 = xm.video_proj.forward_fused(vimg, rows, want_rows=False, img_out=sim.video_image_ptr)
         r2 = xm.imu_proj.forward_fused(out["cls_img"], rows, want_rows=False)
@@ -762,6 +762,34 @@ def main():
                              "launch_ms": ms, "bytes_per_launch": nbytes, "traffic": tr, "traffic_source": tr_src}
         del logits, feat
 
+    # ---- the conv / BN / ReLU IMU encoder (north-star item 1; spec-defined): CUDA-core fp32 kernel vs tensor-core implicit GEMMs
+    conv_sweep = {}
+    if rank == 0 and not args.no_sweep:
+        FLOP_CONV = 2 * (250 * 32 * 30 + 125 * 64 * 160 + 63 * 128 * 320)
+        torch.manual_seed(3)
+        cenc = cm.ConvIMUEncoder(cfg).to(dev).eval()
+        for nb in (256, 65536):
+            xs = [torch.randn(nb, 6, WINDOW, device=dev) for _ in range(max(2, min(8, 400_000_000 // (nb * 6000))))]
+            co = torch.empty(nb, 128, device=dev)
+            entry = {}
+            for prec, kname in (("fp32", "conv_encoder_kernel (CUDA cores, fp32 FMA)"), ("bf16", "conv_encoder_tc_kernel (tcgen05 implicit GEMMs)")):
+                for i in range(3):
+                    cenc.forward_native(xs[i % len(xs)], out=co, precision=prec)
+                torch.cuda.synchronize(dev)
+                reps = max(3, min(100, (4_000_000 if prec == "bf16" else 200_000) // nb))
+                e0.record(stream)
+                for i in range(reps):
+                    cenc.forward_native(xs[i % len(xs)], out=co, precision=prec)
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / reps
+                tfl = FLOP_CONV * nb / (ms * 1e-3) / 1e12
+                entry[prec] = {"kernel": kname, "windows_per_s": nb / (ms * 1e-3), "tflops": tfl, "launch_ms": ms,
+                               "frac_of_bf16_peak": tfl / peaks["bf16_tflops_sustained"] if prec == "bf16" else None,
+                               "hbm_gbs": nb * 6512 / (ms * 1e-3) / 1e9}
+            conv_sweep[str(nb)] = entry
+            del xs
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         wps, cores, iters = cpu_workload(clf, xm, fus, B, budget_s=12.0)
@@ -804,7 +832,7 @@ def main():
                 "workloads": workloads,
                 "roofline": roofline, "roofline_overlapped_launches": roofline_lanes, "roofline_saturated_batch": roofline_sat, "roofline_video_tail": roofline_video,
                 "roofline_scoring": scoring,
-                "cpu_baseline": cpu_baseline, "imu_batch_sweep": sweep}
+                "cpu_baseline": cpu_baseline, "imu_batch_sweep": sweep, "conv_encoder_sweep": conv_sweep}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

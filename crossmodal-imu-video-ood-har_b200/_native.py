@@ -95,6 +95,8 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "cmhar_video_pool_img": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cmhar_video_pool_frames_img": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmhar_operand_image_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "cmhar_linear_forward_img": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),

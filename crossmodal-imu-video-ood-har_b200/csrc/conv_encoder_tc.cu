@@ -41,7 +41,7 @@ constexpr int SLOT_BYTES = SLOT_TILE + (SLOT_X + 1023) / 1024 * 1024;
 constexpr int S_BAR = S_SLOT + 2 * SLOT_BYTES;
 constexpr int SMEM_BYTES = S_BAR + 64;
 static_assert(SMEM_BYTES <= 232448, "conv tensor-core kernel exceeds the shared memory of a CTA");
-enum { B_W = 0, B_RDY = 1 /*[2]*/, B_ACC = 3 /*[2]*/ };
+enum { B_W = 0, B_RDY = 1 /*[2]*/, B_ACC = 3 /*[2]*/, B_X = 5 /*[2]: the slot's next window has landed in shared memory*/ };
 constexpr int NT = 288;                                  // 8 builder / epilogue warps + 1 MMA warp
 // TMEM columns per slot: D1 tile 0 [0,32) tile 1 [32,64) | D2 [64,128) | D3 [128,192)
 constexpr uint32_t T_SLOT = 192, T_D1 = 0, T_D2 = 64, T_D3 = 128;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(NT, 1) conv_encoder_tc_kernel(const uint8_t* _
 
     if (tid == 0) {
         mbar_init(BAR(B_W), 1);
-        for (int g = 0; g < 2; ++g) { mbar_init(BAR(B_RDY + g), 4); mbar_init(BAR(B_ACC + g), 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(BAR(B_RDY + g), 4); mbar_init(BAR(B_ACC + g), 1); mbar_init(BAR(B_X + g), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(BAR(B_W), IMG_BYTES);
         bulk_g2s(sbase + S_W, img, IMG_BYTES, BAR(B_W));
@@ -115,11 +115,11 @@ __global__ void __launch_bounds__(NT, 1) conv_encoder_tc_kernel(const uint8_t* _
         const int g = warp >> 2, r = (warp & 3) * 32 + lane;            // slot, row of the 128-row tiles (== TMEM lane)
         const int gt = tid & 127;                                       // thread index inside the slot's group
         uint8_t* const tile = smem + S_SLOT + g * SLOT_BYTES;
-        float* const xs = reinterpret_cast<float*>(tile + SLOT_TILE);   // [6][L + 4], zero halo
+        float* const xs = reinterpret_cast<float*>(tile + SLOT_TILE);   // [6][L]: the staged window
         const float* bias = reinterpret_cast<const float*>(smem + S_W + WT_BYTES);
         const uint32_t T = tmem + ((uint32_t)((warp & 3) * 32) << 16) + T_SLOT * (uint32_t)g;
-        const int xp = L + 4;
-        uint32_t acc_par = 0;
+        const bool bulk_x = ((((uintptr_t)x) | ((uintptr_t)xstride * 4) | (uintptr_t)(C0 * L * 4)) & 15) == 0;
+        uint32_t acc_par = 0, x_par = 0;
         uint32_t v[32];
         float f[32];
         auto group_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
@@ -137,13 +137,20 @@ __global__ void __launch_bounds__(NT, 1) conv_encoder_tc_kernel(const uint8_t* _
         for (long long p = blockIdx.x; p < pairs; p += gridDim.x) {
             const long long w = 2 * p + g;
             if (w >= n) break;
-            // ---- stage the window (6 x L fp32, contiguous) with zero halos
+            // ---- the window (6 x L fp32, contiguous): bulk-copied into shared memory one window ahead (issued right after the
+            // previous window's im2col build, so the copy runs under that window's three layers); plain loads when misaligned
             const float* src = x + w * xstride;
-            for (int e = gt; e < C0 * xp; e += 128) {
-                const int ci = e / xp, q = e - ci * xp - 2;
-                xs[e] = (q >= 0 && q < L) ? __ldg(src + ci * L + q) : 0.f;
+            if (bulk_x) {
+                if (p == (long long)blockIdx.x && gt == 0) {          // first window of the slot: nothing was prefetched
+                    mbar_expect_tx(BAR(B_X + g), (uint32_t)(C0 * L * 4));
+                    bulk_g2s(smem_u32(xs), src, (uint32_t)(C0 * L * 4), BAR(B_X + g));
+                }
+                mbar_wait(BAR(B_X + g), x_par, 9);
+                x_par ^= 1;
+            } else {
+                for (int e = gt; e < C0 * L; e += 128) xs[e] = __ldg(src + e);
+                group_sync();
             }
-            group_sync();
             // ---- A1: two tiles of 128 positions; row = [hi(x) 30 taps, 0, 0 | lo(x) 30 taps, 0, 0]
 #pragma unroll 1
             for (int j = 0; j < 2; ++j) {
@@ -153,16 +160,28 @@ __global__ void __launch_bounds__(NT, 1) conv_encoder_tc_kernel(const uint8_t* _
                 for (int c = 0; c < 32; ++c) { hi[c] = 0.f; lo[c] = 0.f; }
                 if (pos < L) {
 #pragma unroll
-                    for (int k = 0; k < KW; ++k)
+                    for (int k = 0; k < KW; ++k) {
+                        const int q = pos + k - 2;
+                        const bool in = (q >= 0 && q < L);
 #pragma unroll
                         for (int ci = 0; ci < C0; ++ci) {
-                            const float xv = xs[ci * xp + pos + k];
+                            const float xv = in ? xs[ci * L + q] : 0.f;
                             const float h = __bfloat162float(__float2bfloat16_rn(xv));
                             hi[k * C0 + ci] = h; lo[k * C0 + ci] = xv - h;
                         }
+                    }
                 }
                 store_bf16_32(tile + j * 16384, r, 0, hi);
                 store_bf16_32(tile + j * 16384, r, 4, lo);
+            }
+            group_sync();                 // every thread of the slot has read its samples: the staging buffer is free
+            if (bulk_x && gt == 0) {
+                const long long wn = 2 * (p + gridDim.x) + g;
+                if (wn < n) {
+                    fence_async_smem();   // generic-proxy reads of xs are ordered before the async-proxy write that reuses it
+                    mbar_expect_tx(BAR(B_X + g), (uint32_t)(C0 * L * 4));
+                    bulk_g2s(smem_u32(xs), x + wn * xstride, (uint32_t)(C0 * L * 4), BAR(B_X + g));
+                }
             }
             publish();
             // ---- L1 epilogue: relu(D1 + b1) (zero beyond the window) -> A2, tap-major 32-channel groups

@@ -146,7 +146,10 @@ constexpr int POOL_NT = 128;
 constexpr int POOL_UNROLL = 4;                // frames per explicit load batch (x up to two 16-byte loads each)
 template <typename T, int VEC /* elements per 16-byte vector, 0 = scalar path */, int U = POOL_UNROLL /* frames per load batch */>
 __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict__ fmap, long long n, int frames,
-                                                         int channels, int hw, float* __restrict__ pooled, int batched, uint8_t* __restrict__ img) {
+                                                         int channels, int hw, float* __restrict__ pooled, int batched, uint8_t* __restrict__ img,
+                                                         uint8_t* __restrict__ fimg = nullptr) {
+    // fimg (optional): the per-FRAME spatial means as a bf16 operand image of n * frames rows x channels (row = b * frames + t) --
+    // the cross-attention block's frame tokens, from the same single pass over the feature maps as the clip mean
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= channels) return;
     const unsigned long long trace_t0 = (threadIdx.x == 0) ? trace_begin() : 0ull;
@@ -165,15 +168,22 @@ __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict
                          : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(q), "l"(stream_policy));
             return u;
         };
-        auto add16 = [&](const uint4& u) {
+        auto sum16 = [&](const uint4& u) -> float {
             if (sizeof(T) == 2) {
                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+                float sacc = 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h2[q]); acc += f.x + f.y; }
+                for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h2[q]); sacc += f.x + f.y; }
+                return sacc;
             } else {
                 const float* f = reinterpret_cast<const float*>(&u);
-                acc += (f[0] + f[1]) + (f[2] + f[3]);
+                return (f[0] + f[1]) + (f[2] + f[3]);
             }
+        };
+        auto put_frame = [&](int t, float fsum) {
+            const long long row = b * frames + t;
+            uint8_t* chunk = fimg + ((size_t)(row >> 7) * (channels >> 6) + (c >> 6)) * 16384;
+            *reinterpret_cast<__nv_bfloat16*>(chunk + tc::sw128_off((int)(row & 127), (c & 63) >> 3) + (c & 7) * 2) = __float2bfloat16_rn(fsum / (float)hw);
         };
         if (nv <= 2 && batched) {
             // explicit batches: the 8 loads of 4 frames are ALL issued before the first is consumed (the compiler otherwise
@@ -197,22 +207,36 @@ __global__ void __launch_bounds__(POOL_NT) video_pool_kernel(const T* __restrict
                 }
 #pragma unroll
                 for (int i = 0; i < U; ++i) {
+                    float fs = 0.f;
 #pragma unroll
-                    for (int v = 0; v < 2; ++v) add16(u[i][v]);
+                    for (int v = 0; v < 2; ++v) fs += sum16(u[i][v]);
+                    acc += fs;
+                    if (fimg && t0 + i < frames) put_frame(t0 + i, fs);
                 }
             }
         } else {
             for (int t = 0; t < frames; ++t) {
                 const uint4* p = reinterpret_cast<const uint4*>(base + t * fstride);
-                for (int v = 0; v < nv; ++v) add16(ld16(p + v));
+                float fs = 0.f;
+                for (int v = 0; v < nv; ++v) fs += sum16(ld16(p + v));
+                acc += fs;
+                if (fimg) put_frame(t, fs);
             }
         }
     } else {
-        for (int t = 0; t < frames; ++t)
+        for (int t = 0; t < frames; ++t) {
+            float fs = 0.f;
             for (int p = 0; p < hw; ++p) {
-                if (sizeof(T) == 2) acc += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base + t * fstride)[p]);
-                else acc += reinterpret_cast<const float*>(base + t * fstride)[p];
+                if (sizeof(T) == 2) fs += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base + t * fstride)[p]);
+                else fs += reinterpret_cast<const float*>(base + t * fstride)[p];
             }
+            acc += fs;
+            if (fimg) {
+                const long long row = b * frames + t;
+                uint8_t* chunk = fimg + ((size_t)(row >> 7) * (channels >> 6) + (c >> 6)) * 16384;
+                *reinterpret_cast<__nv_bfloat16*>(chunk + tc::sw128_off((int)(row & 127), (c & 63) >> 3) + (c & 7) * 2) = __float2bfloat16_rn(fs / (float)hw);
+            }
+        }
     }
     const float mean = acc / (float)(frames * hw);
     if (pooled) pooled[b * channels + c] = mean;
@@ -517,9 +541,10 @@ int cmhar_video_pool_coresident(const void* fmap, int32_t is_bf16, int64_t n, in
 }
 
 static int video_pool_impl(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
-                           float* pooled, uint8_t* img, cmhar_stream_t s) {
-    CMHAR_REQUIRE(fmap && (pooled || img) && frames > 0 && channels > 0 && hw > 0, "cmhar_video_pool: bad argument");
-    CMHAR_REQUIRE(!img || channels % 64 == 0, "cmhar_video_pool_img: an operand image needs channels %% 64 == 0 (got %d)", channels);
+                           float* pooled, uint8_t* img, cmhar_stream_t s, uint8_t* fimg = nullptr) {
+    if (n <= 0) return CMHAR_OK;
+    CMHAR_REQUIRE(fmap && (pooled || img || fimg) && frames > 0 && channels > 0 && hw > 0, "cmhar_video_pool: bad argument");
+    CMHAR_REQUIRE(!(img || fimg) || channels % 64 == 0, "cmhar_video_pool_img: an operand image needs channels %% 64 == 0 (got %d)", channels);
     if (n <= 0) return CMHAR_OK;
     cudaStream_t st = (cudaStream_t)s;
     // Default: the flooding kernel below (101 % of the measured copy bandwidth at 2 048 clips; 60 % at 256).  The
@@ -529,7 +554,7 @@ static int video_pool_impl(const void* fmap, int32_t is_bf16, int64_t n, int32_t
     // 29.9 us on one B200 box and 34.3 us on another, against a steady 32.5 us for the flooding kernel.
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("CMHAR_POOL_MODE"); mode = e ? atoi(e) : 1; }        // 1 = flood (default), 2 = ring
-    if (mode == 2 && !img && pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw))
+    if (mode == 2 && !img && !fimg && pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw))
         return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, st);
     static int batched = -1;
     if (batched < 0) { const char* e = getenv("CMHAR_POOL_BATCH"); batched = e ? atoi(e) : 1; }      // development switch
@@ -545,16 +570,16 @@ static int video_pool_impl(const void* fmap, int32_t is_bf16, int64_t n, int32_t
     if (is_bf16) {
         if (aligned && hw % 8 == 0)
         {
-            if (batched == 8) video_pool_kernel<__nv_bfloat16, 8, 8><<<grid, POOL_NT, pad_smem, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
-            else video_pool_kernel<__nv_bfloat16, 8><<<grid, POOL_NT, pad_smem, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
+            if (batched == 8) video_pool_kernel<__nv_bfloat16, 8, 8><<<grid, POOL_NT, pad_smem, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img, fimg);
+            else video_pool_kernel<__nv_bfloat16, 8><<<grid, POOL_NT, pad_smem, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img, fimg);
         }
         else
-            video_pool_kernel<__nv_bfloat16, 0><<<grid, POOL_NT, pad_smem, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img);
+            video_pool_kernel<__nv_bfloat16, 0><<<grid, POOL_NT, pad_smem, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, batched, img, fimg);
     } else {
         if (aligned && hw % 4 == 0)
-            video_pool_kernel<float, 4><<<grid, POOL_NT, pad_smem, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img);
+            video_pool_kernel<float, 4><<<grid, POOL_NT, pad_smem, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img, fimg);
         else
-            video_pool_kernel<float, 0><<<grid, POOL_NT, pad_smem, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img);
+            video_pool_kernel<float, 0><<<grid, POOL_NT, pad_smem, st>>>((const float*)fmap, n, frames, channels, hw, pooled, batched, img, fimg);
     }
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
@@ -569,6 +594,13 @@ int cmhar_video_pool(const void* fmap, int32_t is_bf16, int64_t n, int32_t frame
 int cmhar_video_pool_img(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
                          float* pooled, void* pooled_img, cmhar_stream_t s) {
     return video_pool_impl(fmap, is_bf16, n, frames, channels, hw, pooled, reinterpret_cast<uint8_t*>(pooled_img), s);
+}
+
+int cmhar_video_pool_frames_img(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
+                                float* pooled, void* pooled_img, void* frame_img, cmhar_stream_t s) {
+    CMHAR_REQUIRE(n <= 0 || frame_img, "cmhar_video_pool_frames_img: null frame image");
+    return video_pool_impl(fmap, is_bf16, n, frames, channels, hw, pooled, reinterpret_cast<uint8_t*>(pooled_img), s,
+                           reinterpret_cast<uint8_t*>(frame_img));
 }
 
 }  // extern "C"

@@ -215,6 +215,47 @@ class CrossAttentionFusionClassifier(_FusionBase):
             self._packed[key] = tuple(_PackedLinear(l, None, device) for l in (self.q_proj, self.kv_proj, self.out_proj))
         return self._packed[key]
 
+    def _packed_kv_folded(self, device) -> _PackedLinear:
+        """[k|v] = kv_proj(projection(pooled frame)) is two Linear layers with nothing in between (models.py:213 has no
+        activation), i.e. ONE Linear F -> 2d with W = W_kv W_p, b = W_kv b_p + b_kv (folded in fp64 at pack time): the
+        per-frame F -> video_d_model GEMM (2/3 of the block's flops) disappears."""
+        from .models import pack_generation
+        key = ("xattn_kv_folded", str(device))
+        # the fold reads the VIDEO encoder's projection weights: re-fold whenever any module re-packed (load_state_dict / train /
+        # to() on the encoder alone does not reach this module's cache)
+        if key not in self._packed or self._packed[key][0] != pack_generation():
+            proj = self.video_encoder.projection
+            wp, bp = proj.weight.detach().double(), proj.bias.detach().double()
+            wk, bk = self.kv_proj.weight.detach().double(), self.kv_proj.bias.detach().double()
+            lin = nn.Linear(proj.in_features, self.kv_proj.out_features)
+            lin.weight.data.copy_((wk @ wp).float())
+            lin.bias.data.copy_((wk @ bp + bk).float())
+            self._packed[key] = (pack_generation(), _PackedLinear(lin.to(device), None, device))
+        return self._packed[key][1]
+
+    def fuse_native_img(self, tokens: torch.Tensor, frame_img: torch.Tensor, frames: int) -> torch.Tensor:
+        """bf16 route from the per-frame pooled operand image (``VideoEncoder.pool_features_frames``): folded kv GEMM on
+        tensor cores straight from the image, then attention, out-projection, residual LayerNorm + token mean."""
+        if self.nhead != 8 or self.d_model != 128:
+            raise NotImplementedError("native cross-attention is specialised to 8 heads of 16")
+        B, S, d = tokens.shape
+        dev = tokens.device
+        ql, _, ol = self._packed_linears(dev)
+        kvl = self._packed_kv_folded(dev)
+        tok2 = N.f32c(tokens).reshape(B * S, d)
+        q = ql(tok2, relu=False, precision="bf16")
+        kv, _ = kvl.forward_img(B * frames, False, x_img=frame_img, want_rows=True, want_img=False)
+        attn = torch.empty((B * S, d), dtype=torch.float32, device=dev)
+        fused = torch.empty((B, d), dtype=torch.float32, device=dev)
+        lib = N.lib()
+        with torch.cuda.device(dev):
+            N.check(lib.cmhar_cross_attention(q.data_ptr(), kv.data_ptr(), B, S, frames, attn.data_ptr(), N.stream_ptr(dev)))
+            o = ol(attn, relu=False, precision="bf16")
+            g, b = N.f32c(self.norm.weight.detach()), N.f32c(self.norm.bias.detach())
+            N.check(lib.cmhar_residual_ln_pool(tok2.data_ptr(), o.data_ptr(), g.data_ptr(), b.data_ptr(), B, S,
+                                               float(self.norm.eps), fused.data_ptr(), N.stream_ptr(dev)))
+        return fused
+
     def fuse_native(self, tokens: torch.Tensor, frame_feats: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
         """tokens (B,S,128), frame_feats (B,T,video_d_model) -> fused (B,128)."""
         if self.nhead != 8 or self.d_model != 128:
@@ -242,8 +283,13 @@ class CrossAttentionFusionClassifier(_FusionBase):
                        out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         self._check()
         tokens = imu_forward_native(self.imu_encoder, None, None, imu, want_tokens=True, precision=precision)["tokens"]
-        frame_feats = self.video_encoder.forward_frame_features(fmap, precision=precision)
         B = tokens.shape[0]
+        ve = self.video_encoder
+        if _prec_code(precision) == N.BF16 and ve.feature_dim % 64 == 0 and B > 0 and not ve.is_videomae:
+            # bf16: one pooling pass emits the frame tokens as an operand image; projection folded into the kv GEMM
+            _, frame_img = ve.pool_features_frames(fmap, frames, want_clip_img=False)
+            return self._scores(self.fuse_native_img(tokens, frame_img, frames), out, precision)
+        frame_feats = ve.forward_frame_features(fmap, precision=precision)
         return self._scores(self.fuse_native(tokens, frame_feats.view(B, frames, -1), precision), out, precision)
 
     def _fuse_autograd(self, tokens, frame_feats):
@@ -260,9 +306,12 @@ class CrossAttentionFusionClassifier(_FusionBase):
         B, T = video.shape[0], video.shape[1]
         if _native_mode(self):
             N.require_cuda(imu, "CrossAttentionFusionClassifier")
-            tokens = imu_forward_native(self.imu_encoder, None, None, imu, want_tokens=True)["tokens"]
-            frame_feats = self.video_encoder.frame_features(video)
-            return self._scores(self.fuse_native(tokens, frame_feats), None)["logits"]
+            ve = self.video_encoder
+            if ve.is_videomae:
+                raise NotImplementedError("cross-attention fusion needs a per-frame (CNN) trunk")
+            # the trunk (third-party torch module) produces the feature maps; everything behind it is forward_scores
+            fmap = ve.backbone(video.reshape(B * T, *video.shape[2:]))
+            return self.forward_scores(imu, fmap, T)["logits"]
         _, tokens = self.imu_encoder(imu)
         frame_feats = self.video_encoder.frame_features(video)
         return self.classifier(self._fuse_autograd(tokens, frame_feats))

@@ -462,6 +462,26 @@ class VideoEncoder(_PackedMixin, nn.Module):
                        pooled.data_ptr(), N.stream_ptr(fmap.device)))
         return pooled
 
+    def pool_features_frames(self, fmap: torch.Tensor, frames: int, want_clip_img: bool = True):
+        """ONE pass over fmap (B*T, F, h, w) -> (clip-mean operand image (B, F) or None, per-frame operand image (B*T, F)):
+        the temporal-mean feature of the contrastive branch and the frame tokens of the cross-attention block from the same
+        read of the feature maps (``cmhar_video_pool_frames_img``; bf16 operand images, F % 64 == 0)."""
+        N.require_cuda(fmap, "VideoEncoder")
+        if fmap.dtype not in (torch.float32, torch.bfloat16):
+            fmap = fmap.float()
+        fmap = fmap.contiguous()
+        BT, Fd = fmap.shape[0], fmap.shape[1]
+        hw = fmap[0, 0].numel()
+        if BT % frames or Fd % 64:
+            raise ValueError(f"{BT} frames of {Fd} channels: need whole clips of {frames} frames and channels % 64 == 0")
+        B = BT // frames
+        clip_img = operand_image(B, Fd, fmap.device) if want_clip_img else None
+        frame_img = operand_image(BT, Fd, fmap.device)
+        with torch.cuda.device(fmap.device):
+            N.check(N.lib().cmhar_video_pool_frames_img(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw, None,
+                                                        N.ptr(clip_img), frame_img.data_ptr(), N.stream_ptr(fmap.device)))
+        return clip_img, frame_img
+
     def project_pooled(self, pooled: Optional[torch.Tensor], precision: Optional[str] = None, want_img: bool = False,
                        x_img: Optional[torch.Tensor] = None, n: Optional[int] = None):
         """(B, F) pooled features -> (B, video_d_model): the reference's ``projection`` (models.py:213).  ``want_img``

@@ -287,6 +287,12 @@ int cmhar_video_pool(const void* fmap, int32_t fmap_is_bf16, int64_t n, int32_t 
  * cmhar_linear_forward_img (the projection layer then needs no fp32 staging); pooled may be NULL. channels % 64 == 0. */
 int cmhar_video_pool_img(const void* fmap, int32_t fmap_is_bf16, int64_t n, int32_t frames, int32_t channels,
                          int32_t hw, float* pooled, void* pooled_img, cmhar_stream_t s);
+/* Same single pass over the feature maps, additionally emitting the per-FRAME spatial means (reference
+ * src/models/models.py:210-211 before the temporal mean of :215) as a bf16 operand image of n * frames rows x channels
+ * (row = clip * frames + frame): the frame tokens of the cross-attention fusion block (fusion.py).  pooled / pooled_img
+ * (the clip means) may be NULL. */
+int cmhar_video_pool_frames_img(const void* fmap, int32_t fmap_is_bf16, int64_t n, int32_t frames, int32_t channels,
+                                int32_t hw, float* pooled, void* pooled_img, void* frame_img, cmhar_stream_t s);
 
 /* Same reduction by the co-resident kernel: ONE 128-thread CTA per SM streams [128 channels x hw] slabs through a
  * 32 KiB cp.async.bulk ring (<= 40 registers per thread), small enough to be resident next to an encoder CTA, so

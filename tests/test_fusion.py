@@ -153,3 +153,59 @@ def test_tensor_core_conv_encoder_matches_spec(L, B):
     if B >= 5:
         part = model.encoder.forward_native(xd[3:5].contiguous(), precision="bf16")
         assert torch.equal(part, got[3:5])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,dtype", [(5, 16, torch.bfloat16), (130, 16, torch.bfloat16), (9, 3, torch.float32)])
+def test_single_pass_pooling_emits_clip_and_frame_images(B, T, dtype):
+    """``pool_features_frames``: one read of the feature maps gives the clip means (temporal + spatial) AND the per-frame
+    spatial means, both as bf16 operand images; each equals the fp32 mean rounded to bf16 (images decoded on the host)."""
+    import test_gpu_fused_tail as tail
+    cfg = cm.default_config()
+    ve = cm.CrossModalModel(cfg).video_encoder.to("cuda:0").eval()
+    g = torch.Generator().manual_seed(B * 31 + T)
+    fmap = torch.relu(torch.randn(B * T, 512, 4, 4, generator=g)).to(dtype).cuda()
+    clip_img, frame_img = ve.pool_features_frames(fmap, T)
+    torch.cuda.synchronize()
+    f32 = fmap.float()
+    want_frame = f32.mean(dim=(2, 3))                                   # (B*T, 512)
+    want_clip = want_frame.view(B, T, 512).mean(1)
+    got_frame = tail.rows_of(frame_img, B * T, 512)
+    got_clip = tail.rows_of(clip_img, B, 512)
+    assert float((got_frame - want_frame).abs().max()) <= 2 ** -8 * float(want_frame.abs().max())
+    assert float((got_clip - want_clip).abs().max()) <= 2 ** -8 * float(want_clip.abs().max())
+    # the clip image carries the same values as the rows of the classic entry point
+    pooled, img2 = ve.pool_features(fmap, T, want_img=True)
+    assert torch.equal(tail.rows_of(img2, B, 512), got_clip)
+
+
+@pytest.mark.gpu
+def test_cross_attention_bf16_route_folds_projection_into_kv_and_refolds_after_reload():
+    """bf16 ``forward_scores`` = single-pass pooling + the projection folded into the kv GEMM: within the bf16 contract of the
+    float64 spec, and the fold follows a reload of the VIDEO encoder's weights (its cache is keyed by the pack generation)."""
+    cfg = cm.default_config()
+    sd = fusion_spec.fusion_state(61)
+    xm = cm.CrossModalModel(cfg)
+    xm.load_state_dict(tsd(W.cross_modal_state(61)), strict=True)
+    model = cm.CrossAttentionFusionClassifier(xm.imu_encoder, xm.video_encoder, cfg)
+    own = set(model.state_dict().keys())
+    model.load_state_dict({k: v for k, v in tsd(sd).items() if k in own}, strict=False)
+    model = model.to("cuda:0").eval()
+    B, T = 40, 16
+    imu, fmap = W.imu_windows(3, B), W.video_feature_maps(4, B, T)
+    f_dev = torch.from_numpy(fmap).cuda().to(torch.bfloat16)
+    x = torch.from_numpy(imu).cuda()
+    got = model.forward_scores(x, f_dev, T, precision="bf16")
+    ref = model.forward_scores(x, f_dev, T, precision="fp32")
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(got["fused"], ref["fused"]) < 2e-2 and rel(got["logits"], ref["logits"]) < 2e-2
+    # reload the video encoder's projection with other weights: the folded kv image must follow
+    with torch.no_grad():
+        new_sd = {k: v.clone() for k, v in model.video_encoder.state_dict().items()}
+        new_sd["projection.weight"] = new_sd["projection.weight"] * 0.5
+    model.video_encoder.load_state_dict(new_sd, strict=True)
+    got2 = model.forward_scores(x, f_dev, T, precision="bf16")
+    ref2 = model.forward_scores(x, f_dev, T, precision="fp32")
+    assert rel(got2["fused"], ref2["fused"]) < 2e-2
+    assert not torch.equal(got2["fused"], got["fused"])

@@ -55,6 +55,19 @@ def image_of(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def rows_of(img: torch.Tensor, n: int, dim: int) -> torch.Tensor:
+    """Inverse of ``image_of``: bf16 operand image -> (n, dim) fp32 rows (host-side restatement of the layout)."""
+    tiles, kcs = (n + 127) // 128, dim // 64
+    flat = img[: tiles * kcs * 16384].view(torch.bfloat16).view(tiles, kcs, 128 * 64)
+    r = torch.arange(128, device=img.device)
+    out = torch.zeros(tiles, 128, kcs, 64, dtype=torch.float32, device=img.device)
+    for j in range(8):
+        src = (r // 8) * 512 + (r % 8) * 64 + ((j ^ (r % 8)) * 8)
+        for e in range(8):
+            out[:, :, :, j * 8 + e] = flat[:, :, src + e].transpose(1, 2).float()
+    return out.reshape(tiles * 128, dim)[:n]
+
+
 @pytest.mark.parametrize("n", [5, 128, 300])
 def test_encoder_cls_image_and_fused_projection_head(n):
     xm, fus, sd, sd_x = modules()
