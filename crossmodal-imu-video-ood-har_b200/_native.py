@@ -10,6 +10,7 @@ import ctypes as C
 import os
 import subprocess
 import threading
+import weakref
 from typing import Optional
 
 import torch
@@ -102,6 +103,7 @@ _SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmhar_debug_cta_trace": (C.c_int, [C.c_void_p, C.c_int64]),
     "cmhar_debug_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
+    "cmhar_blob_release": (C.c_int, [C.c_void_p]),
     "cmhar_debug_imu_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmhar_head_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
@@ -230,4 +232,16 @@ def alloc_blob(nbytes: int, device) -> torch.Tensor:
         raise RuntimeError("cmhar_b200: unsupported dimensions for this build (blob size 0)")
     raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
     off = (-raw.data_ptr()) % 1024
-    return raw[off:off + nbytes]
+    blob = raw[off:off + nbytes]
+    # the library's host-side registry is keyed by the blob pointer: forget the entry when the buffer dies, so that memory the
+    # allocator hands out again at the same address is never taken for a packed blob
+    weakref.finalize(blob, _release_blob, blob.data_ptr()).atexit = False
+    return blob
+
+
+def _release_blob(ptr: int) -> None:
+    try:
+        if _lib is not None:
+            _lib.cmhar_blob_release(ptr)
+    except Exception:
+        pass

@@ -83,6 +83,11 @@ int cmhar_debug_cta_trace(uint64_t* device_buffer, int64_t capacity_records) {
     return CMHAR_OK;
 }
 
+int cmhar_blob_release(const void* blob) {
+    if (blob) cmhar::release_blob(blob);
+    return CMHAR_OK;
+}
+
 int cmhar_debug_set_option(const char* key, int32_t value) {
     CMHAR_REQUIRE(key, "cmhar_debug_set_option: null key");
     if (strcmp(key, "enc_kernel") == 0) {

@@ -116,6 +116,7 @@ __host__ __device__ inline size_t tc_section_offset(size_t fp32_floats) {
 struct BlobInfo { uint32_t magic; int a, b, c, has_tc; };
 void register_blob(const void* blob, const BlobInfo& info);
 bool lookup_blob(const void* blob, BlobInfo* info);
+void release_blob(const void* blob);
 
 // ---- device helpers -----------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

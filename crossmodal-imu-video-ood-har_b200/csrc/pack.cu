@@ -29,6 +29,10 @@ void register_blob(const void* blob, const BlobInfo& info) {
     std::lock_guard<std::mutex> lk(g_blob_mu);
     g_blobs[blob] = info;
 }
+void release_blob(const void* blob) {
+    std::lock_guard<std::mutex> lk(g_blob_mu);
+    g_blobs.erase(blob);
+}
 bool lookup_blob(const void* blob, BlobInfo* info) {
     std::lock_guard<std::mutex> lk(g_blob_mu);
     auto it = g_blobs.find(blob);
@@ -219,7 +223,7 @@ size_t cmhar_maha_blob_bytes(int32_t C) {
 int cmhar_maha_pack(const float* whiten, const float* mean_whitened, const float* class_count, int32_t C,
                     void* blob, cmhar_stream_t s) {
     CMHAR_REQUIRE(whiten && mean_whitened && blob, "cmhar_maha_pack: null argument");
-    CMHAR_REQUIRE(cmhar_maha_blob_bytes(C) != 0, "classes=%d outside [1,1024]", C);
+    CMHAR_REQUIRE(cmhar_maha_blob_bytes(C) != 0 && C <= 64, "classes=%d outside [1,64] (the limit of cmhar_maha_accumulate, which produces the state packed here)", C);
     cudaStream_t st = (cudaStream_t)s;
     MahaLayout ml{C};
     float* f = reinterpret_cast<float*>(reinterpret_cast<char*>(blob) + sizeof(BlobHeader));

@@ -159,6 +159,11 @@ int cmhar_debug_imu_bf16(const void* encoder_blob, const float* x, int64_t n_win
  * appends {kernel id, SM id, start ns, end ns} (globaltimer).  Word 0 counts the records.  Synchronous. */
 int cmhar_debug_cta_trace(uint64_t* device_buffer, int64_t capacity_records);
 
+/* Packed blobs are caller-owned memory; the library keeps a host-side record of every blob it packed (dimensions, whether the
+ * tensor-core section exists) keyed by the blob pointer.  Call this BEFORE freeing or reusing a blob's memory so that a later
+ * allocation at the same address is not mistaken for it.  Unknown pointers are ignored. */
+int cmhar_blob_release(const void* blob);
+
 /* Development switch (tools / A-B measurements only; never read from the environment, so a stray variable cannot change
  * results): key "enc_kernel" = 0 / 1 the single-tile tcgen05 kernel (default), 2 the two-tiles-in-flight kernel
  * imu_forward_bf16_pair_kernel (bit-identical results).  Process wide.
