@@ -136,6 +136,7 @@ _SIGNATURES = {
     "cmhar_maha_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int32, C.c_void_p]),
     "cmhar_maha_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "cmhar_near_tie_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmhar_score_key_range": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "cmhar_score_histogram": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p]),

@@ -379,6 +379,32 @@ __global__ void __launch_bounds__(256) score_histogram_kernel(const float* __res
     }
 }
 
+
+// ---- near-tie rows (the "bf16_refined" mode of the classifiers): rows whose top-2 logit margin is below rel_tau * max|logit| are
+// the only ones whose arg-max a bounded logit error can change; they are re-run on the fp32 path by the caller.
+// work[0] = max |logit| as float bits (atomicMax on the non-negative pattern), work[1] = number of selected rows.
+__global__ void near_tie_absmax_kernel(const float* __restrict__ logits, long long total, unsigned int* __restrict__ work) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(logits[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m == m) atomicMax(work, __float_as_uint(m));
+}
+__global__ void near_tie_select_kernel(const float* __restrict__ logits, long long n, int C, float rel_tau, unsigned int* __restrict__ work,
+                                       long long* __restrict__ idx) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float tau = rel_tau * __uint_as_float(work[0]);
+    const float* z = logits + r * C;
+    float a = -INFINITY, b = -INFINITY;
+    bool bad = false;
+    for (int c = 0; c < C; ++c) {
+        const float v = z[c];
+        bad |= !(v == v);
+        if (v > a) { b = a; a = v; } else if (v > b) b = v;
+    }
+    if (bad || a - b < tau) idx[atomicAdd(work + 1, 1u)] = r;
+}
+
 }  // namespace cmhar
 
 namespace cmhar {
@@ -482,6 +508,20 @@ int cmhar_maha_accumulate(const float* feat, const int64_t* labels, int64_t n, i
     const long long chunks = (n + MA_ROWS - 1) / MA_ROWS;
     const int grid = (int)((chunks < (long long)sm_count()) ? chunks : (long long)sm_count());
     maha_accumulate_kernel<<<grid, 256, smem, (cudaStream_t)s>>>(feat, reinterpret_cast<const long long*>(labels), n, classes, count, sum, second);
+    CMHAR_LAUNCH_CHECK();
+    return CMHAR_OK;
+}
+
+int cmhar_near_tie_rows(const float* logits, int64_t n, int32_t classes, float rel_tau, uint32_t* work2, int64_t* idx_out, cmhar_stream_t s) {
+    if (n <= 0) return CMHAR_OK;
+    CMHAR_REQUIRE(logits && work2 && idx_out && classes >= 2 && rel_tau >= 0.f, "cmhar_near_tie_rows: bad argument");
+    cudaStream_t st = (cudaStream_t)s;
+    CMHAR_CHECK_CUDA(cudaMemsetAsync(work2, 0, 2 * sizeof(uint32_t), st));
+    const long long total = (long long)n * classes;
+    const long long blocks = (total + 255) / 256;
+    near_tie_absmax_kernel<<<(unsigned)(blocks < 8LL * sm_count() ? blocks : 8LL * sm_count()), 256, 0, st>>>(logits, total, work2);
+    CMHAR_LAUNCH_CHECK();
+    near_tie_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logits, n, classes, rel_tau, work2, reinterpret_cast<long long*>(idx_out));
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }

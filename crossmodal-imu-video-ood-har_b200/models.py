@@ -733,8 +733,42 @@ class IMUClassifier(_PackedMixin, nn.Module):
         if self.training:
             raise RuntimeError("forward_scores is an inference entry point: call .eval() first")
         N.require_cuda(imu, "IMUClassifier")
+        if (precision or _DEFAULT_PRECISION) == "bf16_refined":
+            return self._forward_scores_refined(imu, want_cls, window_stride, out)
         maha_blob = self._maha_state.blob(imu.device) if self._maha_state is not None else None
         return imu_forward_native(self.imu_encoder, self._head_blob(imu.device), maha_blob, imu,
                                   want_cls=want_cls, want_logits=want_logits, want_pred=True, want_msp=True,
                                   want_energy=True, want_maha=maha_blob is not None, classes=self.num_classes,
                                   precision=precision, window_stride=window_stride, out=out)
+
+    #: "bf16_refined": rows whose top-2 logit margin is below REFINE_REL_TAU * max|logit| are re-run on the fp32 path.
+    #: The bf16 path's measured logit error is 5e-3 * max|logit| (tests/test_gpu_bf16_contract.py); a row can only change its
+    #: arg-max if its margin is below twice the error, so 4e-2 leaves a 4x safety factor.
+    REFINE_REL_TAU = 4e-2
+
+    @torch.no_grad()
+    def _forward_scores_refined(self, imu, want_cls, window_stride, out):
+        """bf16 tensor-core pass over every window, then the fp32 kernel over the near-tie rows only (``cmhar_near_tie_rows``):
+        the predicted labels are those of the fp32 path -- the reference's, bit for bit (goldens) -- at close to bf16
+        throughput.  Scores of the rows that were not re-run keep bf16 accuracy (AUROC within 2e-3 of the reference; the
+        3-decimal AUROC contract is the fp32 path's).  Synchronises once (the number of selected rows is read back)."""
+        res = self.forward_scores(imu, precision="bf16", want_cls=want_cls, want_logits=True, window_stride=window_stride, out=out)
+        n, dev = res["logits"].shape[0], imu.device
+        if n == 0:
+            return res
+        work = torch.empty(2, dtype=torch.int32, device=dev)
+        idx = torch.empty(n, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            N.check(N.lib().cmhar_near_tie_rows(res["logits"].data_ptr(), n, self.num_classes, float(self.REFINE_REL_TAU),
+                                                work.data_ptr(), idx.data_ptr(), N.stream_ptr(dev)))
+        k = int(work[1].item())
+        res["refined_rows"] = k
+        if k == 0:
+            return res
+        sel = idx[:k]
+        sub = imu.index_select(0, sel)                       # data movement only: the selected windows, contiguous
+        exact = self.forward_scores(sub, precision="fp32", want_cls=want_cls, want_logits=True, window_stride=window_stride)
+        for key, val in exact.items():
+            if key in res and isinstance(res[key], torch.Tensor) and res[key].shape[:1] == (n,):
+                res[key].index_copy_(0, sel, val)
+        return res

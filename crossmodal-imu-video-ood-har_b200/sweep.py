@@ -61,7 +61,7 @@ class OODSweep:
         self.device = next(classifier.parameters()).device
         self.maha: Optional[MahalanobisOOD] = None
         self._scores: Dict[str, List[torch.Tensor]] = {}
-        self._ood: List[torch.Tensor] = []
+        self._labels: List[torch.Tensor] = []
         self._correct = torch.zeros(2, dtype=torch.int64, device=self.device)      # (hits, ID rows) of the classifier
         self.windows_seen = 0
 
@@ -84,15 +84,15 @@ class OODSweep:
 
     @torch.no_grad()
     def score(self, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]]) -> None:
-        """One fused launch pair per batch; scores, the OOD mask and the hit count stay on the device."""
+        """One fused launch pair per batch; scores, labels and the hit count stay on the device.  Nothing here synchronises
+        (no boolean indexing per batch): the populations are separated once, in ``metrics``."""
         for x, y in batches:
             res = self.clf.forward_scores(x, precision=self.precision, window_stride=self.window_stride)
-            id_mask, ood_mask = held_out_activity_split(y, self.held_out)
-            keep = id_mask | ood_mask
+            id_mask, _ = held_out_activity_split(y, self.held_out)
             for k in self.SCORERS:
                 if k in res:
-                    self._scores.setdefault(k, []).append(res[k][keep])
-            self._ood.append(ood_mask[keep])
+                    self._scores.setdefault(k, []).append(res[k])
+            self._labels.append(y)
             self._correct[0] += ((res["pred"] == y) & id_mask).sum()
             self._correct[1] += id_mask.sum()
             self.windows_seen += int(x.shape[0])
@@ -101,13 +101,14 @@ class OODSweep:
     def metrics(self) -> Dict[str, Dict[str, float]]:
         """{scorer: {auroc, fpr95, auroc_bound}} over ALL ranks' shards (collective when distributed) + 'accuracy'."""
         import torch.distributed as dist
-        ood = torch.cat(self._ood) if self._ood else torch.zeros(0, dtype=torch.bool, device=self.device)
+        y = torch.cat(self._labels) if self._labels else torch.zeros(0, dtype=torch.int64, device=self.device)
+        id_mask, ood = held_out_activity_split(y, self.held_out)
         table: Dict[str, Dict[str, float]] = {}
         for k in self.SCORERS:
             if k not in self._scores:
                 continue
             s = torch.cat(self._scores[k])
-            r = auroc_fpr95(s[~ood].contiguous(), s[ood].contiguous())
+            r = auroc_fpr95(s[id_mask].contiguous(), s[ood].contiguous())
             table[k] = {"auroc": r["auroc"], "fpr95": r["fpr"], "auroc_bound": r["auroc_bound"]}
         c = self._correct.clone()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

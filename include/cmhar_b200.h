@@ -376,6 +376,13 @@ int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float*
 /* ------------------------------------------------------------------------------------------
  * AUROC / FPR95 (spec row A5): order-preserving histograms of float scores
  * ------------------------------------------------------------------------------------------ */
+/* Rows whose arg-max a bounded logit error could change: top-2 margin < rel_tau * max |logit| (or a non-finite logit).
+ * Writes their indices (any order) to idx_out (capacity n) and their number to work2[1] (work2[0] = max |logit| as float
+ * bits); work2 = 2 uint32 of device memory.  The classifiers' "bf16_refined" precision re-runs exactly those windows on the
+ * fp32 path, which restores the reference's predicted labels (src/eval/evaluator.py:44-45) at bf16 throughput. */
+int cmhar_near_tie_rows(const float* logits, int64_t n, int32_t classes, float rel_tau, uint32_t* work2, int64_t* idx_out,
+                        cmhar_stream_t s);
+
 /* key(score) = monotone uint32 image of the float; bin = (key - key_lo) >> shift, clamped to
  * [0,bins).  hist (bins) uint64 is accumulated (+=).  min/max keys via cmhar_score_key_range. */
 int cmhar_score_key_range(const float* scores, int64_t n, uint32_t* key_min_max /*[2], caller
