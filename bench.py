@@ -442,7 +442,9 @@ def workload_sweep(cm, clf, dev, rank, world, barrier, dist, precision, total_wi
     fit_b = list(batches(n_fit)) if mat else None
     test_b = list(batches(n_test)) if mat else None
     sw = OODSweep(clf, held, precision=precision, ridge=1e-3, window_stride=live)
-    sw.fit(batches(4096))                      # warm-up: packs weights, sizes allocations
+    sw.fit(batches(4096))                      # warm-up of every phase: packs weights, sizes allocations, and makes NCCL set up
+    sw.score(batches(4096))                    # the MIN / MAX / SUM all-reduces of the metrics (first use costs ~100 ms)
+    sw.metrics()
     sw = OODSweep(clf, held, precision=precision, ridge=1e-3, window_stride=live)
     barrier()
     t0 = time.perf_counter()
