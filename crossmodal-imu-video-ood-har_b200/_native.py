@@ -118,6 +118,10 @@ _SIGNATURES = {
     "cmhar_concat_linear_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                               C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
     "cmhar_l2_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cmhar_xattn_blob_bytes": (C.c_size_t, [C.c_int32]),
+    "cmhar_xattn_pack": (C.c_int, [C.c_void_p] * 8 + [C.c_int32, C.c_void_p, C.c_void_p]),
+    "cmhar_xattn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                      C.c_void_p, C.c_void_p]),
     "cmhar_cross_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "cmhar_residual_ln_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                          C.c_void_p, C.c_void_p]),

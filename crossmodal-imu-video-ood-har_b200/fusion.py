@@ -233,13 +233,51 @@ class CrossAttentionFusionClassifier(_FusionBase):
             self._packed[key] = (pack_generation(), _PackedLinear(lin.to(device), None, device))
         return self._packed[key][1]
 
-    def fuse_native_img(self, tokens: torch.Tensor, frame_img: torch.Tensor, frames: int) -> torch.Tensor:
+    def _xattn_blob(self, device) -> Optional[torch.Tensor]:
+        """Packed weights of the fused cross-attention kernel (``cmhar_xattn_pack``): the video projection folded into the k / v
+        projections, the value bias folded into the out-projection bias (fp64), keyed by the pack generation."""
+        from .models import pack_generation
+        key = ("xattn_fused", str(device))
+        if key not in self._packed or self._packed[key][0] != pack_generation():
+            lib = N.lib()
+            proj = self.video_encoder.projection
+            F_dim = proj.in_features
+            nbytes = lib.cmhar_xattn_blob_bytes(F_dim)
+            if nbytes == 0:
+                self._packed[key] = (pack_generation(), None)
+                return None
+            dd = lambda t: t.detach().double()
+            d = self.d_model
+            wkv = dd(self.kv_proj.weight) @ dd(proj.weight)                                  # (2d, F)
+            bkv = dd(self.kv_proj.weight) @ dd(proj.bias) + dd(self.kv_proj.bias)
+            bo = dd(self.out_proj.bias) + dd(self.out_proj.weight) @ bkv[d:]
+            ts = [self.q_proj.weight, self.q_proj.bias, wkv[:d], wkv[d:], self.out_proj.weight, bo, self.norm.weight, self.norm.bias]
+            ts = [t.detach().to(device=device, dtype=torch.float32).contiguous() for t in ts]
+            blob = N.alloc_blob(nbytes, device)
+            with torch.cuda.device(device):
+                N.check(lib.cmhar_xattn_pack(*[t.data_ptr() for t in ts], F_dim, blob.data_ptr(), N.stream_ptr(device)))
+                torch.cuda.current_stream(device).synchronize()
+            self._packed[key] = (pack_generation(), blob)
+        return self._packed[key][1]
+
+    def fuse_native_img(self, tokens: torch.Tensor, frame_img: torch.Tensor, frames: int, fused_kernel: bool = True) -> torch.Tensor:
         """bf16 route from the per-frame pooled operand image (``VideoEncoder.pool_features_frames``): folded kv GEMM on
         tensor cores straight from the image, then attention, out-projection, residual LayerNorm + token mean."""
         if self.nhead != 8 or self.d_model != 128:
             raise NotImplementedError("native cross-attention is specialised to 8 heads of 16")
         B, S, d = tokens.shape
         dev = tokens.device
+        blob = self._xattn_blob(dev) if fused_kernel else None
+        if blob is not None:            # the whole block as ONE tcgen05 launch (csrc/xattn_tc.cu)
+            fused = torch.empty((B, d), dtype=torch.float32, device=dev)
+            tok = N.f32c(tokens)
+            with torch.cuda.device(dev):
+                rc = N.lib().cmhar_xattn_forward(blob.data_ptr(), tok.data_ptr(), frame_img.data_ptr(), B, S, frames,
+                                                 self.video_encoder.projection.in_features, float(self.norm.eps), fused.data_ptr(),
+                                                 N.stream_ptr(dev))
+            if rc != N.UNSUPPORTED:
+                N.check(rc)
+                return fused
         ql, _, ol = self._packed_linears(dev)
         kvl = self._packed_kv_folded(dev)
         tok2 = N.f32c(tokens).reshape(B * S, d)

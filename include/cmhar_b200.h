@@ -249,6 +249,21 @@ int    cmhar_l2_normalize(const float* x, int64_t n, int32_t dim, float* y, cmha
  * Cross-attention fusion block (spec row A6 -- the reference has no fusion block; defined in
  * fusion.py, oracle oracle/fusion_spec.py: self-consistency, not reference parity)
  * ------------------------------------------------------------------------------------------ */
+/* The whole cross-attention fusion block as ONE tensor-core launch (CMHAR_BF16; spec row A6 -- not in the reference):
+ *   q = tokens Wq^T + bq, [k | v] = frame tokens [Wk | Wv]^T, 8-head attention of the `seq` IMU tokens of a window over its 16 frame
+ *   tokens, y = LayerNorm(tokens + attn Wo^T + bo), fused = mean over the tokens -> (n, 128).
+ * Weights are packed once into a caller-owned blob (1 KiB aligned): wq (128,128), bq (128), wk / wv (128, frame_dim) -- the caller may
+ * have folded a preceding Linear into them --, wo (128,128), bo_folded = bo + Wo bv (the value bias commutes with the attention
+ * average; the key bias cancels in the softmax), LayerNorm weight / bias; all fp32 device pointers.  tokens: (n, seq, 128) fp32;
+ * frame_img: bf16 operand image of n * 16 rows x frame_dim (cmhar_video_pool_frames_img).  Returns CMHAR_ERR_UNSUPPORTED for other
+ * shapes (frames != 16, seq > 16, frame_dim % 64 != 0): run the chained route (cmhar_linear_forward, cmhar_cross_attention,
+ * cmhar_residual_ln_pool) then. */
+size_t cmhar_xattn_blob_bytes(int32_t frame_dim);
+int cmhar_xattn_pack(const float* wq, const float* bq, const float* wk, const float* wv, const float* wo, const float* bo_folded,
+                     const float* ln_weight, const float* ln_bias, int32_t frame_dim, void* blob, cmhar_stream_t s);
+int cmhar_xattn_forward(const void* blob, const float* tokens, const void* frame_img, int64_t n, int32_t seq, int32_t frames,
+                        int32_t frame_dim, float ln_eps, float* fused_out, cmhar_stream_t s);
+
 /* q (n*s_len,128) = projected IMU tokens, kv (n*t_len,256) = [K | V] projected frame tokens ->
  * out (n*s_len,128) = concat_h softmax(q_h k_h^T / 4) v_h, 8 heads of 16.  s_len <= 16, t_len <= 32. */
 int cmhar_cross_attention(const float* q, const float* kv, int64_t n, int32_t s_len, int32_t t_len,

@@ -209,3 +209,36 @@ def test_cross_attention_bf16_route_folds_projection_into_kv_and_refolds_after_r
     ref2 = model.forward_scores(x, f_dev, T, precision="fp32")
     assert rel(got2["fused"], ref2["fused"]) < 2e-2
     assert not torch.equal(got2["fused"], got["fused"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,B", [(250, 1), (250, 7), (250, 8), (250, 9), (250, 300), (100, 45), (250, 8 * 148 + 3)])
+def test_fused_cross_attention_kernel_matches_the_chained_route_and_the_spec(L, B):
+    """``xattn_tc_kernel`` (q / k / v projections, 8-head attention with lane-masked MMAs, out-projection on top of the residual,
+    LayerNorm, token mean -- one launch) against the chained bf16 route (linear_tc + cross_attention + residual_ln_pool kernels) and
+    the float64 spec: ragged window counts, a short token sequence (S = 7, padded rows) and several tiles per CTA."""
+    cfg = cm.default_config(imu_window_size=L)
+    sd = fusion_spec.fusion_state(71, W.Dims(imu_window=L)) if L != 250 else fusion_spec.fusion_state(71)
+    xm = cm.CrossModalModel(cfg)
+    xm.load_state_dict(tsd(W.cross_modal_state(71, W.Dims(imu_window=L)) if L != 250 else W.cross_modal_state(71)), strict=True)
+    model = cm.CrossAttentionFusionClassifier(xm.imu_encoder, xm.video_encoder, cfg)
+    own = set(model.state_dict().keys())
+    model.load_state_dict({k: v for k, v in tsd(sd).items() if k in own}, strict=False)
+    model = model.to("cuda:0").eval()
+    T = 16
+    imu = W.imu_windows(3, B, W.Dims(imu_window=L))
+    f_dev = torch.from_numpy(W.video_feature_maps(4, B, T)).cuda().to(torch.bfloat16)
+    x = torch.from_numpy(imu).cuda()
+    from crossmodal_imu_video_ood_har_b200.models import imu_forward_native
+    tokens = imu_forward_native(model.imu_encoder, None, None, x, want_tokens=True, precision="bf16")["tokens"]
+    _, frame_img = model.video_encoder.pool_features_frames(f_dev, T, want_clip_img=False)
+    fused = model.fuse_native_img(tokens, frame_img, T)
+    chain = model.fuse_native_img(tokens, frame_img, T, fused_kernel=False)
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    print(f"L={L} B={B}: fused cross-attention kernel vs chained route {rel(fused, chain):.2e}")
+    assert torch.isfinite(fused).all() and rel(fused, chain) < 1e-2
+    again = model.fuse_native_img(tokens, frame_img, T)
+    assert torch.equal(fused, again)
+    ref = model.forward_scores(x, f_dev, T, precision="fp32")["fused"]
+    assert rel(fused, ref) < 2e-2
