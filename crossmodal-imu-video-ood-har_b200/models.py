@@ -304,7 +304,9 @@ def imu_forward_native(encoder: "IMUEncoder", head_blob: Optional[torch.Tensor],
     if want_cls_img and B > 0:
         cls_img = out.get("cls_img")
         if cls_img is None:
-            cls_img = out["cls_img"] = operand_image(B, encoder.d_model, dev, zero=True)
+            # rows the encoder does not write (past its last 8-window tile) must read as zeros, not stale memory; a whole number
+            # of 128-row image tiles is written completely
+            cls_img = out["cls_img"] = operand_image(B, encoder.d_model, dev, zero=(B % 128 != 0))
     o = N.ImuOutputs(N.ptr(cls), N.ptr(cls_img), N.ptr(tokens), N.ptr(logits), N.ptr(pred), N.ptr(msp), N.ptr(energy), N.ptr(maha))
     with torch.cuda.device(dev):
         N.check(N.lib().cmhar_imu_forward_ex(blob.data_ptr(), N.ptr(head_blob), N.ptr(maha_blob), x.data_ptr(), B, stride,
