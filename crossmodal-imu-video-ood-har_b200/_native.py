@@ -244,6 +244,11 @@ def alloc_blob(nbytes: int, device) -> torch.Tensor:
     return blob
 
 
+def enable_dev_env(on: bool = True) -> None:
+    """Development tools only: let the library read its CMHAR_* A/B switches from the environment (ignored by default)."""
+    check(lib().cmhar_debug_set_option(b"dev_env", int(on)))
+
+
 def _release_blob(ptr: int) -> None:
     try:
         if _lib is not None:

@@ -95,6 +95,10 @@ int cmhar_debug_set_option(const char* key, int32_t value) {
         cmhar::g_enc_kernel.store(value, std::memory_order_relaxed);
         return CMHAR_OK;
     }
+    if (strcmp(key, "dev_env") == 0) {
+        cmhar::g_dev_env.store(value != 0, std::memory_order_relaxed);
+        return CMHAR_OK;
+    }
     set_error("cmhar_debug_set_option: unknown key '%s'", key);
     return CMHAR_ERR_INVALID;
 }

@@ -158,6 +158,11 @@ __device__ __forceinline__ void trace_end(int kernel_id, unsigned long long t0) 
 }
 enum { TRACE_ENCODER = 1, TRACE_POOL = 2, TRACE_HEAD = 3, TRACE_LINEAR = 4, TRACE_SIM = 5 };
 
+// Development switches (A/B measurements on one box) are read from the environment ONLY when the process enabled them through
+// cmhar_debug_set_option("dev_env", 1): a stray CMHAR_* variable in a production environment changes nothing.
+extern std::atomic<int> g_dev_env;
+inline const char* dev_getenv(const char* name) { return g_dev_env.load(std::memory_order_relaxed) ? getenv(name) : nullptr; }
+
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {

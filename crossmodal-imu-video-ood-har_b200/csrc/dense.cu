@@ -515,16 +515,16 @@ static int launch_pool_ring(const void* fmap, int32_t is_bf16, int64_t n, int32_
         configured[dev & 63] = true;
     }
     static int cpt_cap = -1;
-    if (cpt_cap < 0) { const char* e = getenv("CMHAR_POOL_CPT"); cpt_cap = e ? atoi(e) : 1; }     // 4 channels per thread (16 KiB slabs, one unit per clip): +12 % alone, but 256 units on 148 CTAs is 2 uneven rounds
+    if (cpt_cap < 0) { const char* e = dev_getenv("CMHAR_POOL_CPT"); cpt_cap = e ? atoi(e) : 1; }     // 4 channels per thread (16 KiB slabs, one unit per clip): +12 % alone, but 256 units on 148 CTAs is 2 uneven rounds
     int cpt = 1;
     for (int c = 4; c >= 1; --c) if (c <= cpt_cap && channels % (poolring::CB * c) == 0 && poolring::CB * c * hw * esize <= 16384) { cpt = c; break; }
     const long long units = n * (channels / (poolring::CB * cpt));
     static int per_sm = -1;
-    if (per_sm < 0) { const char* e = getenv("CMHAR_POOL_CTAS_PER_SM"); per_sm = e ? atoi(e) : 1; }
+    if (per_sm < 0) { const char* e = dev_getenv("CMHAR_POOL_CTAS_PER_SM"); per_sm = e ? atoi(e) : 1; }
     const long long cap = (long long)per_sm * sm_count();
     const unsigned grid = (unsigned)(units < cap ? units : cap);
     static int stage_target = -1;
-    if (stage_target < 0) { const char* e = getenv("CMHAR_POOL_STAGE"); stage_target = e ? atoi(e) : poolring::STAGE_TARGET; }
+    if (stage_target < 0) { const char* e = dev_getenv("CMHAR_POOL_STAGE"); stage_target = e ? atoi(e) : poolring::STAGE_TARGET; }
     if (is_bf16) poolring::video_pool_ring_kernel<__nv_bfloat16><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
     else poolring::video_pool_ring_kernel<float><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const float*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
     CMHAR_LAUNCH_CHECK();
@@ -553,16 +553,16 @@ static int video_pool_impl(const void* fmap, int32_t is_bf16, int64_t n, int32_t
     // (HBM latency under load is ~3 us), which stretches every lane's dependency chain: the full 16-lane step measured
     // 29.9 us on one B200 box and 34.3 us on another, against a steady 32.5 us for the flooding kernel.
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("CMHAR_POOL_MODE"); mode = e ? atoi(e) : 1; }        // 1 = flood (default), 2 = ring
+    if (mode < 0) { const char* e = dev_getenv("CMHAR_POOL_MODE"); mode = e ? atoi(e) : 1; }        // 1 = flood (default), 2 = ring
     if (mode == 2 && !img && !fimg && pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw))
         return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, st);
     static int batched = -1;
-    if (batched < 0) { const char* e = getenv("CMHAR_POOL_BATCH"); batched = e ? atoi(e) : 1; }      // development switch
+    if (batched < 0) { const char* e = dev_getenv("CMHAR_POOL_BATCH"); batched = e ? atoi(e) : 1; }      // development switch
     static int pad_smem = -1;
-    if (pad_smem < 0) { const char* e = getenv("CMHAR_POOL_SMEM"); pad_smem = e ? atoi(e) : 0; }      // development switch: unused dynamic
+    if (pad_smem < 0) { const char* e = dev_getenv("CMHAR_POOL_SMEM"); pad_smem = e ? atoi(e) : 0; }      // development switch: unused dynamic
                                                                                                       // smem that keeps the CTAs off SMs holding an encoder CTA
     static int cap_y = -1;
-    if (cap_y < 0) { const char* e = getenv("CMHAR_POOL_GRIDY"); cap_y = e ? atoi(e) : 0; }      // development switch
+    if (cap_y < 0) { const char* e = dev_getenv("CMHAR_POOL_GRIDY"); cap_y = e ? atoi(e) : 0; }      // development switch
     long long gy = n < 32768 ? n : 32768;
     if (cap_y > 0 && gy > cap_y) gy = cap_y;
     dim3 grid((channels + POOL_NT - 1) / POOL_NT, (unsigned)gy);

@@ -782,7 +782,7 @@ int pack_encoder_bf16(const cmhar_imu_encoder_params* p, const float* fp32_secti
 
 static int ablate_mask() {
     static int m = -1;
-    if (m < 0) { const char* e = getenv("CMHAR_ABLATE"); m = e ? atoi(e) : 0; }
+    if (m < 0) { const char* e = dev_getenv("CMHAR_ABLATE"); m = e ? atoi(e) : 0; }
     return m;
 }
 
@@ -795,7 +795,7 @@ static int launch_bf16(const Bf16Args& args, cudaStream_t stream) {
     CMHAR_CHECK_CUDA(cudaGetDevice(&dev));
     static int nq = 0;
     if (nq == 0) {
-        const char* e = getenv("CMHAR_EPI_WARPS");      // 8 (default) or 16 epilogue warps (development switch;
+        const char* e = dev_getenv("CMHAR_EPI_WARPS");      // 8 (default) or 16 epilogue warps (development switch;
         nq = (e && atoi(e) == 16) ? 4 : 2;              // measured equal within noise: the tile is latency-bound)
     }
     if (!configured[dev & 63]) {

@@ -220,7 +220,7 @@ int launch_linear_tc(const uint8_t* w_img, const float* bias, const float* x1, c
         configured[dev & 63] = true;
     }
     static int ns = 0;
-    if (ns == 0) { const char* e = getenv("CMHAR_LINEAR_NS"); ns = e ? atoi(e) : 2; if (ns < 2 || ns > lintc::NS) ns = 2; }      // development switch
+    if (ns == 0) { const char* e = dev_getenv("CMHAR_LINEAR_NS"); ns = e ? atoi(e) : 2; if (ns < 2 || ns > lintc::NS) ns = 2; }      // development switch
     // operand-image input: both rings are plain bulk copies, so a 4-deep ring keeps 128 KiB in flight per CTA and the k loop
     // stops being a chain of serial L2 round trips (K = 512: 16 us -> ~4 us per tile); fp32-row input keeps the 2-deep ring
     // (its staging warps are the bound) so that two CTAs of different layers / batches fit one SM

@@ -331,7 +331,7 @@ static int launch_variant(const uint8_t* section, const float* feat, long long n
 
 int launch_maha_score_tc(const uint8_t* section, const float* feat, long long n, float* score, cudaStream_t st) {
     static int variant = -1;
-    if (variant < 0) { const char* e = getenv("CMHAR_MAHA_VARIANT"); variant = e ? atoi(e) : 0; }      // development switch
+    if (variant < 0) { const char* e = dev_getenv("CMHAR_MAHA_VARIANT"); variant = e ? atoi(e) : 0; }      // development switch
     // Measured on B200, 2 M rows (tools/bench_maha_variants.py): one staging group + dedicated MMA warp 213 us (74 % of the
     // copy bandwidth) with the canonical writer-side proxy fence, 210 us with the consumer-side fence that keeps a full
     // tile of loads in flight -- i.e. not latency-bound any more: a tile moves 64 KiB of staging stores + 24 x 9 KiB of

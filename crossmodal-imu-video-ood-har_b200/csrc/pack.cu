@@ -23,6 +23,7 @@ void set_error(const char* fmt, ...) {
 // ---- host-side registry of packed blobs: the launchers need a blob's dimensions (and whether it carries the
 // tensor-core section) without a device->host read.  Keyed by the blob pointer; an unknown pointer (a blob the
 // caller copied elsewhere) simply takes the CUDA-core path.
+std::atomic<int> g_dev_env{0};
 static std::mutex g_blob_mu;
 static std::unordered_map<const void*, BlobInfo> g_blobs;
 void register_blob(const void* blob, const BlobInfo& info) {

@@ -166,7 +166,9 @@ int cmhar_blob_release(const void* blob);
 
 /* Development switch (tools / A-B measurements only; never read from the environment, so a stray variable cannot change
  * results): key "enc_kernel" = 0 / 1 the single-tile tcgen05 kernel (default), 2 the two-tiles-in-flight kernel
- * imu_forward_bf16_pair_kernel (bit-identical results).  Process wide.
+ * imu_forward_bf16_pair_kernel (bit-identical results); key "dev_env" = 1 lets the launchers read their CMHAR_*
+ * development variables (CMHAR_ABLATE, CMHAR_POOL_*, CMHAR_EPI_WARPS, ...) from the environment -- they are ignored
+ * otherwise.  Process wide.
  * Returns CMHAR_ERR_INVALID for an unknown key / value. */
 int cmhar_debug_set_option(const char* key, int32_t value);
 

@@ -516,3 +516,24 @@ def test_empty_shards_are_legal_for_the_scoring_entry_points():
     m.accumulate(torch.from_numpy(feats).to(DEV), torch.from_numpy(labels).to(DEV), precision="bf16")
     m.finalize(all_reduce=False)
     assert m.score(torch.zeros(0, 128, device=DEV), precision="bf16").numel() == 0
+
+
+def test_round2_entry_points_accept_empty_batches_and_refuse_unserved_shapes():
+    """n = 0 is a no-op for the new entry points (null pointers included); shapes the fused kernels do not serve come back as
+    CMHAR_ERR_UNSUPPORTED (callers then run the chained route), never as a silent wrong answer."""
+    lib, N = cm._native.lib(), cm._native
+    st = N.stream_ptr(torch.device(DEV))
+    assert lib.cmhar_xattn_forward(None, None, None, 0, 16, 16, 512, 1e-5, None, st) == 0
+    assert lib.cmhar_conv_encoder_forward_ex(None, None, 0, 250, 1500, None, N.BF16, st) == 0
+    assert lib.cmhar_video_pool_frames_img(None, 1, 0, 16, 512, 16, None, None, None, st) == 0
+    assert lib.cmhar_near_tie_rows(None, 0, 32, 0.04, None, None, st) == 0
+    assert lib.cmhar_xattn_blob_bytes(500) == 0 and lib.cmhar_xattn_blob_bytes(512) > 0
+    blob = N.alloc_blob(lib.cmhar_xattn_blob_bytes(512), torch.device(DEV))
+    tok = torch.zeros(8, 16, 128, device=DEV)
+    img = N.alloc_blob(lib.cmhar_operand_image_bytes(8 * 16, 512), torch.device(DEV))
+    out = torch.zeros(8, 128, device=DEV)
+    rc = lib.cmhar_xattn_forward(blob.data_ptr(), tok.data_ptr(), img.data_ptr(), 8, 16, 8, 512, 1e-5, out.data_ptr(), st)   # 8 frames
+    assert rc == N.UNSUPPORTED
+    with pytest.raises(RuntimeError):
+        N.check(lib.cmhar_debug_set_option(b"no_such_key", 1))
+    assert lib.cmhar_blob_release(None) == 0 and lib.cmhar_blob_release(12345) == 0

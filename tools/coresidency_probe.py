@@ -6,6 +6,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import crossmodal_imu_video_ood_har_b200 as cm
+cm._native.enable_dev_env()            # development tool: honour the CMHAR_* A/B switches of the environment
 from crossmodal_imu_video_ood_har_b200.models import imu_forward_native
 N = cm._native
 dev = torch.device("cuda:0")

@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import crossmodal_imu_video_ood_har_b200 as cm  # noqa: E402
+cm._native.enable_dev_env()            # development tool: honour the CMHAR_* A/B switches of the environment
 from crossmodal_imu_video_ood_har_b200.models import imu_forward_native  # noqa: E402
 
 

@@ -1,6 +1,7 @@
 import sys, os, torch
 sys.path.insert(0, os.getcwd())
 import crossmodal_imu_video_ood_har_b200 as cm
+cm._native.enable_dev_env()            # development tool: honour the CMHAR_* A/B switches of the environment
 from crossmodal_imu_video_ood_har_b200.models import imu_forward_native
 dev = torch.device("cuda:0")
 cfg = cm.default_config(); torch.manual_seed(0)

@@ -2,6 +2,7 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import crossmodal_imu_video_ood_har_b200 as cm
+cm._native.enable_dev_env()            # development tool: honour the CMHAR_* A/B switches of the environment
 N = cm._native; dev = torch.device("cuda:0"); B = 256
 sets = [torch.relu(torch.randn(B * 16, 512, 4, 4, device=dev)).to(torch.bfloat16) for _ in range(8)]
 pooled = torch.empty(B, 512, device=dev)

@@ -4,6 +4,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import crossmodal_imu_video_ood_har_b200 as cm
+cm._native.enable_dev_env()            # development tool: honour the CMHAR_* A/B switches of the environment
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"

@@ -5,6 +5,7 @@ import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import crossmodal_imu_video_ood_har_b200 as cm
+cm._native.enable_dev_env()            # development tool: honour the CMHAR_* A/B switches of the environment
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 8 * 4
 cfg = cm.default_config()
 torch.manual_seed(0)
