@@ -422,7 +422,7 @@ def workload_sweep(cm, clf, dev, rank, world, barrier, dist, precision, total_wi
     lo, hi = cm.shard_bounds(total_windows, rank, world)
     n_test = hi - lo
     n_fit = max(4096, n_test // 10)
-    CH = 65536
+    CH = 262144                # windows per scoring launch pair
     live = 240
     held = [29, 30, 31]
     g = torch.Generator(device=dev).manual_seed(31 + rank)
