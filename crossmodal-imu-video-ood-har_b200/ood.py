@@ -53,6 +53,19 @@ def logit_scores(logits: torch.Tensor, temperature: float = 1.0) -> Dict[str, to
 
 
 # ------------------------------------------------------------------------------- A3 / A4
+def _lower_triangular_inverse(chol: np.ndarray) -> np.ndarray:
+    """G^{-1} of the Cholesky factor: LAPACK dtrtri (0.17 ms for 128 x 128) when scipy is importable, else the general solve
+    (0.5-0.8 ms) -- the finalisation sits inside the timed fit of BASELINE configs[3]."""
+    try:
+        from scipy.linalg.lapack import dtrtri
+        inv, info = dtrtri(np.asfortranarray(chol), lower=1)
+        if info == 0:
+            return np.tril(inv)
+    except ImportError:
+        pass
+    return np.linalg.solve(chol, np.eye(chol.shape[0]))
+
+
 def finalize_mahalanobis(count: np.ndarray, ssum: np.ndarray, second: np.ndarray, ridge: float = 0.0
                          ) -> Dict[str, np.ndarray]:
     """Host fp64 finalisation of the (all-reduced) sufficient statistics: class means, tied
@@ -70,7 +83,7 @@ def finalize_mahalanobis(count: np.ndarray, ssum: np.ndarray, second: np.ndarray
     if ridge:
         cov = cov + ridge * np.eye(cov.shape[0])
     chol = np.linalg.cholesky(cov)
-    whiten = np.linalg.solve(chol, np.eye(cov.shape[0])).T
+    whiten = _lower_triangular_inverse(chol).T
     return {"mean": mean, "cov": cov, "whiten": whiten, "mean_whitened": mean @ whiten, "count": count}
 
 
