@@ -52,7 +52,7 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
 
 __global__ void __launch_bounds__(NT, 1) maha_fit_tc_kernel(const float* __restrict__ feat, const long long* __restrict__ labels,
                                                             long long n, int C, double* __restrict__ count,
-                                                            double* __restrict__ sum, double* __restrict__ second) {
+                                                            double* __restrict__ sum, double* __restrict__ second, int pf_on) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = smem_u32(smem), bar0 = sbase + OFF_BAR;
@@ -127,6 +127,13 @@ __global__ void __launch_bounds__(NT, 1) maha_fit_tc_kernel(const float* __restr
         const int oh_row = warp * 16 + (lane >> 1), oh_half = lane & 1;      // one-hot tile: two lanes per row, 4 pieces each
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             const int b = (int)(it & 1);
+            if (pf_on && warp == 0 && lane == 0) {                  // L2 prefetch of the tile 3 steps ahead (tc_ptx.cuh l2_prefetch_bulk)
+                const long long tl = tile + 3 * (long long)gridDim.x;
+                if (tl < tiles) {
+                    const long long rows = n - tl * 128;
+                    tc::l2_prefetch_bulk(feat + (size_t)tl * (128 * D), (uint32_t)((rows < 128 ? rows : 128) * D * 4));
+                }
+            }
             const long long r_oh = tile * 128 + oh_row;
             long long lab_oh = (r_oh < n) ? __ldg(labels + r_oh) : -1;
             if (lab_oh < 0 || lab_oh >= C) lab_oh = -1;              // rows with a label outside [0, C) are skipped entirely
@@ -216,7 +223,9 @@ int launch_maha_fit_tc(const float* feat, const long long* labels, long long n, 
     }
     const long long tiles = (n + 127) / 128;
     const int grid = (int)(tiles < (long long)sm_count() ? tiles : (long long)sm_count());
-    fittc::maha_fit_tc_kernel<<<grid, fittc::NT, fittc::SMEM_BYTES, st>>>(feat, labels, n, C, count, sum, second);
+    static int pf = -1;
+    if (pf < 0) { const char* e = dev_getenv("CMHAR_L2_PREFETCH"); pf = e ? atoi(e) : 1; }      // development switch (default on)
+    fittc::maha_fit_tc_kernel<<<grid, fittc::NT, fittc::SMEM_BYTES, st>>>(feat, labels, n, C, count, sum, second, pf);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }

@@ -116,7 +116,7 @@ __device__ __forceinline__ void load_rows(float4 (&t)[ROWS], const float* __rest
 template <int GROUPS, bool MERGED, bool CFENCE>
 __global__ void __launch_bounds__(Roles<GROUPS, MERGED>::NT, 1) maha_score_tc_kernel(const uint8_t* __restrict__ section,
                                                                                      const float* __restrict__ feat, long long n,
-                                                                                     float* __restrict__ score) {
+                                                                                     float* __restrict__ score, int pf_on) {
     using R = Roles<GROUPS, MERGED>;
     constexpr int N_STAGE_WARPS = R::STAGE_WARPS, EPI_WARP0 = R::EPI_WARP0, MMA_WARP = R::MMA_WARP;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -164,9 +164,20 @@ __global__ void __launch_bounds__(Roles<GROUPS, MERGED>::NT, 1) maha_score_tc_ke
             load_rows<ROWS_PER_WARP>(t, lane_src + (size_t)tile * (128 * D), left < ROWS_PER_WARP ? (int)left : ROWS_PER_WARP);
         };
         int tile = (int)blockIdx.x + g * (int)gridDim.x;
+        // L2 prefetch of the tiles PF_AHEAD .. steps ahead (one lane per CTA; see tc_ptx.cuh l2_prefetch_bulk)
+        constexpr int PF_AHEAD = 3;
+        auto prefetch_tile = [&](int tl) __attribute__((always_inline)) {
+            if (tl < ntiles) {
+                const long long rows = n - (long long)tl * 128;
+                l2_prefetch_bulk(feat + (size_t)tl * (128 * D), (uint32_t)((rows < 128 ? rows : 128) * D * 4));
+            }
+        };
+        if (pf_on && warp == 0 && lane == 0)
+            for (int a = 1; a < PF_AHEAD; ++a) prefetch_tile(tile + a * step);
         if (tile < ntiles) fetch(tile);
         for (int it = g; tile < ntiles; tile += step, it += GROUPS) {        // it = index within this CTA's tile sequence
             const int b = it & 1;                                    // A buffer == accumulator index of this tile
+            if (pf_on && warp == 0 && lane == 0) prefetch_tile(tile + PF_AHEAD * step);
             mbar_wait(BAR(B_FREE + b), (uint32_t)(((it >> 1) & 1) ^ 1), 83);       // the MMAs that read this buffer are complete
             if (CFENCE) {
                 // consumer-side proxy fence: this warp never executes the MEMBAR, so the refill loads issued row by row
@@ -324,7 +335,9 @@ static int launch_variant(const uint8_t* section, const float* feat, long long n
     const long long tiles = (n + 127) / 128;
     CMHAR_REQUIRE(tiles < 0x7fffffffLL, "too many rows");
     const int grid = (int)(tiles < (long long)sm_count() ? tiles : (long long)sm_count());
-    kern<<<grid, mstc::Roles<GROUPS, MERGED>::NT, mstc::SMEM_BYTES, st>>>(section, feat, n, score);
+    static int pf = -1;
+    if (pf < 0) { const char* e = dev_getenv("CMHAR_L2_PREFETCH"); pf = e ? atoi(e) : 1; }      // development switch (default on)
+    kern<<<grid, mstc::Roles<GROUPS, MERGED>::NT, mstc::SMEM_BYTES, st>>>(section, feat, n, score, pf);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }

@@ -8,6 +8,7 @@ from oracle import weights as W
 import numpy as np
 
 N = cm._native
+N.enable_dev_env()            # development tool: honour the CMHAR_* A/B switches of the environment
 dev = torch.device("cuda:0")
 peak = 6539.9
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
