@@ -18,5 +18,6 @@ from .pipeline import CrossModalOODPipeline
 from .shards import WindowShard, write_shard, pack_npy_windows, live_samples
 from .tables import generate_ood_table, ood_rows, save_tables
 from .sweep import OODSweep, held_out_activity_split
+from .video_trunk import DeviceVideoTrunk, fold_conv_bn
 
 __version__ = "0.1.0"

@@ -268,8 +268,9 @@ constexpr int STAGE_TARGET = 16384;          // bytes per ring stage (whole fram
 constexpr int OFF_BAR = RING_BYTES, SMEM_BYTES = RING_BYTES + 2 * MAX_STAGES * 8;
 
 template <typename T>
-__global__ void __launch_bounds__(CB, 12) video_pool_ring_kernel(const T* __restrict__ fmap, long long n, int frames, int channels,
-                                                                 int hw, float* __restrict__ pooled, int stage_target, int cpt) {
+__global__ void __launch_bounds__(CB, 9) video_pool_ring_kernel(const T* __restrict__ fmap, long long n, int frames, int channels,
+                                                                 int hw, float* __restrict__ pooled, int stage_target, int cpt,
+                                                                 uint8_t* __restrict__ img, int pf_ahead) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned long long trace_t0 = (tid == 0) ? trace_begin() : 0ull;
@@ -312,8 +313,27 @@ __global__ void __launch_bounds__(CB, 12) video_pool_ring_kernel(const T* __rest
         if (++p_s == nst) { p_s = 0; p_par ^= 1u; }
         ++p_n;
     };
-    if (tid == 0)
+    // L2 prefetch cursor (thread 0 only), pf_ahead stage-steps in front of the producer: the ring's 32 KiB in flight cover ~1 us of L2
+    // latency, not the ~3 us of HBM under load -- cp.async.bulk.prefetch.L2 costs neither registers nor shared memory, so the bytes
+    // in flight towards HBM are no longer limited by what fits next to an encoder CTA
+    int q_unit = blockIdx.x, q_f = 0, q_n = 0;
+    auto prefetch = [&](bool fire) {                          // fire = false: advance the cursor only (steps the ring itself holds)
+        const int g = (frames - q_f < G) ? frames - q_f : G;
+        if (fire) {
+            const int b = q_unit / cblocks, cb = q_unit - b * cblocks;
+            const T* src = fmap + (((size_t)b * frames + q_f) * channels + (size_t)cb * CBC) * hw;
+            if (cblocks == 1) l2_prefetch_bulk(src, (uint32_t)(g * slab_bytes));            // whole frames: contiguous
+            else for (int f = 0; f < g; ++f) l2_prefetch_bulk(src + (size_t)f * channels * hw, (uint32_t)slab_bytes);
+        }
+        q_f += g;
+        if (q_f == frames) { q_f = 0; q_unit += gridDim.x; }
+        ++q_n;
+    };
+    if (tid == 0) {
         while (p_n < nst && p_n < total) issue();
+        if (pf_ahead > 0)
+            while (q_n < nst + pf_ahead && q_n < total) prefetch(q_n >= nst);
+    }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int f0 = 0, s = 0, unit = blockIdx.x;
     uint32_t par = 0u;
@@ -344,13 +364,24 @@ __global__ void __launch_bounds__(CB, 12) video_pool_ring_kernel(const T* __rest
         __syncwarp();
         if (lane == 0) mbar_arrive(EMPTY(s));                 // this warp's channels of the stage are in registers
         if (++s == nst) { s = 0; par ^= 1u; }
-        if (tid == 0 && p_n < total) issue();
+        if (tid == 0 && p_n < total) {
+            if (pf_ahead > 0 && q_n < total) prefetch(true);
+            issue();
+        }
         f0 += g;
         if (f0 == frames) {
             const int b = unit / cblocks, cb = unit - b * cblocks;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (j < cpt) pooled[(size_t)b * channels + cb * CBC + j * CB + tid] = acc[j] * inv;
+                if (j < cpt) {
+                    const int c = cb * CBC + j * CB + tid;
+                    const float mean = acc[j] * inv;
+                    if (pooled) pooled[(size_t)b * channels + c] = mean;
+                    if (img) {                                      // bf16 operand image, as video_pool_kernel writes it
+                        uint8_t* chunk = img + ((size_t)(b >> 7) * (channels >> 6) + (c >> 6)) * 16384;
+                        *reinterpret_cast<__nv_bfloat16*>(chunk + tc::sw128_off((int)(b & 127), (c & 63) >> 3) + (c & 7) * 2) = __float2bfloat16_rn(mean);
+                    }
+                }
                 acc[j] = 0.f;
             }
             f0 = 0; unit += gridDim.x;
@@ -501,7 +532,7 @@ static bool pool_ring_eligible(const void* fmap, int32_t is_bf16, int64_t n, int
 }
 
 static int launch_pool_ring(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
-                            float* pooled, cudaStream_t st) {
+                            float* pooled, cudaStream_t st, uint8_t* img = nullptr) {
     const int esize = is_bf16 ? 2 : 4;
     static bool configured[64] = {};
     int dev = 0;
@@ -525,8 +556,10 @@ static int launch_pool_ring(const void* fmap, int32_t is_bf16, int64_t n, int32_
     const unsigned grid = (unsigned)(units < cap ? units : cap);
     static int stage_target = -1;
     if (stage_target < 0) { const char* e = dev_getenv("CMHAR_POOL_STAGE"); stage_target = e ? atoi(e) : poolring::STAGE_TARGET; }
-    if (is_bf16) poolring::video_pool_ring_kernel<__nv_bfloat16><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
-    else poolring::video_pool_ring_kernel<float><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const float*)fmap, n, frames, channels, hw, pooled, stage_target, cpt);
+    static int pf_ahead = -1;
+    if (pf_ahead < 0) { const char* e = dev_getenv("CMHAR_POOL_PF"); pf_ahead = e ? atoi(e) : 12; }      // ring stages prefetched into L2 ahead of the producer
+    if (is_bf16) poolring::video_pool_ring_kernel<__nv_bfloat16><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const __nv_bfloat16*)fmap, n, frames, channels, hw, pooled, stage_target, cpt, img, pf_ahead);
+    else poolring::video_pool_ring_kernel<float><<<grid, poolring::CB, poolring::SMEM_BYTES, st>>>((const float*)fmap, n, frames, channels, hw, pooled, stage_target, cpt, img, pf_ahead);
     CMHAR_LAUNCH_CHECK();
     return CMHAR_OK;
 }
@@ -554,8 +587,8 @@ static int video_pool_impl(const void* fmap, int32_t is_bf16, int64_t n, int32_t
     // 29.9 us on one B200 box and 34.3 us on another, against a steady 32.5 us for the flooding kernel.
     static int mode = -1;
     if (mode < 0) { const char* e = dev_getenv("CMHAR_POOL_MODE"); mode = e ? atoi(e) : 1; }        // 1 = flood (default), 2 = ring
-    if (mode == 2 && !img && !fimg && pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw))
-        return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, st);
+    if (mode == 2 && !fimg && pool_ring_eligible(fmap, is_bf16, n, frames, channels, hw))
+        return launch_pool_ring(fmap, is_bf16, n, frames, channels, hw, pooled, st, img);
     static int batched = -1;
     if (batched < 0) { const char* e = dev_getenv("CMHAR_POOL_BATCH"); batched = e ? atoi(e) : 1; }      // development switch
     static int pad_smem = -1;

@@ -94,7 +94,8 @@ class _PackedMixin:
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            object.__setattr__(new, k, {} if k == "_packed" else copy.deepcopy(v, memo))
+            # (the device trunk holds CUDA graphs and a snapshot of the backbone weights: rebuilt on demand, never copied)
+            object.__setattr__(new, k, {} if k == "_packed" else None if k == "_device_trunk" else copy.deepcopy(v, memo))
         return new
 
 
@@ -368,6 +369,14 @@ class _PackedLinear:
         return self.in_dim % 64 == 0 and self.out_dim % 64 == 0
 
 
+def _is_channels_last_map(fmap: torch.Tensor) -> bool:
+    """A 4-d feature map stored channels-last (what ``DeviceVideoTrunk`` returns) that ``cmhar_video_pool_nhwc`` can read in place."""
+    if fmap.dim() != 4 or fmap.is_contiguous() or not fmap.is_contiguous(memory_format=torch.channels_last):
+        return False
+    per16 = 8 if fmap.dtype == torch.bfloat16 else 4
+    return fmap.shape[1] % per16 == 0 and fmap.data_ptr() % 16 == 0
+
+
 def operand_image(n: int, dim: int, device, zero: bool = False) -> torch.Tensor:
     """bf16 operand image for (n, dim) activations: [ceil(n/128)][dim/64] SWIZZLE_128B chunks of 16 KiB (what
     ``cmhar_linear_forward_img`` / ``cmhar_mlp2_forward_img`` write for the next kernel).  ``zero``: rows no kernel writes
@@ -391,7 +400,8 @@ class VideoEncoder(_PackedMixin, nn.Module):
     """Video encoder (reference src/models/models.py:137-216).
 
     The trunk (HF VideoMAE, torchvision resnet18 / mobilenet_v2) is third-party code and runs as
-    the ordinary torch module it is (out of scope).  Everything after it --
+    the ordinary torch module it is (out of scope) -- eagerly in fp32 by default, or, after
+    ``attach_device_trunk()``, in channels-last bf16 under a CUDA graph (video_trunk.py).  Everything after it --
     spatial average pool, ``projection`` and the temporal mean -- is the hot path: one HBM-bound
     pooling kernel over the trunk's feature map followed by one small GEMM (pooling and the
     Linear commute, models.py:210-215)."""
@@ -425,7 +435,34 @@ class VideoEncoder(_PackedMixin, nn.Module):
         self.projection = nn.Linear(self.feature_dim, m.video_d_model)
         if not self.is_videomae:
             self.temporal_pool = nn.AdaptiveAvgPool1d(1)
+        self._device_trunk, self._device_trunk_kwargs, self._device_trunk_stale = None, None, False
         self._init_packed()
+
+    def attach_device_trunk(self, trunk=True, **kwargs):
+        """Route the eval-mode forward of a CNN trunk through ``video_trunk.DeviceVideoTrunk`` (channels-last bf16, folded
+        BatchNorm, CUDA graph; bf16 contract).  ``trunk``: a DeviceVideoTrunk, True (build one from the current ``backbone``
+        weights -- call again after loading new weights) or None / False (back to the eager fp32 trunk).  With it the module
+        also accepts decoded uint8 frames ``(B, T, H, W, 3)``, normalised on the device."""
+        self._device_trunk_kwargs = dict(kwargs) if trunk is True else None
+        if trunk is True:
+            from .video_trunk import DeviceVideoTrunk
+            trunk = DeviceVideoTrunk(self, **kwargs)
+        self._device_trunk = trunk or None
+        self._device_trunk_stale = False
+        return self._device_trunk
+
+    def invalidate_packed(self):
+        # parameters may have changed: a trunk built here from the backbone's weights is a snapshot and is rebuilt on next use
+        if getattr(self, "_device_trunk_kwargs", None) is not None:
+            self._device_trunk_stale = True
+        super().invalidate_packed()
+
+    def _trunk(self):
+        if self._device_trunk is None and getattr(self, "_device_trunk_kwargs", None) is not None:
+            self._device_trunk_stale = True                      # dropped by a deep copy
+        if getattr(self, "_device_trunk_stale", False):
+            self.attach_device_trunk(True, **self._device_trunk_kwargs)
+        return self._device_trunk
 
     def _packed_projection(self, device) -> _PackedLinear:
         key = ("proj", str(device))
@@ -443,7 +480,9 @@ class VideoEncoder(_PackedMixin, nn.Module):
         N.require_cuda(fmap, "VideoEncoder")
         if fmap.dtype not in (torch.float32, torch.bfloat16):
             fmap = fmap.float()
-        fmap = fmap.contiguous()
+        nhwc = _is_channels_last_map(fmap)
+        if not nhwc:
+            fmap = fmap.contiguous()
         BT, Fd = fmap.shape[0], fmap.shape[1]
         hw = fmap[0, 0].numel()
         if BT % frames:
@@ -454,6 +493,11 @@ class VideoEncoder(_PackedMixin, nn.Module):
         if pooled is None and (want_rows or not want_img):
             pooled = torch.empty((B, Fd), dtype=torch.float32, device=fmap.device)
         with torch.cuda.device(fmap.device):
+            if nhwc:            # the device trunk's output as it lies (video_trunk.py): physical (B*T, h*w, F), no permuted copy
+                img = operand_image(B, Fd, fmap.device) if want_img else None
+                N.check(N.lib().cmhar_video_pool_nhwc(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw,
+                                                      N.ptr(pooled), N.ptr(img), None, N.stream_ptr(fmap.device)))
+                return (pooled, img) if want_img else pooled
             if want_img:
                 img = operand_image(B, Fd, fmap.device)
                 N.check(N.lib().cmhar_video_pool_img(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw,
@@ -471,7 +515,9 @@ class VideoEncoder(_PackedMixin, nn.Module):
         N.require_cuda(fmap, "VideoEncoder")
         if fmap.dtype not in (torch.float32, torch.bfloat16):
             fmap = fmap.float()
-        fmap = fmap.contiguous()
+        nhwc = _is_channels_last_map(fmap)
+        if not nhwc:
+            fmap = fmap.contiguous()
         BT, Fd = fmap.shape[0], fmap.shape[1]
         hw = fmap[0, 0].numel()
         if BT % frames or Fd % 64:
@@ -480,6 +526,10 @@ class VideoEncoder(_PackedMixin, nn.Module):
         clip_img = operand_image(B, Fd, fmap.device) if want_clip_img else None
         frame_img = operand_image(BT, Fd, fmap.device)
         with torch.cuda.device(fmap.device):
+            if nhwc:
+                N.check(N.lib().cmhar_video_pool_nhwc(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw, None,
+                                                      N.ptr(clip_img), frame_img.data_ptr(), N.stream_ptr(fmap.device)))
+                return clip_img, frame_img
             N.check(N.lib().cmhar_video_pool_frames_img(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), B, frames, Fd, hw, None,
                                                         N.ptr(clip_img), frame_img.data_ptr(), N.stream_ptr(fmap.device)))
         return clip_img, frame_img
@@ -510,12 +560,18 @@ class VideoEncoder(_PackedMixin, nn.Module):
         N.require_cuda(fmap, "VideoEncoder")
         if fmap.dtype not in (torch.float32, torch.bfloat16):
             fmap = fmap.float()
-        fmap = fmap.contiguous()
+        nhwc = _is_channels_last_map(fmap)
+        if not nhwc:
+            fmap = fmap.contiguous()
         BT, Fd = fmap.shape[0], fmap.shape[1]
         pooled = torch.empty((BT, Fd), dtype=torch.float32, device=fmap.device)
         with torch.cuda.device(fmap.device):
-            N.check(N.lib().cmhar_video_pool(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), BT, 1, Fd, fmap[0, 0].numel(),
-                                             pooled.data_ptr(), N.stream_ptr(fmap.device)))
+            if nhwc:
+                N.check(N.lib().cmhar_video_pool_nhwc(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), BT, 1, Fd, fmap[0, 0].numel(),
+                                                      pooled.data_ptr(), None, None, N.stream_ptr(fmap.device)))
+            else:
+                N.check(N.lib().cmhar_video_pool(fmap.data_ptr(), int(fmap.dtype == torch.bfloat16), BT, 1, Fd, fmap[0, 0].numel(),
+                                                 pooled.data_ptr(), N.stream_ptr(fmap.device)))
         return self._packed_projection(fmap.device)(pooled, relu=False, precision=precision)
 
     def frame_features(self, x):
@@ -523,6 +579,8 @@ class VideoEncoder(_PackedMixin, nn.Module):
         if self.is_videomae:
             raise NotImplementedError("frame_features needs a per-frame (CNN) trunk")
         B, T = x.shape[0], x.shape[1]
+        if _native_mode(self) and self._trunk() is not None:
+            return self.forward_frame_features(self._device_trunk(x)).view(B, T, -1)
         fmap = self.backbone(x.reshape(B * T, *x.shape[2:]))
         if _native_mode(self):
             return self.forward_frame_features(fmap).view(B, T, -1)
@@ -537,6 +595,8 @@ class VideoEncoder(_PackedMixin, nn.Module):
                 N.require_cuda(feat, "VideoEncoder")
                 return self._packed_projection(feat.device)(feat, relu=False)
             return self.projection(feat)
+        if native and self._trunk() is not None:
+            return self.forward_features(self._device_trunk(x), T)      # channels-last bf16 trunk under a CUDA graph (video_trunk.py)
         fmap = self.backbone(x.reshape(B * T, *x.shape[2:]))
         if native:
             return self.forward_features(fmap, T)

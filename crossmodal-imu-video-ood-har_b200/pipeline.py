@@ -42,8 +42,38 @@ class CrossModalOODPipeline:
             (self.fusion if self.fusion is not None else self.clf).set_mahalanobis(mahalanobis)
         self.sig = (float(sigmoid_scale), float(sigmoid_bias))
         self._host = None
+        self.trunk = None           # video_trunk.DeviceVideoTrunk (attach_trunk): frames in, feature maps never leave the device
         self._side = None           # side stream: the video branch runs concurrently with the IMU kernel
         self._fused_ok = True       # bf16: the 7-launch route (fused projection heads / fusion head / similarity on operand images)
+
+    # ------------------------------------------------------------------ frames in, trunk on the device
+    def attach_trunk(self, trunk=True, **kwargs):
+        """Give the pipeline the video trunk (``video_trunk.DeviceVideoTrunk``: channels-last bf16, CUDA graph; True = build it from
+        ``cross_modal.video_encoder.backbone``).  ``run_frames`` / ``run_host`` / ``stream_host`` then accept decoded uint8 frames
+        ``(B, T, H, W, 3)`` where they take feature maps: the frames are normalised on the device, the trunk's channels-last map
+        is pooled in place, and no feature map crosses PCIe."""
+        self.trunk = self.xm.video_encoder.attach_device_trunk(trunk, **kwargs)
+        return self.trunk
+
+    def _frames_to_map(self, frames: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        trunk = getattr(self, "trunk", None)
+        if trunk is None:
+            raise RuntimeError("uint8 frames need the device trunk: call pipeline.attach_trunk() first")
+        if frames.dim() == 5 and frames.shape[1] != self.frames:
+            raise ValueError(f"clips of {frames.shape[1]} frames, pipeline built for {self.frames}")
+        return trunk(frames, slot=slot)
+
+    def _frame_buffer(self, shape, dev, slot: int) -> torch.Tensor:
+        """Device landing buffer of a uint8 frame batch = the trunk graph's static input of ``slot`` (no second device copy)."""
+        n = 1
+        for d in shape[:-3]:
+            n *= int(d)
+        return self.trunk.to(dev).frame_buffer(n, int(shape[-3]), int(shape[-2]), slot).view(shape)
+
+    @torch.no_grad()
+    def run_frames(self, imu: torch.Tensor, frames: torch.Tensor, slot: int = 0, **kwargs) -> Dict[str, torch.Tensor]:
+        """``run`` from frames on the device: uint8 ``(B, T, H, W, 3)`` (normalised here) or the reference's float ``(B, T, 3, H, W)``."""
+        return self.run(imu, self._frames_to_map(frames, slot), **kwargs)
 
     def _fused_route(self, fmap: Optional[torch.Tensor], pooled) -> bool:
         ve = self.xm.video_encoder
@@ -177,7 +207,7 @@ class CrossModalOODPipeline:
         B, L = imu_host.shape[0], imu_host.shape[-1]
         live = 16 * (self.clf.imu_encoder._check_native_dims(L) - 1)
         h = self._host
-        if h is None or h["B"] != B or h["live"] != live or (fmap_host is not None and h.get("fmap_shape") != tuple(fmap_host.shape)):
+        if h is None or h["B"] != B or h["live"] != live or (fmap_host is not None and h.get("fmap_shape") != (tuple(fmap_host.shape), fmap_host.dtype)):
             h = {"B": B, "live": live,
                  "imu_pin": torch.empty((B, live), dtype=torch.float32).pin_memory(),
                  "imu_dev": torch.empty((B, live), dtype=torch.float32, device=dev),
@@ -185,9 +215,10 @@ class CrossModalOODPipeline:
                  "pred_pin": torch.empty((B,), dtype=torch.int64).pin_memory(),
                  "loss_pin": torch.empty((), dtype=torch.float64).pin_memory()}
             if fmap_host is not None:
-                h["fmap_shape"] = tuple(fmap_host.shape)
+                h["fmap_shape"] = (tuple(fmap_host.shape), fmap_host.dtype)
                 h["fmap_pin"] = fmap_host if fmap_host.is_pinned() else torch.empty_like(fmap_host).pin_memory()
-                h["fmap_dev"] = torch.empty(fmap_host.shape, dtype=fmap_host.dtype, device=dev)
+                h["fmap_dev"] = (self._frame_buffer(tuple(fmap_host.shape), dev, 0) if fmap_host.dtype == torch.uint8
+                                 else torch.empty(fmap_host.shape, dtype=fmap_host.dtype, device=dev))
             self._host = h
         h["imu_pin"].copy_(imu_host[:, 0, :live] if imu_host.dim() == 3 else imu_host[:, :live])
         h["imu_dev"].copy_(h["imu_pin"], non_blocking=True)
@@ -199,6 +230,8 @@ class CrossModalOODPipeline:
                 src = h["fmap_pin"]
             h["fmap_dev"].copy_(src, non_blocking=True)
             fdev = h["fmap_dev"]
+            if fdev.dtype == torch.uint8:                    # decoded frames: normalise + trunk on the device
+                fdev = self._frames_to_map(fdev, 0)
         out = self.run(h["imu_dev"], fdev, window_stride=live)
         h["pred_pin"].copy_(out["pred"], non_blocking=True)
         h["res_pin"][0].copy_(out["msp"], non_blocking=True)
@@ -273,7 +306,8 @@ class CrossModalOODPipeline:
                           up=torch.cuda.Event(), done=torch.cuda.Event())
                 if fmap_host is not None:
                     sl["fmap_pin"] = torch.empty_like(fmap_host).pin_memory()
-                    sl["fmap_dev"] = torch.empty(fmap_host.shape, dtype=fmap_host.dtype, device=dev)
+                    sl["fmap_dev"] = (self._frame_buffer(tuple(fmap_host.shape), dev, i % depth) if fmap_host.dtype == torch.uint8
+                                      else torch.empty(fmap_host.shape, dtype=fmap_host.dtype, device=dev))
             sl["imu_pin"].copy_(imu_host[:, 0, :live] if imu_host.dim() == 3 else imu_host[:, :live])
             if fmap_host is None and graphs:
                 if sl.get("graph") is None or sl.get("generation") != pack_generation():      # weights re-packed: re-record
@@ -320,6 +354,8 @@ class CrossModalOODPipeline:
                     fdev = sl["fmap_dev"]
                 sl["up"].record(copy)
             main.wait_event(sl["up"])
+            if fdev is not None and fdev.dtype == torch.uint8:       # decoded frames: normalise + trunk graph of this ring slot
+                fdev = self._frames_to_map(fdev, i % depth)
             out = self.run(sl["imu_dev"], fdev, window_stride=live)
             sl["pred_pin"].copy_(out["pred"], non_blocking=True)
             sl["res_pin"][0].copy_(out["msp"], non_blocking=True)

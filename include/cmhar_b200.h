@@ -324,6 +324,21 @@ int cmhar_video_pool_frames_img(const void* fmap, int32_t fmap_is_bf16, int64_t 
 int cmhar_video_pool_coresident(const void* fmap, int32_t is_bf16, int64_t n, int32_t frames, int32_t channels,
                                 int32_t hw, float* pooled, cmhar_stream_t s);
 
+/* ---- video trunk on the device: the two kernels either side of the channels-last bf16 trunk -------------- */
+/* ToTensor + Normalize of the reference's per-frame transform (src/data/datasets.py:52-58: x/255, (x - mean) / std) on the
+ * device: frames_u8 = n_pixels interleaved RGB pixels (decoded HWC frames, any number of frames back to back) ->
+ * out_bf16 = n_pixels x cpad bf16 (channels-last pixels; cpad 3, 4 or 8, channels >= 3 are zero so that the first
+ * convolution can run with padded input channels).  mean3 / std3 are HOST pointers to three floats.  Same fp32
+ * operation order as torch, one rounding to bf16. */
+int cmhar_frames_normalize(const uint8_t* frames_u8, int64_t n_pixels, const float* mean3, const float* std3, int32_t cpad,
+                           void* out_bf16, cmhar_stream_t s);
+/* cmhar_video_pool_frames_img for a CHANNELS-LAST feature map -- physical layout (n*frames, hw, channels), what a
+ * channels-last trunk writes (reference models.py:209 output, permuted) -- so that no NCHW copy of the map is made:
+ * pooled (n, channels) fp32, pooled_img / frame_img bf16 operand images; any of the three may be NULL (not all).
+ * Needs a 16-byte aligned map and channels % 8 == 0 (bf16) / % 4 == 0 (fp32); images need channels % 64 == 0. */
+int cmhar_video_pool_nhwc(const void* fmap, int32_t fmap_is_bf16, int64_t n, int32_t frames, int32_t channels, int32_t hw,
+                          float* pooled, void* pooled_img, void* frame_img, cmhar_stream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * Contrastive similarity (replaces SigmoidContrastiveLoss.forward / InfoNCELoss.forward,
  *                         reference src/models/losses.py:25-54,67-87)
