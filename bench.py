@@ -443,8 +443,9 @@ def workload_sharded_similarity(cm, cfg, clf, xm, dev, rank, world, barrier, dis
 def workload_mahalanobis(cm, dev, rank, world, barrier, dist, precision, n_rows, peaks):
     """BASELINE configs[3]: Mahalanobis class-mean / tied-covariance fit with the NCCL all-reduce of the statistics INSIDE the
     timed region, then `n_rows` test rows scored, per GPU (weak scaling: every rank owns its shard of stored 128-d features).
-    One step = accumulate (tensor-core GEMMs over the rows) -> all-reduce of 20 512 doubles -> host fp64 Cholesky + pack ->
-    score (streaming GEMM + per-row reduction)."""
+    One step = accumulate (tensor-core GEMMs over the rows) -> all-reduce of 20 512 doubles -> device fp64 finalisation (means,
+    tied covariance, Cholesky, whitening factor: cmhar_maha_finalize) + pack, all stream-ordered, one status word read back ->
+    score (streaming GEMM + per-row reduction).  The host fp64 finalisation it replaced is timed beside it."""
     import torch
     g = torch.Generator(device=dev).manual_seed(99)
     mu = 2.0 * torch.randn(32, 128, device=dev, generator=g)               # same class means on every rank
@@ -462,8 +463,8 @@ def workload_mahalanobis(cm, dev, rank, world, barrier, dist, precision, n_rows,
         ev[0].record(stream)
         m.accumulate(feats, y, precision=precision)
         ev[1].record(stream)
-        m.finalize()                          # NCCL all-reduce + D2H + host fp64 Cholesky (synchronises)
-        m.blob(dev)                           # pack the scorer state
+        m.finalize()                          # NCCL all-reduce + device finalisation + pack (reads one status word: synchronises)
+        m.blob(dev)                           # (already packed by the device route)
         ev[2].record(stream)
         sc = m.score(test, precision=precision)
         ev[3].record(stream)
@@ -476,6 +477,16 @@ def workload_mahalanobis(cm, dev, rank, world, barrier, dist, precision, n_rows,
             for k, v in zip(rec, t.tolist()):
                 rec[k].append(v)
     med = {k: _median(v) for k, v in rec.items()}
+    # the host route of the same finalisation (D2H of the statistics, numpy Cholesky + LAPACK triangular inverse, H2D, pack), for comparison
+    host_ms = []
+    for _ in range(5):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        m.finalize(on_device=False)
+        m.blob(dev)
+        torch.cuda.synchronize(dev)
+        host_ms.append((time.perf_counter() - t0) * 1e3)
+    m.finalize()
     # the collective alone (device time of the all-reduce of the statistics buffer)
     coll_ms = 0.0
     if world > 1:
@@ -497,6 +508,8 @@ def workload_mahalanobis(cm, dev, rank, world, barrier, dist, precision, n_rows,
             "metric": "rows fitted and scored / s", "scaling": "weak", "value": world * n_rows / (med["total"] * 1e-3), "ms_per_step": med["total"],
             "rows_per_gpu": n_rows, "steps": len(rec["total"]),
             "breakdown_ms": {"accumulate": med["accumulate"], "allreduce_finalize_pack": med["allreduce_finalize"], "score": med["score"]},
+            "finalisation": {"route": "device: cmhar_maha_finalize (one fp64 CTA) + cmhar_maha_pack on the stream, 4-byte status read",
+                             "host_route_ms": _median(host_ms), "note": "host route = D2H of the statistics + numpy Cholesky + LAPACK dtrtri + H2D + pack (incl. the all-reduce)"},
             "collective": {"op": "all_reduce(SUM) of 20 512 doubles (164 KB), torch.distributed NCCL", "ms": coll_ms,
                            "share_of_step": coll_ms / med["total"] if med["total"] else None},
             "roofline": {"maha_fit_tc_kernel": {"bound": "hbm", "launch_ms": acc_ms, "achieved": acc_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": acc_gbs / peaks["hbm_gbs"],

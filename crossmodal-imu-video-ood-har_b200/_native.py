@@ -140,6 +140,8 @@ _SIGNATURES = {
     "cmhar_similarity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
                                    C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "cmhar_maha_fit64_doubles": (C.c_size_t, [C.c_int32]),
+    "cmhar_maha_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmhar_maha_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int32, C.c_void_p]),
     "cmhar_maha_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),

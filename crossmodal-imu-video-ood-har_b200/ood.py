@@ -102,8 +102,25 @@ class MahalanobisOOD:
     def reset(self):
         n = self.num_classes * (1 + FEAT_DIM) + FEAT_DIM * FEAT_DIM
         self._stats = torch.zeros(n, dtype=torch.float64, device=self.device)   # one buffer -> one all-reduce
-        self.fit_: Optional[Dict[str, np.ndarray]] = None
+        self._fit: Optional[Dict[str, np.ndarray]] = None
+        self._fit_dev: Optional[Dict[str, torch.Tensor]] = None     # device finalisation: fit64 + the fp32 inputs of cmhar_maha_pack
         self._blobs: Dict[str, torch.Tensor] = {}
+
+    @property
+    def fit_(self) -> Optional[Dict[str, np.ndarray]]:
+        """The fitted state as host fp64 arrays (mean, cov, whiten, mean_whitened, count); after a device finalisation it is
+        read back on first access only (the scorer itself never needs it on the host)."""
+        if self._fit is None and self._fit_dev is not None:
+            c, d = self.num_classes, FEAT_DIM
+            f = self._fit_dev["fit64"].cpu().numpy()
+            o = [0, c * d, c * d + d * d, c * d + 2 * d * d, 2 * c * d + 2 * d * d]
+            self._fit = {"mean": f[o[0]:o[1]].reshape(c, d), "cov": f[o[1]:o[2]].reshape(d, d), "whiten": f[o[2]:o[3]].reshape(d, d),
+                         "mean_whitened": f[o[3]:o[4]].reshape(c, d), "count": self._fit_dev["count64"].cpu().numpy()}
+        return self._fit
+
+    @fit_.setter
+    def fit_(self, value):
+        self._fit, self._fit_dev = value, None
 
     def _views(self):
         c = self.num_classes
@@ -125,13 +142,23 @@ class MahalanobisOOD:
                                                   cnt.data_ptr(), ssum.data_ptr(), second.data_ptr(),
                                                   _prec(precision), N.stream_ptr(f.device)))
 
-    def finalize(self, all_reduce: bool = True) -> "MahalanobisOOD":
+    def finalize(self, all_reduce: bool = True, on_device: Optional[bool] = None, check: bool = True) -> "MahalanobisOOD":
         """``all_reduce=False`` keeps the fit local to this rank (a scorer fitted on replicated data, or code that only
-        one rank executes -- a collective entered by a single rank would hang the others)."""
+        one rank executes -- a collective entered by a single rank would hang the others).
+
+        ``on_device`` (default: whenever the statistics live on a CUDA device and classes <= 64): means, tied covariance, Cholesky
+        factor, whitening matrix and the packed scorer state are produced by ``cmhar_maha_finalize`` + ``cmhar_maha_pack`` on the
+        current stream, right behind the accumulate kernels and the NCCL all-reduce -- no statistics cross PCIe and nothing
+        synchronises except the read of one status word (``check``; False leaves even that to the caller: ``finalize_status()``).
+        ``on_device=False`` is the host fp64 route (numpy / LAPACK), identical algebra."""
         stats = self._stats
         if all_reduce and _dist_on():
             stats = stats.clone()
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)       # 20 512 doubles over NCCL/NVLink
+        if on_device is None:
+            on_device = stats.is_cuda and self.num_classes <= 64
+        if on_device:
+            return self._finalize_device(stats, check)
         host = stats.cpu().numpy()
         c = self.num_classes
         self.fit_ = finalize_mahalanobis(host[:c], host[c:c + c * FEAT_DIM].reshape(c, FEAT_DIM),
@@ -141,15 +168,50 @@ class MahalanobisOOD:
         _PACK_GENERATION[0] += 1          # a re-fit replaces the packed scorer state recorded graphs point into
         return self
 
+    def _finalize_device(self, stats: torch.Tensor, check: bool) -> "MahalanobisOOD":
+        N.require_cuda(stats, "MahalanobisOOD.finalize(on_device=True)")
+        lib, dev, c = N.lib(), stats.device, self.num_classes
+        fit64 = torch.empty(lib.cmhar_maha_fit64_doubles(c), dtype=torch.float64, device=dev)
+        w32 = torch.empty((FEAT_DIM, FEAT_DIM), dtype=torch.float32, device=dev)
+        mw32 = torch.empty((c, FEAT_DIM), dtype=torch.float32, device=dev)
+        cnt32 = torch.empty(c, dtype=torch.float32, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        blob = N.alloc_blob(lib.cmhar_maha_blob_bytes(c), dev)
+        with torch.cuda.device(dev):
+            st = N.stream_ptr(dev)
+            N.check(lib.cmhar_maha_finalize(stats.data_ptr(), c, float(self.ridge), fit64.data_ptr(), w32.data_ptr(), mw32.data_ptr(),
+                                            cnt32.data_ptr(), info.data_ptr(), st))
+            N.check(lib.cmhar_maha_pack(w32.data_ptr(), mw32.data_ptr(), cnt32.data_ptr(), c, blob.data_ptr(), st))
+        self._fit, self._blobs = None, {str(dev): blob}
+        self._fit_dev = {"fit64": fit64, "count64": stats[:c].clone(), "w32": w32, "mw32": mw32, "cnt32": cnt32, "info": info}
+        from .models import _PACK_GENERATION
+        _PACK_GENERATION[0] += 1          # a re-fit replaces the packed scorer state recorded graphs point into
+        if check:
+            self.finalize_status()
+        return self
+
+    def finalize_status(self) -> int:
+        """Status word of the last device finalisation (one 4-byte D2H read; synchronises).  Raises like the host route."""
+        if self._fit_dev is None:
+            return 0
+        code = int(self._fit_dev["info"].item())
+        if code == -1:
+            self._fit_dev, self._blobs = None, {}
+            raise ValueError("Mahalanobis fit saw no labelled rows")
+        if code != 0:
+            self._fit_dev, self._blobs = None, {}
+            raise np.linalg.LinAlgError(f"Mahalanobis fit: covariance not positive definite (pivot {code}); use a ridge")
+        return code
+
     def fit(self, feats: torch.Tensor, labels: torch.Tensor, all_reduce: bool = True) -> "MahalanobisOOD":
         self.reset()
         self.accumulate(feats, labels)
         return self.finalize(all_reduce=all_reduce)
 
     def blob(self, device) -> torch.Tensor:
-        if self.fit_ is None:
+        if self._fit is None and self._fit_dev is None:
             raise RuntimeError("MahalanobisOOD: call fit()/finalize() first")
-        key = str(device)
+        key = str(torch.device(device))
         if key not in self._blobs:
             lib = N.lib()
             w = torch.from_numpy(self.fit_["whiten"].astype(np.float32)).to(device).contiguous()

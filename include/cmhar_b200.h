@@ -400,6 +400,17 @@ int cmhar_peer_barrier(void* const* flag_blocks, int32_t rank, int32_t world, vo
  * CMHAR_FP32: fp32 FMA register tiles flushed into fp64. */
 int cmhar_maha_accumulate(const float* feat, const int64_t* labels, int64_t n, int32_t classes,
                           double* count, double* sum, double* second, int32_t precision, cmhar_stream_t s);
+/* Finalisation of the fit ON THE DEVICE, stream-ordered behind the accumulate calls and the NCCL all-reduce (no host round trip):
+ * stats = [count (classes) | sum (classes,128) | second (128,128)] doubles, contiguous, as accumulated above ->
+ *   fit64 (cmhar_maha_fit64_doubles(classes) doubles) = [mean (classes,128) | cov (128,128) | whiten (128,128) | mean_whitened (classes,128)]
+ *   with cov = (second - sum_c n_c mu_c mu_c^T) / N, symmetrised, + ridge I; cov = G G^T (Cholesky); whiten = G^-T
+ *   whiten_f32 / mean_w_f32 / count_f32: the fp32 inputs of cmhar_maha_pack, which may follow on the same stream
+ *   info (device int32): 0 = ok, k > 0 = pivot k of the Cholesky factorisation is not positive, -1 = no labelled rows.
+ * One fp64 CTA (~0.1 ms); classes <= 64.  Same algebra as the host finalisation it replaces (ood.finalize_mahalanobis, spec oracle
+ * oracle/ood_spec.py); no reference implementation exists. */
+size_t cmhar_maha_fit64_doubles(int32_t classes);
+int cmhar_maha_finalize(const double* stats, int32_t classes, double ridge, double* fit64, float* whiten_f32,
+                        float* mean_w_f32, float* count_f32, int32_t* info, cmhar_stream_t s);
 /* score (n) = min_c || feat@whiten - mean_whitened_c ||^2.  CMHAR_BF16: whitening and class-mean products as
  * split-bf16 tcgen05 MMAs (fp32-grade, see cmhar_head_forward) when classes <= 32; CMHAR_FP32: fp32 FMA. */
 int cmhar_maha_score(const void* maha_blob, const float* feat, int64_t n, float* score, int32_t precision,
