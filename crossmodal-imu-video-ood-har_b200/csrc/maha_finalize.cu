@@ -3,7 +3,7 @@
 // leaving the stream: class means, tied covariance Sigma = (sum f f^T - sum_c n_c mu_c mu_c^T) / N (+ ridge I), Cholesky
 // Sigma = G G^T, whitening factor W = G^-T (so that d_c(f) = |f W - mu_c W|^2) and the whitened means mu_c W -- the algebra of
 // ood.finalize_mahalanobis / oracle/ood_spec.py (host fp64), which took 0.8 of the 1.13 ms of a configs[3] step (D2H of the statistics,
-// numpy Cholesky + LAPACK triangular inverse, H2D of the factors, two stream synchronisations).  Here it is one fp64 CTA, ~0.1 ms,
+// numpy Cholesky + LAPACK triangular inverse, H2D of the factors, two stream synchronisations).  Here it is one fp64 CTA,
 // followed on the same stream by cmhar_maha_pack's kernels; the host reads back one status word.
 // No reference implementation exists for this stage: parity unpinned, spec oracle = oracle/ood_spec.py.
 #include "common.cuh"
@@ -27,93 +27,167 @@ __global__ void __launch_bounds__(NT, 1) maha_finalize_kernel(const double* __re
     double* mean = A + (size_t)D * LD;
     double* diag = mean + (size_t)C * D;
     int* fail = reinterpret_cast<int*>(diag + D);
-    const int tid = threadIdx.x;
-    const double* count = stats;
+    __shared__ double cnt[MAX_C];
+    __shared__ double total_s;
+    const int tid = threadIdx.x, row = tid >> 3, l8 = tid & 7;      // covariance phase: 8 lanes per matrix row
     const double* ssum = stats + C;
     const double* second = stats + C + (size_t)C * D;
     if (tid == 0) *fail = 0;
-    double total = 0.0;
-    for (int c = 0; c < C; ++c) total += count[c];            // every thread: C <= 64 loads from L2
+    if (tid < C) { cnt[tid] = stats[tid]; count_f32[tid] = (float)stats[tid]; }
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int c = 0; c < C; ++c) t += cnt[c]; total_s = t; }
     for (int e = tid; e < C * D; e += NT) {
-        const int c = e / D;
-        const double m = ssum[e] / fmax(count[c], 1.0);
+        const double m = ssum[e] / fmax(cnt[e / D], 1.0);
         mean[e] = m;
         fit64[e] = m;
     }
-    if (tid < C) count_f32[tid] = (float)count[tid];
     __syncthreads();
+    const double total = total_s;
     if (!(total > 0.0)) {                                       // no labelled rows: nothing to factor
         if (tid == 0) *info = -1;
         return;
     }
-    // covariance, symmetrised, lower triangle incl. diagonal into A; the full matrix into fit64
+    // covariance, symmetrised: lower triangle incl. diagonal into A, the full matrix into fit64.  Row `row`, columns l8, l8 + 8, ...
     double* cov_out = fit64 + (size_t)C * D;
-    for (int e = tid; e < D * D; e += NT) {
-        const int i = e / D, j = e - i * D;
-        if (j > i) continue;
-        double s = 0.5 * (second[(size_t)i * D + j] + second[(size_t)j * D + i]);
+    for (int j = l8; j <= row; j += 8) {
+        const int i = row;
         double corr = 0.0;
-        for (int c = 0; c < C; ++c) corr += count[c] * mean[c * D + i] * mean[c * D + j];
-        double v = (s - corr) / total;
+        for (int c = 0; c < C; ++c) corr += cnt[c] * mean[c * D + i] * mean[c * D + j];
+        double v = (0.5 * (second[(size_t)i * D + j] + second[(size_t)j * D + i]) - corr) / total;
         if (i == j) v += ridge;
         A[i * LD + j] = v;
         cov_out[(size_t)i * D + j] = v;
         cov_out[(size_t)j * D + i] = v;
     }
     __syncthreads();
-    // right-looking Cholesky on the lower triangle: G below the diagonal, its diagonal in diag[]
-    for (int k = 0; k < D; ++k) {
-        if (tid == 0) {
-            const double d = A[k * LD + k];
-            if (!(d > 0.0)) { if (*fail == 0) *fail = k + 1; diag[k] = 1.0; }       // not positive definite: reported, loop finishes harmlessly
-            else diag[k] = sqrt(d);
-        }
-        __syncthreads();
-        const double dk = diag[k];
-        for (int i = k + 1 + tid; i < D; i += NT) A[i * LD + k] /= dk;
-        __syncthreads();
-        const int m = D - 1 - k;                                // trailing block rows / columns k+1 .. 127
-        for (int e = tid; e < m * m; e += NT) {
-            const int i = k + 1 + e / m, j = k + 1 + e % m;
-            if (j <= i) A[i * LD + j] -= A[i * LD + k] * A[j * LD + k];
-        }
-        __syncthreads();
-    }
-    // W = G^-T, upper triangle incl. diagonal of A: thread j solves G x = e_j by forward substitution, x_i = W[j][i] (row j of the upper
-    // triangle is this thread's alone; the strictly lower triangle and diag[] are read-only now)
-    if (tid < D) {
-        const int j = tid;
-        A[j * LD + j] = 1.0 / diag[j];
-        for (int i = j + 1; i < D; ++i) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int k = j;
-            for (; k + 3 < i; k += 4) {
-                s0 += A[i * LD + k] * A[j * LD + k];
-                s1 += A[i * LD + k + 1] * A[j * LD + k + 1];
-                s2 += A[i * LD + k + 2] * A[j * LD + k + 2];
-                s3 += A[i * LD + k + 3] * A[j * LD + k + 3];
+    // Cholesky-Crout, column by column: G[i][k] = (A[i][k] - sum_{p<k} G[i][p] G[k][p]) / G[k][k] for all rows i >= k at once.
+    // G's strictly lower triangle stays in A, 1 / G[k][k] in diag[] (reciprocal square root: no fp64 division on the critical path).
+    // This phase is bound by the NUMBER of instructions one SM issues (ncu: 0.36 IPC per scheduler, fp64 pipe 12 % busy), so it runs on
+    // 256 threads -- two lanes per row, one shuffle per column -- with exact trip counts: 8 lanes per row and predicated fixed-length
+    // dot products cost 313 K warp instructions, three times as many.  A warp whose 16 rows lie above column k leaves the loop; the two
+    // barriers per column are named barriers counted over the warps still in it.
+    if (tid < 256) {
+        const int r2 = tid >> 1, h = tid & 1, w8 = tid >> 5;
+        const double* rowp = A + r2 * LD;
+        for (int k = 0; k < D; ++k) {
+            if ((k >> 4) > w8) break;
+            const unsigned live = 32u * (unsigned)(8 - (k >> 4));
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            if (r2 >= k) {
+                const double* rk = A + k * LD;
+                int p = h;
+                for (; p + 6 < k; p += 8) {
+                    a0 = fma(rowp[p], rk[p], a0); a1 = fma(rowp[p + 2], rk[p + 2], a1);
+                    a2 = fma(rowp[p + 4], rk[p + 4], a2); a3 = fma(rowp[p + 6], rk[p + 6], a3);
+                }
+                for (; p < k; p += 2) a0 = fma(rowp[p], rk[p], a0);
             }
-            for (; k < i; ++k) s0 += A[i * LD + k] * A[j * LD + k];
-            // careful: A[i][k] with k < i is G (lower); A[j][k] with k >= j is this thread's x_k (upper, row j)
-            A[j * LD + i] = -((s0 + s1) + (s2 + s3)) / diag[i];
+            double part = (a0 + a1) + (a2 + a3);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);      // every lane of the warp takes part (rows above k add zeros)
+            double v = 0.0;
+            if (r2 >= k) {
+                v = rowp[k] - part;
+                if (r2 == k && h == 0) {
+                    if (!(v > 0.0)) { if (*fail == 0) *fail = k + 1; diag[k] = 1.0; }      // not positive definite: reported, the loop finishes harmlessly
+                    else diag[k] = rsqrt(v);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(live) : "memory");
+            if (r2 > k && h == 0) A[r2 * LD + k] = v * diag[k];
+            asm volatile("bar.sync 1, %0;" ::"r"(live) : "memory");
         }
     }
     __syncthreads();
-    // outputs: whiten[k][j] = W[k][j] = x^{(j)}_k ... stored above as A[j][i] = x^{(j)}_i, i.e. A[j][i] = (G^-1)[i][j] = W[j][i]
+    // X = G^-1 by recursive doubling, stored transposed (W = X^T = G^-T) in the upper triangle incl. diagonal of A: X[i][j] lives at
+    // A[j][i].  With X11 = inv(G11), X22 = inv(G22) of two adjacent b x b diagonal blocks, the block below them is
+    // X21 = -X22 (G21 X11): two small products per level, 7 levels -- a dependent chain of ~100 fp64 operations, where forward substitution
+    // column by column has 127 steps of ~13 (dependent fp64 operations cost ~50 cycles each here: that route measured 170 K cycles).
+    if (tid < D) A[tid * LD + tid] = diag[tid];
+    __syncthreads();
+    for (int lb = 0; lb < 7; ++lb) {
+        const int bsz = 1 << lb, outs = 64 << lb;               // (64 / b) pairs x b^2 elements
+        // T = G21 X11 into X21's place: T[r][c] = sum_{q=c}^{b-1} G[o+b+r][o+q] X[o+q][o+c]
+        double t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * NT;
+            t[u] = 0.0;
+            if (e < outs) {
+                const int pair = e >> (2 * lb), rem = e & (bsz * bsz - 1), r = rem >> lb, c = rem & (bsz - 1), o = pair << (lb + 1);
+                const double* g = A + (o + bsz + r) * LD + o;   // G row, contiguous in q
+                const double* x = A + (o + c) * LD + o;         // X column c of X11 = row o + c of the upper triangle, contiguous in q
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int q = c;
+                for (; q + 3 < bsz; q += 4) { a0 = fma(g[q], x[q], a0); a1 = fma(g[q + 1], x[q + 1], a1); a2 = fma(g[q + 2], x[q + 2], a2); a3 = fma(g[q + 3], x[q + 3], a3); }
+                for (; q < bsz; ++q) a0 = fma(g[q], x[q], a0);
+                t[u] = (a0 + a1) + (a2 + a3);
+            }
+        }
+        __syncthreads();                                        // (nothing read above is written below, but keep the phases apart)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * NT;
+            if (e < outs) {
+                const int pair = e >> (2 * lb), rem = e & (bsz * bsz - 1), r = rem >> lb, c = rem & (bsz - 1), o = pair << (lb + 1);
+                A[(o + c) * LD + (o + bsz + r)] = t[u];
+            }
+        }
+        __syncthreads();
+        // X21[r][c] = -sum_{q=0}^{r} X[o+b+r][o+b+q] T[q][c]
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * NT;
+            t[u] = 0.0;
+            if (e < outs) {
+                const int pair = e >> (2 * lb), rem = e & (bsz * bsz - 1), r = rem >> lb, c = rem & (bsz - 1), o = pair << (lb + 1);
+                const double* x22 = A + (o + bsz) * LD + (o + bsz + r);      // X[o+b+r][o+b+q] = A[(o+b+q)][o+b+r]: stride LD in q
+                const double* tt = A + (o + c) * LD + (o + bsz);             // T[q][c], contiguous in q
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int q = 0;
+                for (; q + 3 <= r; q += 4) {
+                    a0 = fma(x22[q * LD], tt[q], a0); a1 = fma(x22[(q + 1) * LD], tt[q + 1], a1);
+                    a2 = fma(x22[(q + 2) * LD], tt[q + 2], a2); a3 = fma(x22[(q + 3) * LD], tt[q + 3], a3);
+                }
+                for (; q <= r; ++q) a0 = fma(x22[q * LD], tt[q], a0);
+                t[u] = -((a0 + a1) + (a2 + a3));
+            }
+        }
+        __syncthreads();                                        // every T has been read before any X21 overwrites it
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * NT;
+            if (e < outs) {
+                const int pair = e >> (2 * lb), rem = e & (bsz * bsz - 1), r = rem >> lb, c = rem & (bsz - 1), o = pair << (lb + 1);
+                A[(o + c) * LD + (o + bsz + r)] = t[u];
+            }
+        }
+        __syncthreads();
+    }
+    // outputs: whiten[r][c] = W[r][c] = A[r][c] for c >= r (upper triangular), 0 below
     double* whiten_out = fit64 + (size_t)C * D + (size_t)D * D;
     for (int e = tid; e < D * D; e += NT) {
         const int r = e / D, c2 = e - r * D;
-        const double w = (c2 >= r) ? A[r * LD + c2] : 0.0;     // W is upper triangular
+        const double w = (c2 >= r) ? A[r * LD + c2] : 0.0;
         whiten_out[e] = w;
         whiten_f32[e] = (float)w;
     }
     double* mw_out = whiten_out + (size_t)D * D;
     for (int e = tid; e < C * D; e += NT) {
         const int c = e / D, j = e - c * D;
-        double s = 0.0;
-        for (int k = 0; k <= j; ++k) s += mean[c * D + k] * A[k * LD + j];
-        mw_out[e] = s;
-        mean_w_f32[e] = (float)s;
+        double acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+        const double* mrow = mean + c * D;
+        const double* wcol = A + j;
+        int k = 0;
+        for (; k + 7 <= j; k += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = fma(mrow[k + u], wcol[(k + u) * LD], acc[u]);
+        }
+        for (; k <= j; ++k) acc[0] = fma(mrow[k], wcol[k * LD], acc[0]);
+        const double sum = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        mw_out[e] = sum;
+        mean_w_f32[e] = (float)sum;
     }
     __syncthreads();
     if (tid == 0) *info = *fail;
