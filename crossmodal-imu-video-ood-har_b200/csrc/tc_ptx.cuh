@@ -150,6 +150,13 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
                  : "r"(addr)                                                                                      \
                  : "memory")
 
+#define TMEM_LD16(addr, v)                                                                                        \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+                 : "r"(addr)                                                                                      \
+                 : "memory")
+
 #define TMEM_ST32(addr, v)                                                                                        \
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                  \
                  "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26," \
