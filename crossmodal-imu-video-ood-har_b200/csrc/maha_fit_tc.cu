@@ -33,7 +33,8 @@ constexpr int OFF_CNT = 2 * BUF;                   // int counters [128]
 constexpr int OFF_BAR = OFF_CNT + 512;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 enum { B_STAGED = 0, B_FREE = 2, B_ACC = 4, B_DRAINED = 5, B_COUNT = 6 };
-constexpr int NSW = 8;                             // staging warps (8 or 16; 16 warps of 8 rows each measured 277 us against 258 us for 2 M rows).
+constexpr int NSW = 8;                             // staging warps (8 or 16; 16 warps of 8 rows each: 226 / 125 us against 218 / 130 us for 2 M / 1 M rows,
+                                                   // 96 registers and spills).
                                                    // 9 warps = 3 on one scheduler: 16 384 / 96 = 168 registers per thread is the ceiling
 constexpr int RPW = 128 / NSW;                     // rows per staging warp
 constexpr int LPR = 32 / RPW;                      // lanes per row of the one-hot tile, 8 / LPR pieces each

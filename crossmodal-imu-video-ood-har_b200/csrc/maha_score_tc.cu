@@ -88,28 +88,40 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
     return v;
 }
 
-// convert this warp's rows of one tile (registers t) into the hi / lo A tiles of buffer `abuf`
+// convert this warp's rows of one tile (registers t) into the hi / lo A tiles of buffer `abuf`.
+// The staging warps are bound by the number of instructions they issue (two warps per scheduler; measured on the fit kernel, which
+// stages the same way: 940 instructions per thread and tile, half of them address arithmetic and predicates), so: row0 is a multiple
+// of 8, which makes the SW128 offset a per-thread constant + a compile-time function of j + one XOR; the hi halves are unpacked with
+// a shift and a mask; full tiles load with immediate offsets and no predicates.
 template <int ROWS>
 __device__ __forceinline__ void stage_rows(const float4 (&t)[ROWS], uint8_t* abuf, int row0, int piece, int sub) {
+    uint8_t* base = abuf + (row0 >> 3) * 1024 + sub;
+    const uint32_t p4 = (uint32_t)piece << 4;
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) {
         const float4 x = t[j];
         const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
-        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-        const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
-        const uint32_t off = sw128_off(row0 + j, piece) + sub;
-        *reinterpret_cast<uint2*>(abuf + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-        *reinterpret_cast<uint2*>(abuf + 2 * ACH + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+        const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __uint_as_float(u01 << 16), x.y - __uint_as_float(u01 & 0xffff0000u));
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __uint_as_float(u23 << 16), x.w - __uint_as_float(u23 & 0xffff0000u));
+        uint8_t* dst = base + ((j >> 3) * 1024 + (j & 7) * 128) + (p4 ^ (uint32_t)((j & 7) << 4));
+        *reinterpret_cast<uint2*>(dst) = make_uint2(u01, u23);
+        *reinterpret_cast<uint2*>(dst + 2 * ACH) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
     }
 }
 // this warp's rows of a tile -> registers: src = address of (first row, this lane's 4 elements); rows past
 // `valid` read as zero
 template <int ROWS>
 __device__ __forceinline__ void load_rows(float4 (&t)[ROWS], const float* __restrict__ src, int valid) {
+    if (valid >= ROWS) {
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) {
-        t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < valid) t[j] = ld_stream(src + j * D);
+        for (int j = 0; j < ROWS; ++j) t[j] = ld_stream(src + j * D);
+    } else {
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < valid) t[j] = ld_stream(src + j * D);
+        }
     }
 }
 
@@ -172,33 +184,29 @@ __global__ void __launch_bounds__(Roles<GROUPS, MERGED>::NT, 1) maha_score_tc_ke
                 l2_prefetch_bulk(feat + (size_t)tl * (128 * D), (uint32_t)((rows < 128 ? rows : 128) * D * 4));
             }
         };
-        if (pf_on && warp == 0 && lane == 0)
+        if (pf_on > 0 && warp == 0 && lane == 0)
             for (int a = 1; a < PF_AHEAD; ++a) prefetch_tile(tile + a * step);
         if (tile < ntiles) fetch(tile);
         for (int it = g; tile < ntiles; tile += step, it += GROUPS) {        // it = index within this CTA's tile sequence
             const int b = it & 1;                                    // A buffer == accumulator index of this tile
-            if (pf_on && warp == 0 && lane == 0) prefetch_tile(tile + PF_AHEAD * step);
+            if (pf_on > 0 && warp == 0 && lane == 0) prefetch_tile(tile + PF_AHEAD * step);
             mbar_wait(BAR(B_FREE + b), (uint32_t)(((it >> 1) & 1) ^ 1), 83);       // the MMAs that read this buffer are complete
             if (CFENCE) {
                 // consumer-side proxy fence: this warp never executes the MEMBAR, so the refill loads issued row by row
                 // right after each row is consumed stay in flight across the hand-off (a full tile of prefetch)
+                // (rows are refilled half a tile at a time, right after the half is converted and stored)
                 const bool more = tile + step < ntiles;
                 const long long left = more ? n - ((long long)(tile + step) * 128 + row0) : 0;
                 const int valid = left < ROWS_PER_WARP ? (int)left : ROWS_PER_WARP;
                 const float* nsrc = lane_src + (size_t)(tile + step) * (128 * D);
                 uint8_t* abuf = smem + OFF_A + b * ABUF + kc * ACH;
-#pragma unroll
-                for (int j = 0; j < ROWS_PER_WARP; ++j) {
-                    const float4 x = t[j];
-                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
-                    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-                    const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
-                    const uint32_t off = sw128_off(row0 + j, piece) + sub;
-                    *reinterpret_cast<uint2*>(abuf + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-                    *reinterpret_cast<uint2*>(abuf + 2 * ACH + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-                    t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j < valid) t[j] = ld_stream(nsrc + j * D);
-                }
+                constexpr int HR = ROWS_PER_WARP / 2;
+                float4 (&ta)[HR] = *reinterpret_cast<float4 (*)[HR]>(&t[0]);
+                float4 (&tb)[HR] = *reinterpret_cast<float4 (*)[HR]>(&t[HR]);
+                stage_rows<HR>(ta, abuf, row0, piece, sub);
+                load_rows<HR>(ta, nsrc, valid);
+                stage_rows<HR>(tb, abuf, row0 + HR, piece, sub);
+                load_rows<HR>(tb, nsrc + HR * D, valid - HR);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_STAGED + b));       // release: the warp's shared-memory stores are ordered before it
             } else {
