@@ -884,9 +884,14 @@ def main():
         feat = mu[torch.randint(0, 32, (n_feat,), device=dev, generator=g)] + torch.randn(n_feat, 128, device=dev, generator=g)
         sc = torch.empty(n_feat, device=dev)
         mblob = maha_alone.blob(dev)
+        yfeat = torch.randint(0, 32, (n_feat,), device=dev, generator=g)
+        st_cnt = torch.zeros(32, dtype=torch.float64, device=dev); st_sum = torch.zeros(32, 128, dtype=torch.float64, device=dev)
+        st_sec = torch.zeros(128, 128, dtype=torch.float64, device=dev)
         for name, fn, nbytes in (
                 ("logit_scores_ring_kernel", lambda: N.check(N.lib().cmhar_logit_scores(logits.data_ptr(), n_rows, 32, 1.0, pr.data_ptr(), s1.data_ptr(), s2.data_ptr(), N.stream_ptr(dev))), n_rows * (128 + 16)),
-                ("maha_score_tc_kernel", lambda: N.check(N.lib().cmhar_maha_score(mblob.data_ptr(), feat.data_ptr(), n_feat, sc.data_ptr(), N.BF16, N.stream_ptr(dev))), n_feat * (512 + 4))):
+                ("maha_score_tc_kernel", lambda: N.check(N.lib().cmhar_maha_score(mblob.data_ptr(), feat.data_ptr(), n_feat, sc.data_ptr(), N.BF16, N.stream_ptr(dev))), n_feat * (512 + 4)),
+                ("maha_fit_tc_kernel", lambda: N.check(N.lib().cmhar_maha_accumulate(feat.data_ptr(), yfeat.data_ptr(), n_feat, 32, st_cnt.data_ptr(), st_sum.data_ptr(), st_sec.data_ptr(),
+                                                                                      N.BF16, N.stream_ptr(dev))), n_feat * (512 + 8))):
             for _ in range(3):
                 fn()
             torch.cuda.synchronize(dev)

@@ -75,9 +75,18 @@ extern "C" {
 
 int cmhar_peer_alloc(size_t bytes, void** ptr_out) {
     CMHAR_REQUIRE(ptr_out && bytes > 0, "cmhar_peer_alloc: bad argument");
+    // Operand images inside the buffer must start on a 1 KiB boundary on EVERY rank that maps it.  cudaMalloc promises 256 bytes only
+    // (a 1 MiB + 1 KiB request came back 512-byte aligned once other allocations had moved the heap: the 2-GPU bench failed in
+    // cmhar_mlp2_forward_img); requests of whole 2 MiB pages are page aligned, locally and through cudaIpcOpenMemHandle.  Checked, not assumed.
+    const size_t page = (size_t)2 << 20;
+    const size_t rounded = (bytes + page - 1) / page * page;
     void* p = nullptr;
-    CMHAR_CHECK_CUDA(cudaMalloc(&p, bytes));
-    CMHAR_CHECK_CUDA(cudaMemset(p, 0, bytes));
+    CMHAR_CHECK_CUDA(cudaMalloc(&p, rounded));
+    if (((uintptr_t)p & 1023) != 0) {
+        cudaFree(p);
+        CMHAR_REQUIRE(false, "cmhar_peer_alloc: cudaMalloc(%zu) returned a pointer that is not 1 KiB aligned", rounded);
+    }
+    CMHAR_CHECK_CUDA(cudaMemset(p, 0, rounded));
     *ptr_out = p;
     return CMHAR_OK;
 }
@@ -102,6 +111,10 @@ int cmhar_peer_open(const void* handle, void** ptr_out) {
     memcpy(&h, handle, sizeof(h));
     void* p = nullptr;
     CMHAR_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    if (((uintptr_t)p & 1023) != 0) {
+        cudaIpcCloseMemHandle(p);
+        CMHAR_REQUIRE(false, "cmhar_peer_open: the mapping of the peer buffer is not 1 KiB aligned");
+    }
     *ptr_out = p;
     return CMHAR_OK;
 }
