@@ -65,6 +65,10 @@ class CrossModalOODPipeline:
 
     def _frame_buffer(self, shape, dev, slot: int) -> torch.Tensor:
         """Device landing buffer of a uint8 frame batch = the trunk graph's static input of ``slot`` (no second device copy)."""
+        if self.trunk is None:
+            raise RuntimeError("uint8 frames need the device trunk: call pipeline.attach_trunk() first")
+        if len(shape) < 4 or int(shape[-1]) != 3:
+            raise ValueError(f"frames must be uint8 (.., H, W, 3); got shape {tuple(shape)}")
         n = 1
         for d in shape[:-3]:
             n *= int(d)

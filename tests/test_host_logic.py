@@ -249,3 +249,27 @@ def test_held_out_activity_split_numpy_and_torch():
     assert idt.tolist() == idm.tolist() and oodt.tolist() == oodm.tolist()
     idm2, oodm2 = held_out_activity_split(y, [])
     assert oodm2.sum() == 0 and idm2.sum() == 7
+
+
+def test_mahalanobis_finalize_route_selection_on_cpu():
+    """Statistics on the CPU take the host fp64 route by default (what the gloo test relies on); asking for the device route on CPU
+    statistics fails loudly; `fit_` stays a plain dict of fp64 arrays; a failed fit leaves no blob behind."""
+    feats, labels = W.class_features(5, 3000)
+    m = cm.MahalanobisOOD(32, device="cpu", ridge=1e-3)
+    n, s, ff = ood_spec.mahalanobis_sufficient_stats(feats, labels, 32)
+    cnt, ssum, second = m._views()
+    cnt.copy_(torch.from_numpy(n)); ssum.copy_(torch.from_numpy(s)); second.copy_(torch.from_numpy(ff))
+    m.finalize(all_reduce=False)
+    assert m._fit_dev is None and m.finalize_status() == 0
+    spec = ood_spec.mahalanobis_fit(feats, labels, 32, ridge=1e-3)
+    np.testing.assert_allclose(m.fit_["mean"], spec["mean"], atol=1e-12)
+    np.testing.assert_allclose(m.fit_["cov"], spec["cov"], atol=1e-10)
+    w = m.fit_["whiten"]
+    np.testing.assert_allclose(w @ w.T @ m.fit_["cov"], np.eye(128), atol=1e-8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.finalize(all_reduce=False, on_device=True)
+    m.reset()
+    with pytest.raises(ValueError, match="no labelled rows"):
+        m.finalize(all_reduce=False)
+    with pytest.raises(RuntimeError, match="fit"):
+        m.blob("cpu")

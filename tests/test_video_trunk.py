@@ -219,3 +219,17 @@ def test_pipeline_from_frames_matches_pipeline_from_maps():
     assert len({int(o["pred"][0]) for o in outs} | {0}) >= 1
     hb = pipe.host_bytes_per_step(B, 250, batches[0])
     assert hb[0] == B * 240 * 4 + B * T * H * H * 3
+
+
+def test_pipeline_frames_need_an_attached_trunk():
+    """Host logic only: the frame entry points fail loudly before any device work when no trunk is attached / the layout is wrong."""
+    cfg = cm.default_config()
+    clf = cm.IMUClassifier(cm.IMUEncoder(cfg), cfg)
+    pipe = cm.CrossModalOODPipeline(clf, cm.CrossModalModel(cfg), None, frames=16)
+    with pytest.raises(RuntimeError, match="attach_trunk"):
+        pipe._frame_buffer((2, 16, 32, 32, 3), "cuda:0", 0)
+    with pytest.raises(RuntimeError, match="attach_trunk"):
+        pipe._frames_to_map(torch.zeros(2, 16, 32, 32, 3, dtype=torch.uint8))
+    pipe.trunk = object()
+    with pytest.raises(ValueError, match="H, W, 3"):
+        pipe._frame_buffer((2, 16, 3, 32, 32), "cuda:0", 0)
