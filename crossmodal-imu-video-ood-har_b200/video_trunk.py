@@ -211,6 +211,9 @@ class DeviceVideoTrunk:
 
     def normalize_into(self, frames_u8: torch.Tensor, x: torch.Tensor) -> None:
         """uint8 (n, h, w, 3) on the device -> the channels-last bf16 input ``x`` (n, cpad, h, w): cmhar_frames_normalize."""
+        if frames_u8.dtype != torch.uint8 or frames_u8.shape[-1] != 3 or not x.is_contiguous(memory_format=torch.channels_last) and x.shape[-1] != self.cpad:
+            raise ValueError("normalize_into: uint8 (.., H, W, 3) frames into a channels-last (n, cpad, H, W) bf16 buffer")
+        frames_u8 = frames_u8.contiguous()
         with torch.cuda.device(frames_u8.device):
             N.check(N.lib().cmhar_frames_normalize(frames_u8.data_ptr(), frames_u8.numel() // 3, self._mean, self._std, self.cpad,
                                                    x.data_ptr(), N.stream_ptr(frames_u8.device)))
