@@ -52,10 +52,39 @@ def _to_torch_sd(torch, sd):
     return {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
 
 
+def video_encoder_resnet18(torch, CONFIG, M):
+    """a4 WITH the reference's resnet18 trunk (src/models/models.py:163-167,208-216), random init: the module is constructed under
+    torch.manual_seed(seed_init) -- the tests construct theirs the same way, so no 45 MB state dict has to be stored -- and its
+    BatchNorm statistics are randomised from a numpy stream.  Records the output and the per-frame spatial means of the trunk's map."""
+    cfg = copy.deepcopy(CONFIG)
+    cfg.model.video_backbone = "resnet18"
+    cfg.model.video_pretrained = False
+    seed_init, seed_bn, seed_x, B, T, H = 1234, 71, 72, 2, 4, 64
+    torch.manual_seed(seed_init)
+    ve = M.VideoEncoder(cfg).eval()
+    rs = np.random.RandomState(seed_bn)
+    for m in ve.backbone.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.from_numpy((0.2 * rs.standard_normal(m.num_features)).astype(np.float32)))
+            m.running_var.copy_(torch.from_numpy((0.5 + rs.rand(m.num_features)).astype(np.float32)))
+            m.weight.data.copy_(torch.from_numpy((1.0 + 0.2 * rs.standard_normal(m.num_features)).astype(np.float32)))
+            m.bias.data.copy_(torch.from_numpy((0.1 * rs.standard_normal(m.num_features)).astype(np.float32)))
+    x = torch.from_numpy(np.random.RandomState(seed_x).standard_normal((B, T, 3, H, H)).astype(np.float32))
+    with torch.no_grad():
+        out = ve(x)
+        fmap = ve.backbone(x.view(B * T, 3, H, H))
+    np.savez_compressed(os.path.join(OUT, "video_encoder_resnet18.npz"), seed_init=seed_init, seed_bn=seed_bn, seed_x=seed_x, B=B, T=T, H=H,
+                        out=out.numpy(), frame_means=fmap.mean(dim=(2, 3)).numpy(), fmap_shape=np.array(fmap.shape))
+    print(f"video_encoder_resnet18: out absmax {out.abs().max():.4f}, map {tuple(fmap.shape)}")
+
+
 def main():
     sys.path.insert(0, REPO)
     from oracle import weights as W
     torch, CONFIG, M, LS, EV = _import_reference()
+    if "--only-trunk" in sys.argv:                          # add this fixture without rewriting the others
+        os.makedirs(OUT, exist_ok=True)
+        return video_encoder_resnet18(torch, CONFIG, M)
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(OUT, exist_ok=True)
@@ -153,6 +182,7 @@ def main():
         metrics=np.array([res["metrics"][k] for k in sorted(res["metrics"])], dtype=np.float64),
         m2_seed=26, m2=np.array([m2[k] for k in sorted(m2)], dtype=np.float64))
     print("evaluator:", res["metrics"])
+    video_encoder_resnet18(torch, CONFIG, M)
     print("wrote", sorted(os.listdir(OUT)))
 
 

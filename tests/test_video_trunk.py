@@ -233,3 +233,41 @@ def test_pipeline_frames_need_an_attached_trunk():
     pipe.trunk = object()
     with pytest.raises(ValueError, match="H, W, 3"):
         pipe._frame_buffer((2, 16, 3, 32, 32), "cuda:0", 0)
+
+
+def test_video_encoder_with_resnet18_trunk_vs_reference_golden(golden_dir):
+    """Row a4 WITH the reference's trunk (src/models/models.py:163-167,208-216): the golden holds the output of the UNMODIFIED reference
+    ``VideoEncoder`` constructed under a fixed torch seed (oracle/make_golden.py: video_encoder_resnet18).  This module built under the
+    same seed has the same parameters; its torch route (what the reference's trainers use) must give the reference's output, and the
+    BatchNorm-folded, channel-padded, epilogue-fused trunk that DeviceVideoTrunk runs on the device must reproduce the reference
+    trunk's map in fp32 (the bf16 device run is held to the eager trunk in the GPU test above)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "video_encoder_resnet18.npz"))
+    cfg = cm.default_config()
+    cfg.model.video_backbone, cfg.model.video_pretrained = "resnet18", False
+    torch.manual_seed(int(g["seed_init"]))
+    ve = cm.VideoEncoder(cfg).eval()
+    rs = np.random.RandomState(int(g["seed_bn"]))
+    for m in ve.backbone.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.from_numpy((0.2 * rs.standard_normal(m.num_features)).astype(np.float32)))
+            m.running_var.copy_(torch.from_numpy((0.5 + rs.rand(m.num_features)).astype(np.float32)))
+            m.weight.data.copy_(torch.from_numpy((1.0 + 0.2 * rs.standard_normal(m.num_features)).astype(np.float32)))
+            m.bias.data.copy_(torch.from_numpy((0.1 * rs.standard_normal(m.num_features)).astype(np.float32)))
+    B, T, H = int(g["B"]), int(g["T"]), int(g["H"])
+    x = torch.from_numpy(np.random.RandomState(int(g["seed_x"])).standard_normal((B, T, 3, H, H)).astype(np.float32))
+    out = ve(x).detach()                                            # grad enabled: the differentiable torch route, on the CPU
+    want = torch.from_numpy(g["out"])
+    assert out.shape == want.shape and (out - want).abs().max().item() <= 2e-5 * want.abs().max().item()
+    trunk = cm.DeviceVideoTrunk(ve)                                 # fp32 on the CPU until .to(cuda): the algebra, not the kernels
+    assert trunk.folded == 20 and trunk.fused == 9
+    xp = torch.zeros(B * T, trunk.cpad, H, H)
+    xp[:, :3] = x.view(B * T, 3, H, H)
+    with torch.no_grad():
+        fmap = trunk.net(xp)
+    assert tuple(fmap.shape) == tuple(int(v) for v in g["fmap_shape"])
+    fm = torch.from_numpy(g["frame_means"])
+    assert (fmap.mean(dim=(2, 3)) - fm).abs().max().item() <= 5e-5 * fm.abs().max().item()
+    # ... and the tail on that map (the reference's pool -> projection -> temporal mean, models.py:210-215)
+    tail = ve.projection(fmap.mean(dim=(2, 3)).view(B, T, -1)).mean(dim=1).detach()
+    assert (tail - want).abs().max().item() <= 5e-5 * want.abs().max().item()
