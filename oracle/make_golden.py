@@ -52,12 +52,12 @@ def _to_torch_sd(torch, sd):
     return {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
 
 
-def video_encoder_resnet18(torch, CONFIG, M):
-    """a4 WITH the reference's resnet18 trunk (src/models/models.py:163-167,208-216), random init: the module is constructed under
+def video_encoder_with_trunk(torch, CONFIG, M, backbone="resnet18"):
+    """a4 WITH the reference's CNN trunks (resnet18: src/models/models.py:163-167, mobilenet_v2: :169-173; tail :208-216), random init: the module is constructed under
     torch.manual_seed(seed_init) -- the tests construct theirs the same way, so no 45 MB state dict has to be stored -- and its
     BatchNorm statistics are randomised from a numpy stream.  Records the output and the per-frame spatial means of the trunk's map."""
     cfg = copy.deepcopy(CONFIG)
-    cfg.model.video_backbone = "resnet18"
+    cfg.model.video_backbone = backbone
     cfg.model.video_pretrained = False
     seed_init, seed_bn, seed_x, B, T, H = 1234, 71, 72, 2, 4, 64
     torch.manual_seed(seed_init)
@@ -73,9 +73,9 @@ def video_encoder_resnet18(torch, CONFIG, M):
     with torch.no_grad():
         out = ve(x)
         fmap = ve.backbone(x.view(B * T, 3, H, H))
-    np.savez_compressed(os.path.join(OUT, "video_encoder_resnet18.npz"), seed_init=seed_init, seed_bn=seed_bn, seed_x=seed_x, B=B, T=T, H=H,
+    np.savez_compressed(os.path.join(OUT, f"video_encoder_{backbone}.npz"), seed_init=seed_init, seed_bn=seed_bn, seed_x=seed_x, B=B, T=T, H=H,
                         out=out.numpy(), frame_means=fmap.mean(dim=(2, 3)).numpy(), fmap_shape=np.array(fmap.shape))
-    print(f"video_encoder_resnet18: out absmax {out.abs().max():.4f}, map {tuple(fmap.shape)}")
+    print(f"video_encoder_{backbone}: out absmax {out.abs().max():.4f}, map {tuple(fmap.shape)}")
 
 
 def main():
@@ -84,7 +84,9 @@ def main():
     torch, CONFIG, M, LS, EV = _import_reference()
     if "--only-trunk" in sys.argv:                          # add this fixture without rewriting the others
         os.makedirs(OUT, exist_ok=True)
-        return video_encoder_resnet18(torch, CONFIG, M)
+        for bb in ("resnet18", "mobilenet_v2"):
+            video_encoder_with_trunk(torch, CONFIG, M, bb)
+        return
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(OUT, exist_ok=True)
@@ -182,7 +184,8 @@ def main():
         metrics=np.array([res["metrics"][k] for k in sorted(res["metrics"])], dtype=np.float64),
         m2_seed=26, m2=np.array([m2[k] for k in sorted(m2)], dtype=np.float64))
     print("evaluator:", res["metrics"])
-    video_encoder_resnet18(torch, CONFIG, M)
+    for bb in ("resnet18", "mobilenet_v2"):
+        video_encoder_with_trunk(torch, CONFIG, M, bb)
     print("wrote", sorted(os.listdir(OUT)))
 
 

@@ -235,16 +235,17 @@ def test_pipeline_frames_need_an_attached_trunk():
         pipe._frame_buffer((2, 16, 3, 32, 32), "cuda:0", 0)
 
 
-def test_video_encoder_with_resnet18_trunk_vs_reference_golden(golden_dir):
-    """Row a4 WITH the reference's trunk (src/models/models.py:163-167,208-216): the golden holds the output of the UNMODIFIED reference
-    ``VideoEncoder`` constructed under a fixed torch seed (oracle/make_golden.py: video_encoder_resnet18).  This module built under the
+@pytest.mark.parametrize("backbone,folded,fused", [("resnet18", 20, 9), ("mobilenet_v2", 52, 0)])
+def test_video_encoder_with_cnn_trunk_vs_reference_golden(golden_dir, backbone, folded, fused):
+    """Row a4 WITH the reference's trunks (src/models/models.py:163-173,208-216): the golden holds the output of the UNMODIFIED reference
+    ``VideoEncoder`` constructed under a fixed torch seed (oracle/make_golden.py: video_encoder_with_trunk).  This module built under the
     same seed has the same parameters; its torch route (what the reference's trainers use) must give the reference's output, and the
     BatchNorm-folded, channel-padded, epilogue-fused trunk that DeviceVideoTrunk runs on the device must reproduce the reference
     trunk's map in fp32 (the bf16 device run is held to the eager trunk in the GPU test above)."""
     import os
-    g = np.load(os.path.join(golden_dir, "video_encoder_resnet18.npz"))
+    g = np.load(os.path.join(golden_dir, f"video_encoder_{backbone}.npz"))
     cfg = cm.default_config()
-    cfg.model.video_backbone, cfg.model.video_pretrained = "resnet18", False
+    cfg.model.video_backbone, cfg.model.video_pretrained = backbone, False
     torch.manual_seed(int(g["seed_init"]))
     ve = cm.VideoEncoder(cfg).eval()
     rs = np.random.RandomState(int(g["seed_bn"]))
@@ -260,7 +261,7 @@ def test_video_encoder_with_resnet18_trunk_vs_reference_golden(golden_dir):
     want = torch.from_numpy(g["out"])
     assert out.shape == want.shape and (out - want).abs().max().item() <= 2e-5 * want.abs().max().item()
     trunk = cm.DeviceVideoTrunk(ve)                                 # fp32 on the CPU until .to(cuda): the algebra, not the kernels
-    assert trunk.folded == 20 and trunk.fused == 9
+    assert trunk.folded == folded and trunk.fused == fused
     xp = torch.zeros(B * T, trunk.cpad, H, H)
     xp[:, :3] = x.view(B * T, 3, H, H)
     with torch.no_grad():
